@@ -1,0 +1,221 @@
+"""ctypes binding of the C ABI (include/gstar_raster.h) with torch tensors as device memory.
+
+This is the "reference-side binding" in Python form: what a maintainer of a Python host would write
+to call libgstar_raster.so directly (see INTEGRATION.md for the C++/pybind form that replaces
+DGR/rasterize_points.cu).  The parity tests and bench.py go through this module so that they
+exercise exactly the exported C symbols.  No compute happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgstar_raster.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+# every symbol declared in include/gstar_raster.h
+EXPORTED = [
+    "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
+    "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
+    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name",
+]
+STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
+
+
+class FwdArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int),
+        ("background", C.c_void_p), ("width", C.c_int), ("height", C.c_int),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+        ("scales", C.c_void_p), ("scale_modifier", C.c_float), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("cam_pos", C.c_void_p),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int),
+        ("out_color", C.c_void_p), ("radii", C.c_void_p), ("debug", C.c_int),
+    ]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int),
+        ("background", C.c_void_p), ("width", C.c_int), ("height", C.c_int),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("scales", C.c_void_p),
+        ("scale_modifier", C.c_float), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("radii", C.c_void_p), ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("image_buffer", C.c_void_p),
+        ("dL_dpix", C.c_void_p),
+        ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dcolor", C.c_void_p),
+        ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
+        ("dL_drot", C.c_void_p), ("blend_grad_scratch", C.c_void_p), ("debug", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libgstar_raster.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built; run `python -m gaustar_b200.build`")
+        L = C.CDLL(LIB_PATH)
+        L.gstar_last_error.restype = C.c_char_p
+        L.gstar_stage_name.restype = C.c_char_p
+        L.gstar_stage_name.argtypes = [C.c_int]
+        for n in ("gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes"):
+            getattr(L, n).restype = C.c_size_t
+        L.gstar_geom_bytes.argtypes = [C.c_int]
+        L.gstar_image_bytes.argtypes = [C.c_int, C.c_int]
+        L.gstar_binning_bytes.argtypes = [C.c_size_t]
+        L.gstar_raster_forward.argtypes = [C.POINTER(FwdArgs), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p]
+        L.gstar_raster_backward.argtypes = [C.POINTER(BwdArgs), C.c_void_p]
+        L.gstar_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gstar_geom_unpack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.gstar_image_views.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.gstar_binning_views.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.gstar_profile_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class GstarError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc < 0:
+        raise GstarError(f"gstar error {rc}: {lib().gstar_last_error().decode()}")
+    return rc
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
+
+
+def _f32(t, dev):
+    if t is None:
+        return None
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _Resizable:
+    """A torch uint8 tensor grown through the gstar_alloc_fn callback (cf. resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, dev):
+        self.t = torch.empty(0, dtype=torch.uint8, device=dev)
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        self.t.resize_(int(nbytes))
+        return self.t.data_ptr()
+
+
+def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, W, H, shs=None, colors_precomp=None,
+            scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, prefiltered=False, debug=False):
+    """gstar_raster_forward.  Returns dict(num_rendered, out_color, radii, geom, binning, image)."""
+    L = lib()
+    dev = means3D.device
+    assert dev.type == "cuda", "gaustar_b200 has no CPU path"
+    keep = [_f32(x, dev) for x in (means3D, opacities, viewmatrix, projmatrix, campos, bg, shs, colors_precomp, scales, rotations, cov3D_precomp)]
+    m3, op, vm, pm, cp, bgc, sh, col, sc, rot, cov = keep
+    P = m3.shape[0]
+    M = 0 if sh is None or sh.numel() == 0 else sh.shape[1]
+    out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    geom, binning, image = _Resizable(dev), _Resizable(dev), _Resizable(dev)
+    a = FwdArgs(P, sh_degree, M, _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(op), _ptr(sc), scale_modifier, _ptr(rot), _ptr(cov),
+                _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, int(prefiltered), _ptr(out_color), _ptr(radii), int(debug))
+    with torch.cuda.device(dev):
+        R = _check(L.gstar_raster_forward(C.byref(a), geom.cb, None, binning.cb, None, image.cb, None, _stream(dev)))
+    if P == 0:
+        out_color.zero_()
+    return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom.t, binning=binning.t, image=image.t, _keep=keep)
+
+
+def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,
+             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False):
+    """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts)."""
+    L = lib()
+    dev = means3D.device
+    keep = [_f32(x, dev) for x in (means3D, viewmatrix, projmatrix, campos, bg, shs, colors_precomp, scales, rotations, cov3D_precomp, dL_dout_color)]
+    m3, vm, pm, cp, bgc, sh, col, sc, rot, cov, dpix = keep
+    P = m3.shape[0]
+    M = 0 if sh is None or sh.numel() == 0 else sh.shape[1]
+    H, W = dpix.shape[1], dpix.shape[2]
+    e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    g = dict(dL_dmeans2D=e(P, 3), dL_dconic=e(P, 4), dL_dopacity=e(P, 1), dL_dcolors=e(P, 3), dL_dmeans3D=e(P, 3), dL_dcov3D=e(P, 6),
+             dL_dsh=e(P, M, 3), dL_dscales=e(P, 3), dL_drotations=e(P, 4))
+    scratch = torch.zeros(P, 12, dtype=torch.float32, device=dev)
+    a = BwdArgs(P, sh_degree, M, int(fwd["num_rendered"]), _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(sc), scale_modifier, _ptr(rot),
+                _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]), _ptr(fwd["binning"]),
+                _ptr(fwd["image"]), _ptr(dpix), _ptr(g["dL_dmeans2D"]), _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolors"]),
+                _ptr(g["dL_dmeans3D"]), _ptr(g["dL_dcov3D"]), _ptr(g["dL_dsh"]), _ptr(g["dL_dscales"]), _ptr(g["dL_drotations"]),
+                _ptr(scratch), int(debug))
+    with torch.cuda.device(dev):
+        _check(L.gstar_raster_backward(C.byref(a), _stream(dev)))
+    g["_keep"] = keep + [scratch]
+    return g
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    dev = means3D.device
+    m3, vm, pm = _f32(means3D, dev), _f32(viewmatrix, dev), _f32(projmatrix, dev)
+    present = torch.zeros(m3.shape[0], dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().gstar_mark_visible(m3.shape[0], _ptr(m3), _ptr(vm), _ptr(pm), _ptr(present), _stream(dev)))
+    return present
+
+
+def unpack_geometry(fwd, P):
+    """Per-Gaussian intermediates in the reference's GeometryState layouts (rasterizer_impl.h:33-47)."""
+    dev = fwd["geom"].device
+    out = dict(depths=torch.zeros(P, device=dev), means2D=torch.zeros(P, 2, device=dev), conic_opacity=torch.zeros(P, 4, device=dev),
+               rgb=torch.zeros(P, 3, device=dev), tiles_touched=torch.zeros(P, dtype=torch.int32, device=dev),
+               clamped=torch.zeros(P, 3, dtype=torch.uint8, device=dev))
+    with torch.cuda.device(dev):
+        _check(lib().gstar_geom_unpack(_ptr(fwd["geom"]), P, _ptr(out["depths"]), _ptr(out["means2D"]), _ptr(out["conic_opacity"]),
+                                       _ptr(out["rgb"]), _ptr(out["tiles_touched"]), _ptr(out["clamped"]), _stream(dev)))
+    return out
+
+
+def _view(base: torch.Tensor, addr: int, nbytes: int, dtype):
+    off = addr - base.data_ptr()
+    return base[off:off + nbytes].view(dtype)
+
+
+def image_state(fwd, W, H):
+    """final_T[H*W], n_contrib[H*W] (int32 view of uint32), ranges[T,2] -- views into the image buffer."""
+    ft, nc, rg = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _check(lib().gstar_image_views(_ptr(fwd["image"]), W, H, C.byref(ft), C.byref(nc), C.byref(rg)))
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    img = fwd["image"]
+    return dict(final_T=_view(img, ft.value, W * H * 4, torch.float32), n_contrib=_view(img, nc.value, W * H * 4, torch.int32),
+                ranges=_view(img, rg.value, T * 8, torch.int32).view(T, 2))
+
+
+def point_list(fwd):
+    """Sorted instance list (BinningState::point_list): int32 view of the first num_rendered entries."""
+    R = int(fwd["num_rendered"])
+    if R == 0:
+        return torch.zeros(0, dtype=torch.int32, device=fwd["geom"].device)
+    pl = C.c_void_p()
+    cap = C.c_uint64()
+    _check(lib().gstar_binning_views(_ptr(fwd["binning"]), C.byref(pl), C.byref(cap)))
+    return _view(fwd["binning"], pl.value, R * 4, torch.int32)
+
+
+def profile_stage(stage: int, start: Optional[torch.cuda.Event] = None, stop: Optional[torch.cuda.Event] = None):
+    """Record start/stop around kernel stage `stage` of every later call on this thread (stage < 0: off)."""
+    s = C.c_void_p(start.cuda_event) if start is not None else None
+    e = C.c_void_p(stop.cuda_event) if stop is not None else None
+    _check(lib().gstar_profile_stage(stage, s, e))

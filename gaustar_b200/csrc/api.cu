@@ -1,0 +1,384 @@
+// api.cu -- the C ABI of libgstar_raster.so (include/gstar_raster.h): orchestration only.
+//
+// Forward pipeline (replaces CudaRasterizer::Rasterizer::forward, rasterizer_impl.cu:198-336):
+//   memset(tile histogram) -> K1 preprocess_fwd -> K2 tile_scan -> K3 emit -> K4 tile_sort -> K6 blend_fwd
+// The reference blocks the host on a D2H copy of num_rendered right after its prefix sum
+// (rasterizer_impl.cu:281) and only then sizes the binning buffer.  Here the binning buffer is
+// provisioned from the previous call's instance count, K2 publishes R and an overflow flag through
+// mapped pinned memory, all remaining kernels are enqueued immediately, and the host waits on an
+// event recorded right behind K2 only AFTER it has enqueued everything -- the GPU never idles, and
+// the exact R is still returned.  If R exceeded the provision (rare) the kernels behind K2 no-op'd
+// on the device flag and binning + blend are re-enqueued with an exact-size buffer.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/gstar_raster.h"
+#include "gstar_common.cuh"
+#include "gstar_kernels.h"
+
+namespace {
+
+thread_local std::string t_err;
+
+int fail(int code, const std::string& msg)
+{
+    t_err = msg;
+    return code;
+}
+
+#define CU_OK(expr)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return fail(GSTAR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int MAX_DEV = 64;
+struct DevCtx {
+    bool inited = false;
+    uint32_t* host_counts = nullptr;  // pinned + mapped: [0]=R [1]=overflow [2]=max tile
+    uint32_t* host_counts_dev = nullptr;
+    cudaEvent_t scan_done = nullptr;
+    double estimate = 0.0;  // running provision for R
+    bool have_estimate = false;
+};
+thread_local DevCtx t_ctx[MAX_DEV];
+
+struct Profile {
+    int stage = -1;
+    cudaEvent_t start = nullptr, stop = nullptr;
+};
+thread_local Profile t_prof;
+
+struct StageScope {
+    int stage;
+    cudaStream_t s;
+    StageScope(int st, cudaStream_t stream) : stage(st), s(stream)
+    {
+        if (t_prof.stage == stage && t_prof.start) cudaEventRecord(t_prof.start, s);
+    }
+    ~StageScope()
+    {
+        if (t_prof.stage == stage && t_prof.stop) cudaEventRecord(t_prof.stop, s);
+    }
+};
+
+int get_ctx(DevCtx** out)
+{
+    int dev = 0;
+    CU_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return fail(GSTAR_ERR_INVALID, "device index out of range");
+    DevCtx& c = t_ctx[dev];
+    if (!c.inited) {
+        CU_OK(cudaHostAlloc((void**)&c.host_counts, 64, cudaHostAllocMapped));
+        memset(c.host_counts, 0, 64);
+        CU_OK(cudaHostGetDevicePointer((void**)&c.host_counts_dev, c.host_counts, 0));
+        CU_OK(cudaEventCreateWithFlags(&c.scan_done, cudaEventDisableTiming));
+        CU_OK((cudaError_t)gstar::tile_sort_setup());
+        c.inited = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+// ---- private layouts of the three opaque buffers ----
+struct ImgLayout {
+    size_t hdr, final_T, n_contrib, ranges, tile_count, tile_cursor, big_tiles, total;
+};
+ImgLayout img_layout(int W, int H)
+{
+    const size_t npix = (size_t)W * H;
+    const size_t T = (size_t)((W + GSTAR_TILE - 1) / GSTAR_TILE) * ((H + GSTAR_TILE - 1) / GSTAR_TILE);
+    ImgLayout L;
+    size_t o = 0;
+    L.hdr = o; o = align_up(o + sizeof(GHeader), 128);
+    L.final_T = o; o = align_up(o + npix * 4, 128);
+    L.n_contrib = o; o = align_up(o + npix * 4, 128);
+    L.ranges = o; o = align_up(o + T * 8, 128);
+    L.tile_count = o; o = align_up(o + T * 4, 128);
+    L.tile_cursor = o; o = align_up(o + T * 4, 128);
+    L.big_tiles = o; o = align_up(o + T * 4, 128);
+    L.total = o;
+    return L;
+}
+struct BinLayout {
+    size_t point_list, entries, total;
+};
+BinLayout bin_layout(size_t cap)
+{
+    BinLayout L;
+    L.point_list = 0;  // first, so that backward needs no capacity to find it
+    L.entries = align_up(cap * 4, 128);
+    L.total = align_up(L.entries + cap * 8, 128);
+    return L;
+}
+
+int debug_sync(int debug, const char* what)
+{
+    if (!debug) {
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return 0;
+    }
+    cudaError_t e = cudaDeviceSynchronize();  // auxiliary.h:166-173 CHECK_CUDA
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, std::string("[CUDA ERROR] in ") + what + ": " + cudaGetErrorString(e));
+    return 0;
+}
+#define STAGE_CHECK(what)                        \
+    do {                                         \
+        int rc_ = debug_sync(a->debug, what);    \
+        if (rc_ < 0) return rc_;                 \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char* gstar_last_error(void) { return t_err.c_str(); }
+int gstar_abi_version(void) { return GSTAR_ABI_VERSION; }
+
+size_t gstar_geom_bytes(int P) { return align_up((size_t)std::max(P, 0) * sizeof(GRec), 128) + 128; }
+size_t gstar_image_bytes(int width, int height) { return img_layout(width, height).total + 128; }
+size_t gstar_binning_bytes(size_t cap) { return bin_layout(cap).total + 128; }
+
+const char* gstar_stage_name(int stage)
+{
+    static const char* names[GSTAR_NUM_STAGES] = {"preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"};
+    return (stage >= 0 && stage < GSTAR_NUM_STAGES) ? names[stage] : "";
+}
+
+int gstar_profile_stage(int stage, void* start_event, void* stop_event)
+{
+    t_prof.stage = stage;
+    t_prof.start = (cudaEvent_t)start_event;
+    t_prof.stop = (cudaEvent_t)stop_event;
+    return 0;
+}
+
+static inline char* aligned128(char* p) { return (char*)align_up((size_t)p, 128); }
+
+int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, void* geom_user, gstar_alloc_fn binning_alloc,
+                         void* binning_user, gstar_alloc_fn image_alloc, void* image_user, void* stream_)
+{
+    using namespace gstar;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || !geom_alloc || !binning_alloc || !image_alloc) return fail(GSTAR_ERR_INVALID, "null argument");
+    if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(GSTAR_ERR_INVALID, "bad sizes");
+    if (a->P == 0) return 0;
+    if (!a->colors_precomp && !a->shs) return fail(GSTAR_ERR_NONRGB, "For non-RGB, provide precomputed Gaussian colors!");
+    if (!a->cov3D_precomp && (!a->scales || !a->rotations))
+        return fail(GSTAR_ERR_INVALID, "provide scales+rotations or cov3D_precomp");
+    if (a->width > 32767 || a->height > 32767) return fail(GSTAR_ERR_INVALID, "image larger than 32767 pixels");
+    DevCtx* ctx;
+    int rc = get_ctx(&ctx);
+    if (rc < 0) return rc;
+
+    const int W = a->width, H = a->height;
+    const int gx = (W + GSTAR_TILE - 1) / GSTAR_TILE, gy = (H + GSTAR_TILE - 1) / GSTAR_TILE;
+    const int T = gx * gy;
+    char* geom = geom_alloc(geom_user, gstar_geom_bytes(a->P));
+    char* img = image_alloc(image_user, gstar_image_bytes(W, H));
+    if (!geom || !img) return fail(GSTAR_ERR_ALLOC, "buffer callback returned NULL");
+    geom = aligned128(geom);
+    img = aligned128(img);
+    const ImgLayout IL = img_layout(W, H);
+    GHeader* hdr = (GHeader*)(img + IL.hdr);
+    uint32_t* tile_count = (uint32_t*)(img + IL.tile_count);
+
+    CU_OK(cudaMemsetAsync(tile_count, 0, (size_t)T * 4, stream));
+
+    PreFwdParams pp;
+    pp.P = a->P; pp.D = a->D; pp.M = a->M; pp.W = W; pp.H = H; pp.gx = gx; pp.gy = gy;
+    pp.means3D = a->means3D; pp.scales = a->scales; pp.scale_modifier = a->scale_modifier; pp.rotations = a->rotations;
+    pp.opacities = a->opacities; pp.shs = a->shs; pp.cov3D_precomp = a->cov3D_precomp; pp.colors_precomp = a->colors_precomp;
+    pp.viewmatrix = a->viewmatrix; pp.projmatrix = a->projmatrix; pp.campos = a->cam_pos;
+    pp.tan_fovx = a->tan_fovx; pp.tan_fovy = a->tan_fovy;
+    pp.focal_y = H / (2.0f * a->tan_fovy);  // rasterizer_impl.cu:222-223
+    pp.focal_x = W / (2.0f * a->tan_fovx);
+    pp.prefiltered = a->prefiltered;
+    pp.recs = (GRec*)geom; pp.radii = a->radii; pp.tile_count = tile_count;
+    {
+        StageScope sc(GSTAR_STAGE_PREPROCESS_FWD, stream);
+        launch_preprocess_fwd(pp, stream);
+    }
+    STAGE_CHECK("preprocess_fwd");
+
+    BinParams bp;
+    bp.P = a->P; bp.gx = gx; bp.gy = gy; bp.num_tiles = T;
+    bp.recs = (const GRec*)geom; bp.hdr = hdr; bp.tile_count = tile_count;
+    bp.tile_cursor = (uint32_t*)(img + IL.tile_cursor);
+    bp.ranges = (uint32_t*)(img + IL.ranges);
+    bp.big_tiles = (uint32_t*)(img + IL.big_tiles);
+    bp.host_counts = ctx->host_counts_dev;
+
+    BlendParams bl;
+    bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
+    bl.recs = (const GRec*)geom; bl.hdr = hdr; bl.ranges = bp.ranges; bl.bg = a->background;
+    bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
+    bl.dL_dpix = nullptr; bl.gacc = nullptr;
+
+    size_t cap = ctx->have_estimate ? (size_t)ctx->estimate : 0;
+    uint32_t R = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        char* bin = nullptr;
+        if (cap > 0) {
+            if (cap > 0xfffffff0ull) return fail(GSTAR_ERR_INVALID, "more than 2^32 instances");
+            bin = binning_alloc(binning_user, gstar_binning_bytes(cap));
+            if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
+            bin = aligned128(bin);
+        }
+        const BinLayout BL = bin_layout(cap);
+        bp.capacity = (uint32_t)cap;
+        bp.point_list = bin ? (uint32_t*)(bin + BL.point_list) : nullptr;
+        bp.entries = bin ? (uint2*)(bin + BL.entries) : nullptr;
+        bl.point_list = bp.point_list;
+        {
+            StageScope sc(GSTAR_STAGE_TILE_SCAN, stream);
+            launch_tile_scan(bp, stream);
+        }
+        CU_OK(cudaEventRecord(ctx->scan_done, stream));
+        STAGE_CHECK("tile_scan");
+        if (cap > 0) {
+            {
+                StageScope sc(GSTAR_STAGE_EMIT, stream);
+                launch_emit(bp, stream);
+            }
+            STAGE_CHECK("emit");
+            {
+                StageScope sc(GSTAR_STAGE_TILE_SORT, stream);
+                launch_tile_sort(bp, stream);
+            }
+            STAGE_CHECK("tile_sort");
+            {
+                StageScope sc(GSTAR_STAGE_BLEND_FWD, stream);
+                launch_blend_fwd(bl, stream);
+            }
+            STAGE_CHECK("blend_fwd");
+        }
+        // everything is enqueued; only now wait for the scan result (the GPU keeps working)
+        CU_OK(cudaEventSynchronize(ctx->scan_done));
+        R = ctx->host_counts[0];
+        const bool overflow = R > cap;
+        // provision for the next call: 25% headroom over a slowly decaying high-water mark
+        ctx->estimate = std::max(ctx->estimate * 0.98, (double)R * 1.25 + 65536.0);
+        ctx->have_estimate = true;
+        if (!overflow) break;
+        if (attempt == 1) return fail(GSTAR_ERR_INVALID, "instance count changed between attempts");
+        cap = (size_t)R;  // exact size; tile_scan reruns to reset cursors and the device flag
+    }
+    if (R == 0) {
+        // no instance anywhere: the image is the background. (with cap == 0 no blend was launched)
+        if (cap == 0) {
+            // cheapest correct path: run blend with empty ranges
+            char* bin = binning_alloc(binning_user, gstar_binning_bytes(1));
+            if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
+            bl.point_list = (uint32_t*)aligned128(bin);
+            bp.capacity = 1;
+            launch_tile_scan(bp, stream);
+            launch_blend_fwd(bl, stream);
+            STAGE_CHECK("blend_fwd(empty)");
+        }
+    }
+    return (int)R;
+}
+
+int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
+{
+    using namespace gstar;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a) return fail(GSTAR_ERR_INVALID, "null argument");
+    if (a->P == 0) return 0;
+    if (!a->geom_buffer || !a->image_buffer || !a->blend_grad_scratch || !a->dL_dpix)
+        return fail(GSTAR_ERR_INVALID, "missing buffer");
+    if (a->R > 0 && !a->binning_buffer) return fail(GSTAR_ERR_INVALID, "missing binning buffer");
+    const int W = a->width, H = a->height;
+    const int gx = (W + GSTAR_TILE - 1) / GSTAR_TILE, gy = (H + GSTAR_TILE - 1) / GSTAR_TILE;
+    char* geom = aligned128(a->geom_buffer);
+    char* img = aligned128(a->image_buffer);
+    const ImgLayout IL = img_layout(W, H);
+
+    if (a->R > 0) {
+        BlendParams bl;
+        bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
+        bl.recs = (const GRec*)geom; bl.hdr = (const GHeader*)(img + IL.hdr);
+        bl.ranges = (const uint32_t*)(img + IL.ranges);
+        bl.point_list = (const uint32_t*)aligned128(a->binning_buffer);
+        bl.bg = a->background;
+        bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
+        bl.dL_dpix = a->dL_dpix; bl.gacc = a->blend_grad_scratch;
+        {
+            StageScope sc(GSTAR_STAGE_BLEND_BWD, stream);
+            launch_blend_bwd(bl, stream);
+        }
+        STAGE_CHECK("blend_bwd");
+    }
+    PreBwdParams pb;
+    pb.P = a->P; pb.D = a->D; pb.M = a->M; pb.W = W; pb.H = H;
+    pb.means3D = a->means3D; pb.scales = a->scales; pb.scale_modifier = a->scale_modifier; pb.rotations = a->rotations;
+    pb.shs = a->shs; pb.cov3D_precomp = a->cov3D_precomp; pb.viewmatrix = a->viewmatrix; pb.projmatrix = a->projmatrix;
+    pb.campos = a->campos; pb.tan_fovx = a->tan_fovx; pb.tan_fovy = a->tan_fovy;
+    pb.focal_y = H / (2.0f * a->tan_fovy);
+    pb.focal_x = W / (2.0f * a->tan_fovx);
+    pb.radii = a->radii; pb.recs = (const GRec*)geom; pb.gacc = a->blend_grad_scratch;
+    pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;
+    pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = (a->M > 0) ? a->dL_dsh : nullptr;
+    pb.dL_dscale = a->dL_dscale; pb.dL_drot = a->dL_drot;
+    if (!pb.dL_dmean2D || !pb.dL_dopacity || !pb.dL_dcolor || !pb.dL_dmean3D || !pb.dL_dcov3D)
+        return fail(GSTAR_ERR_INVALID, "missing gradient output");
+    if (a->shs && a->M > 0 && !a->dL_dsh) return fail(GSTAR_ERR_INVALID, "missing dL_dsh");
+    {
+        StageScope sc(GSTAR_STAGE_PREPROCESS_BWD, stream);
+        launch_preprocess_bwd(pb, stream);
+    }
+    STAGE_CHECK("preprocess_bwd");
+    return 0;
+}
+
+int gstar_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, unsigned char* present, void* stream)
+{
+    (void)projmatrix;  // the reference computes p_proj but only tests view z (auxiliary.h:154)
+    if (P <= 0) return 0;
+    if (!means3D || !viewmatrix || !present) return fail(GSTAR_ERR_INVALID, "null argument");
+    gstar::launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+int gstar_geom_unpack(const char* geom_buffer, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
+                      unsigned char* clamped, void* stream)
+{
+    if (P <= 0) return 0;
+    if (!geom_buffer) return fail(GSTAR_ERR_INVALID, "null geometry buffer");
+    gstar::launch_geom_unpack((const GRec*)aligned128((char*)geom_buffer), P, depths, means2D, conic_opacity, rgb, tiles_touched, clamped,
+                              (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+int gstar_image_views(char* image_buffer, int width, int height, float** final_T, uint32_t** n_contrib, uint32_t** ranges)
+{
+    if (!image_buffer) return fail(GSTAR_ERR_INVALID, "null image buffer");
+    char* img = aligned128(image_buffer);
+    const ImgLayout IL = img_layout(width, height);
+    if (final_T) *final_T = (float*)(img + IL.final_T);
+    if (n_contrib) *n_contrib = (uint32_t*)(img + IL.n_contrib);
+    if (ranges) *ranges = (uint32_t*)(img + IL.ranges);
+    return 0;
+}
+
+int gstar_binning_views(char* binning_buffer, uint32_t** point_list, uint64_t* capacity)
+{
+    if (!binning_buffer) return fail(GSTAR_ERR_INVALID, "null binning buffer");
+    if (point_list) *point_list = (uint32_t*)aligned128(binning_buffer);
+    if (capacity) *capacity = 0;
+    return 0;
+}
+
+}  // extern "C"

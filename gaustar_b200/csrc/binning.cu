@@ -1,0 +1,218 @@
+// binning.cu -- tile binning: K2 tile_scan, K3 emit, K4 tile_sort (+ big-tile variant).
+//
+// Replaces, with an MSD formulation of the same 64-bit tile|depth key sort,
+//   cub::DeviceScan::InclusiveSum      rasterizer_impl.cu:277
+//   duplicateWithKeys                  rasterizer_impl.cu:70-111
+//   cub::DeviceRadixSort::SortPairs    rasterizer_impl.cu:303-308
+//   identifyTileRanges                 rasterizer_impl.cu:116-138
+// The reference sorts (tile<<32 | depth_bits) with a stable LSD radix sort whose input is
+// Gaussian-index ordered, i.e. its output order is (tile, depth_bits, gaussian index).  Here the
+// high digit (tile id) is resolved first by a counting sort over tiles -- the histogram comes out of
+// preprocess_fwd, this file scans it (ranges[] falls out of the scan for free) and scatters
+// (depth, idx) pairs into per-tile segments -- and each segment is then sorted on the remaining
+// (depth_bits, idx) 64-bit key inside shared memory by one CTA.  The concatenation of the sorted
+// segments is bit-identical to the reference's sorted list.
+#include "gstar_common.cuh"
+#include "gstar_kernels.h"
+
+namespace gstar {
+
+constexpr int SCAN_THREADS = 1024;
+constexpr uint32_t SORT_SMALL_CAP = 4096;          // keys (32 KB) handled by the 256-thread kernel
+constexpr uint32_t SORT_BIG_CAP = 24576;           // keys (192 KB) handled in shared memory by the big kernel
+constexpr int SORT_BIG_THREADS = 1024;
+
+// ---- K2: exclusive scan over the per-tile histogram; one CTA --------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
+{
+    __shared__ uint32_t s_part[SCAN_THREADS];
+    __shared__ uint32_t s_nbig, s_max;
+    const int tid = threadIdx.x;
+    const int T = p.num_tiles;
+    const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int t0 = tid * per, t1 = min(T, t0 + per);
+    if (tid == 0) { s_nbig = 0; s_max = 0; }
+    uint32_t sum = 0, mx = 0;
+    for (int t = t0; t < t1; t++) { const uint32_t c = p.tile_count[t]; sum += c; mx = max(mx, c); }
+    s_part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan of 1024 partials
+    for (int off = 1; off < SCAN_THREADS; off <<= 1) {
+        uint32_t v = 0;
+        if (tid >= off) v = s_part[tid - off];
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;  // exclusive prefix of this thread's chunk
+    atomicMax(&s_max, mx);
+    for (int t = t0; t < t1; t++) {
+        const uint32_t c = p.tile_count[t];
+        p.tile_cursor[t] = run;
+        // identifyTileRanges leaves untouched tiles at the memset value (0,0): rasterizer_impl.cu:310
+        p.ranges[2 * t] = c ? run : 0u;
+        p.ranges[2 * t + 1] = c ? run + c : 0u;
+        if (c > SORT_SMALL_CAP) p.big_tiles[atomicAdd(&s_nbig, 1u)] = (uint32_t)t;
+        run += c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t total = s_part[SCAN_THREADS - 1];
+        const uint32_t ovf = total > p.capacity ? 1u : 0u;
+        p.hdr->num_rendered = total;
+        p.hdr->capacity = p.capacity;
+        p.hdr->overflow = ovf;
+        p.hdr->n_big = s_nbig;
+        p.hdr->big_cursor = 0;
+        p.hdr->max_tile = s_max;
+        if (p.host_counts) {  // zero-copy write of R to pinned host memory: no separate D2H memcpy
+            p.host_counts[1] = ovf;
+            p.host_counts[2] = s_max;
+            __threadfence_system();
+            p.host_counts[0] = total;
+        }
+    }
+}
+
+// ---- K3: scatter (idx, depth) into the tile segments ---------------------------------------------
+__global__ void __launch_bounds__(256) k_emit(BinParams p)
+{
+    if (p.hdr->overflow) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool vis = false;
+    uint32_t minx = 0, miny = 0, w = 0, h = 0, dbits = 0;
+    if (idx < p.P) {
+        // last 16 bytes of the record: depth, rect_min, rect_max, radius
+        const uint4 q = *(reinterpret_cast<const uint4*>(p.recs + idx) + 3);
+        vis = (int)q.w > 0;
+        dbits = q.x;
+        minx = q.y & 0xffffu; miny = q.y >> 16;
+        w = (q.z & 0xffffu) - minx; h = (q.z >> 16) - miny;
+    }
+    uint32_t* cur = p.tile_cursor;
+    uint2* ent = p.entries;
+    const int gx = p.gx;
+    const unsigned lane = threadIdx.x & 31;
+    // small rects: every lane scatters its own <=4 instances
+    if (vis && w * h <= 4) {
+        for (uint32_t t = 0; t < w * h; t++) {
+            const uint32_t tile = (miny + t / w) * gx + (minx + t % w);
+            const uint32_t slot = atomicAdd(cur + tile, 1u);
+            ent[slot] = make_uint2((uint32_t)idx, dbits);
+        }
+    }
+    // large rects: the whole warp drains one Gaussian's rect at a time (warp-cooperative emission)
+    unsigned big = __ballot_sync(0xffffffffu, vis && w * h > 4);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t bx = __shfl_sync(0xffffffffu, minx, src), by = __shfl_sync(0xffffffffu, miny, src);
+        const uint32_t bw = __shfl_sync(0xffffffffu, w, src), ba = bw * __shfl_sync(0xffffffffu, h, src);
+        const uint32_t bd = __shfl_sync(0xffffffffu, dbits, src);
+        const uint32_t bi = (uint32_t)__shfl_sync(0xffffffffu, idx, src);
+        for (uint32_t t = lane; t < ba; t += 32) {
+            const uint32_t tile = (by + t / bw) * gx + (bx + t % bw);
+            const uint32_t slot = atomicAdd(cur + tile, 1u);
+            ent[slot] = make_uint2(bi, bd);
+        }
+    }
+}
+
+// ---- K4: per-tile sort of (depth_bits<<32 | idx) ----------------------------------------------------
+// Bitonic network in its "flip/disperse" form: every compare-exchange is ascending, so the virtual
+// +inf padding up to the next power of two never moves and out-of-range partners are simply skipped.
+__device__ __forceinline__ void cmpxchg(uint64_t* a, uint32_t i, uint32_t l)
+{
+    const uint64_t x = a[i], y = a[l];
+    if (x > y) { a[i] = y; a[l] = x; }
+}
+
+__device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, uint32_t tid, uint32_t nthreads)
+{
+    if (n < 2) return;
+    uint32_t npad = 1;
+    while (npad < n) npad <<= 1;
+    const uint32_t pairs = npad >> 1;
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+        const uint32_t half = k >> 1;
+        const uint32_t hshift = 31 - __clz(half);
+        for (uint32_t t = tid; t < pairs; t += nthreads) {
+            const uint32_t blk = t >> hshift, off = t & (half - 1);
+            const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+            if (l < n) cmpxchg(a, i, l);
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            const uint32_t jshift = 31 - __clz(j);
+            for (uint32_t t = tid; t < pairs; t += nthreads) {
+                const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
+                if (l < n) cmpxchg(a, i, l);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tile_sort(BinParams p)
+{
+    __shared__ uint64_t s_keys[SORT_SMALL_CAP];
+    if (p.hdr->overflow) return;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
+    const uint32_t n = end - start;
+    if (n == 0 || n > SORT_SMALL_CAP) return;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(p.entries) + start;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = src[i];
+    __syncthreads();
+    bitonic_sort(s_keys, n, threadIdx.x, blockDim.x);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)s_keys[i];
+}
+
+// Long tile lists: persistent CTAs with ~192 KB of shared memory pull tiles from the work list; a list
+// that does not even fit there is sorted in place in global memory (L2-resident) by the same network.
+__global__ void __launch_bounds__(SORT_BIG_THREADS) k_tile_sort_big(BinParams p)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);
+    __shared__ uint32_t s_work;
+    if (p.hdr->overflow) return;
+    const uint32_t n_big = p.hdr->n_big;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_work = atomicAdd(&p.hdr->big_cursor, 1u);
+        __syncthreads();
+        const uint32_t wi = s_work;
+        if (wi >= n_big) break;
+        const uint32_t tile = p.big_tiles[wi];
+        const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
+        const uint32_t n = end - start;
+        uint64_t* g = reinterpret_cast<uint64_t*>(p.entries) + start;
+        if (n <= SORT_BIG_CAP) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = g[i];
+            __syncthreads();
+            bitonic_sort(s_keys, n, threadIdx.x, blockDim.x);
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)s_keys[i];
+        } else {
+            bitonic_sort(g, n, threadIdx.x, blockDim.x);
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)g[i];
+        }
+    }
+}
+
+int tile_sort_setup()
+{
+    return (int)cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_BIG_CAP * sizeof(uint64_t)));
+}
+
+void launch_tile_scan(const BinParams& p, cudaStream_t s) { k_tile_scan<<<1, SCAN_THREADS, 0, s>>>(p); }
+void launch_emit(const BinParams& p, cudaStream_t s) { k_emit<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
+void launch_tile_sort(const BinParams& p, cudaStream_t s)
+{
+    k_tile_sort<<<p.num_tiles, 256, 0, s>>>(p);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    k_tile_sort_big<<<sms, SORT_BIG_THREADS, SORT_BIG_CAP * sizeof(uint64_t), s>>>(p);
+}
+
+}  // namespace gstar

@@ -1,0 +1,98 @@
+// gstar_common.cuh -- shared device-side definitions for the sm_100a surface-Gaussian rasterizer.
+//
+// Data layout in HBM:
+//   GRec[P]       64-byte packed per-Gaussian record written by preprocess_fwd and gathered
+//                 (first 48 bytes, one cp.async.bulk each) by the blend kernels.
+//   entries[R]    unsorted per-tile segments of (depth bits, gaussian idx) pairs.
+//   point_list[R] per-tile depth-sorted gaussian indices == the reference's sorted value list
+//                 (DGR/cuda_rasterizer/rasterizer_impl.cu:303-308).
+//   ranges[T]     [start,end) of every tile in point_list (rasterizer_impl.cu:116-138).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GSTAR_TILE 16          // DGR/cuda_rasterizer/config.h:16-17 (BLOCK_X, BLOCK_Y)
+#define GSTAR_BATCH 256        // records staged in shared memory per pipeline stage
+#define GSTAR_REC_BYTES 64     // stride of GRec in HBM
+#define GSTAR_REC_SMEM 48      // bytes of a record the blend kernels need (bulk-copied)
+#define GSTAR_GACC 12          // floats per Gaussian in the blend-gradient accumulator
+
+struct __align__(16) GRec {
+    float x, y;        // pixel centre (means2D)            forward.cu:233,252
+    float A, B;        // conic.x, conic.y                  forward.cu:223
+    float C, o;        // conic.z, opacity                  forward.cu:254
+    float r, g;        // colour (SH result or colors_precomp)
+    uint32_t bbox_x;   // int16 xmin | int16 xmax << 16 : exact-conservative alpha>=1/255 pixel bounds
+    uint32_t bbox_y;   // int16 ymin | int16 ymax << 16
+    float b;           // colour, third channel
+    uint32_t flags;    // bit0..2: SH clamp mask (forward.cu:67-69)
+    float depth;       // view-space z                      forward.cu:250
+    uint32_t rect_min; // tile rect min x | y << 16         auxiliary.h:46-56
+    uint32_t rect_max; // tile rect max x | y << 16 (exclusive)
+    int32_t radius;    // forward.cu:251 (0 = culled)
+};
+static_assert(sizeof(GRec) == GSTAR_REC_BYTES, "GRec must be 64 bytes");
+
+// Small header kept at the start of the image buffer (device) -- counters of one forward call.
+struct GHeader {
+    uint32_t num_rendered;   // R = sum of tiles_touched
+    uint32_t capacity;       // instances the binning buffer can hold
+    uint32_t overflow;       // 1 if R > capacity (binning/blend skipped, host retries)
+    uint32_t n_big;          // tiles whose list does not fit the small sort kernel
+    uint32_t big_cursor;     // work counter of the big-tile sort kernel
+    uint32_t max_tile;       // longest tile list
+    uint32_t pad[2];
+};
+
+namespace gstar {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA bulk copy global -> shared (linear, 16-byte granularity), completion on an mbarrier. SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace gstar

@@ -1,0 +1,101 @@
+// gstar_kernels.h -- host-visible launch interfaces of the kernels (internal to libgstar_raster.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct GRec;
+struct GHeader;
+
+namespace gstar {
+
+struct PreFwdParams {
+    int P, D, M, W, H, gx, gy;
+    const float* means3D;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* colors_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    int prefiltered;
+    GRec* recs;
+    int* radii;
+    uint32_t* tile_count;
+};
+
+struct PreBwdParams {
+    int P, D, M, W, H;
+    const float* means3D;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    const int* radii;
+    const GRec* recs;
+    const float* gacc;  // [P][12] blend-stage gradient accumulator
+    float* dL_dmean2D;
+    float* dL_dconic;
+    float* dL_dopacity;
+    float* dL_dcolor;
+    float* dL_dmean3D;
+    float* dL_dcov3D;
+    float* dL_dsh;
+    float* dL_dscale;
+    float* dL_drot;
+};
+
+struct BinParams {
+    int P, gx, gy, num_tiles;
+    const GRec* recs;
+    GHeader* hdr;          // device header (image buffer)
+    uint32_t* tile_count;  // [T] histogram from preprocess
+    uint32_t* tile_cursor; // [T] running write position per tile
+    uint32_t* ranges;      // [T][2]
+    uint32_t* big_tiles;   // [T] worklist of tiles too long for the small sort kernel
+    uint2* entries;        // [capacity] (depth bits, idx), tile-segmented
+    uint32_t* point_list;  // [capacity] sorted gaussian ids
+    uint32_t capacity;
+    volatile uint32_t* host_counts;  // mapped pinned host memory: [0]=R, [1]=overflow
+};
+
+struct BlendParams {
+    int W, H, gx, gy;
+    const GRec* recs;
+    const GHeader* hdr;
+    const uint32_t* ranges;
+    const uint32_t* point_list;
+    const float* bg;
+    // forward
+    float* out_color;
+    float* final_T;
+    uint32_t* n_contrib;
+    // backward
+    const float* dL_dpix;
+    float* gacc;
+};
+
+void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s);
+void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s);
+void launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present, cudaStream_t s);
+void launch_geom_unpack(const GRec* recs, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
+                        unsigned char* clamped, cudaStream_t s);
+
+void launch_tile_scan(const BinParams& p, cudaStream_t s);
+void launch_emit(const BinParams& p, cudaStream_t s);
+void launch_tile_sort(const BinParams& p, cudaStream_t s);
+int  tile_sort_setup();  // one-time cudaFuncSetAttribute calls; returns cudaError_t
+
+void launch_blend_fwd(const BlendParams& p, cudaStream_t s);
+void launch_blend_bwd(const BlendParams& p, cudaStream_t s);
+
+}  // namespace gstar

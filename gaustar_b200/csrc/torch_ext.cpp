@@ -1,0 +1,177 @@
+// torch_ext.cpp -- thin PyTorch shim over the C ABI (include/gstar_raster.h).
+//
+// Exposes the exact three functions of the reference's pybind module
+// (DGR/ext.cpp:15-19; signatures DGR/rasterize_points.h:18-66) so that
+// diff_gaussian_rasterization/__init__.py-style callers work unchanged:
+//     rasterize_gaussians, rasterize_gaussians_backward, mark_visible
+// PyTorch is used only for memory (caching allocator through the resize callbacks), the current
+// stream and the device guard.  No computation happens here; there is no CPU fallback.
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/extension.h>
+
+#include <tuple>
+
+#include "../../include/gstar_raster.h"
+
+namespace {
+
+// mirrors resizeFunctional(), DGR/rasterize_points.cu:27-33
+char* resize_cb(void* user, size_t nbytes)
+{
+    auto* t = reinterpret_cast<torch::Tensor*>(user);
+    t->resize_({(long long)nbytes});
+    return reinterpret_cast<char*>(t->data_ptr());
+}
+
+const float* fptr(const torch::Tensor& t) { return t.numel() == 0 ? nullptr : t.data_ptr<float>(); }
+
+torch::Tensor prep(const torch::Tensor& t, const torch::Device& dev)
+{
+    if (t.numel() == 0) return t;
+    TORCH_CHECK(t.scalar_type() == torch::kFloat32, "rasterizer inputs must be float32");
+    torch::Tensor r = t;
+    if (r.device() != dev) r = r.to(dev);
+    return r.contiguous();
+}
+
+void check(int rc)
+{
+    if (rc < 0) {
+        if (rc == GSTAR_ERR_NONRGB) throw std::runtime_error(gstar_last_error());
+        TORCH_CHECK(false, gstar_last_error());
+    }
+}
+
+}  // namespace
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> RasterizeGaussiansCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors, const torch::Tensor& opacity,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
+    const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const bool prefiltered,
+    const bool debug)
+{
+    if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
+        AT_ERROR("means3D must have dimensions (num_points, 3)");
+    }
+    TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
+    const torch::Device dev = means3D.device();
+    c10::cuda::CUDAGuard guard(dev);
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(dev.index()).stream();
+
+    const int P = means3D.size(0);
+    const int H = image_height, W = image_width;
+    auto float_opts = means3D.options().dtype(torch::kFloat32);
+    auto byte_opts = torch::TensorOptions(torch::kByte).device(dev);
+
+    torch::Tensor radii = torch::empty({P}, means3D.options().dtype(torch::kInt32));
+    torch::Tensor geomBuffer = torch::empty({0}, byte_opts);
+    torch::Tensor binningBuffer = torch::empty({0}, byte_opts);
+    torch::Tensor imgBuffer = torch::empty({0}, byte_opts);
+    int rendered = 0;
+    torch::Tensor out_color;
+    if (P != 0) {
+        out_color = torch::empty({3, H, W}, float_opts);
+        int M = 0;
+        if (sh.size(0) != 0) M = sh.size(1);
+        const torch::Tensor bg = prep(background, dev), m3 = prep(means3D, dev), col = prep(colors, dev), op = prep(opacity, dev),
+                            sc = prep(scales, dev), rot = prep(rotations, dev), cov = prep(cov3D_precomp, dev), vm = prep(viewmatrix, dev),
+                            pm = prep(projmatrix, dev), shc = prep(sh, dev), cp = prep(campos, dev);
+        gstar_fwd_args a;
+        a.P = P; a.D = degree; a.M = M;
+        a.background = fptr(bg); a.width = W; a.height = H;
+        a.means3D = fptr(m3); a.shs = fptr(shc); a.colors_precomp = fptr(col); a.opacities = fptr(op);
+        a.scales = fptr(sc); a.scale_modifier = scale_modifier; a.rotations = fptr(rot); a.cov3D_precomp = fptr(cov);
+        a.viewmatrix = fptr(vm); a.projmatrix = fptr(pm); a.cam_pos = fptr(cp);
+        a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered ? 1 : 0;
+        a.out_color = out_color.data_ptr<float>(); a.radii = radii.data_ptr<int>(); a.debug = debug ? 1 : 0;
+        rendered = gstar_raster_forward(&a, resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer, stream);
+        check(rendered);
+    } else {
+        out_color = torch::zeros({3, H, W}, float_opts);  // rasterize_points.cu:66
+    }
+    return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                               const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                               const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                               const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                               const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                               const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
+                               const torch::Tensor& imageBuffer, const bool debug)
+{
+    TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
+    const torch::Device dev = means3D.device();
+    c10::cuda::CUDAGuard guard(dev);
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(dev.index()).stream();
+    const int P = means3D.size(0);
+    const int H = dL_dout_color.size(1);
+    const int W = dL_dout_color.size(2);
+    int M = 0;
+    if (sh.size(0) != 0) M = sh.size(1);
+    auto opts = means3D.options().dtype(torch::kFloat32);
+    // every output is fully written by the fused per-Gaussian backward kernel: no zero-fills
+    // (the reference zero-fills nine tensors per call, rasterize_points.cu:150-158)
+    torch::Tensor dL_dmeans3D = torch::empty({P, 3}, opts);
+    torch::Tensor dL_dmeans2D = torch::empty({P, 3}, opts);
+    torch::Tensor dL_dcolors = torch::empty({P, 3}, opts);
+    torch::Tensor dL_dconic = torch::empty({P, 2, 2}, opts);
+    torch::Tensor dL_dopacity = torch::empty({P, 1}, opts);
+    torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
+    torch::Tensor dL_dsh = torch::empty({P, M, 3}, opts);
+    torch::Tensor dL_dscales = torch::empty({P, 3}, opts);
+    torch::Tensor dL_drotations = torch::empty({P, 4}, opts);
+    if (P != 0) {
+        torch::Tensor scratch = torch::zeros({P, GSTAR_GRAD_SCRATCH_FLOATS}, opts);
+        const torch::Tensor bg = prep(background, dev), m3 = prep(means3D, dev), col = prep(colors, dev), sc = prep(scales, dev),
+                            rot = prep(rotations, dev), cov = prep(cov3D_precomp, dev), vm = prep(viewmatrix, dev),
+                            pm = prep(projmatrix, dev), shc = prep(sh, dev), cp = prep(campos, dev), dpix = prep(dL_dout_color, dev);
+        const torch::Tensor rad = radii.contiguous(), gb = geomBuffer.contiguous(), bb = binningBuffer.contiguous(),
+                            ib = imageBuffer.contiguous();
+        gstar_bwd_args a;
+        a.P = P; a.D = degree; a.M = M; a.R = R;
+        a.background = fptr(bg); a.width = W; a.height = H;
+        a.means3D = fptr(m3); a.shs = fptr(shc); a.colors_precomp = fptr(col); a.scales = fptr(sc); a.scale_modifier = scale_modifier;
+        a.rotations = fptr(rot); a.cov3D_precomp = fptr(cov); a.viewmatrix = fptr(vm); a.projmatrix = fptr(pm); a.campos = fptr(cp);
+        a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+        a.radii = rad.data_ptr<int>();
+        a.geom_buffer = reinterpret_cast<char*>(gb.data_ptr());
+        a.binning_buffer = bb.numel() ? reinterpret_cast<char*>(bb.data_ptr()) : nullptr;
+        a.image_buffer = reinterpret_cast<char*>(ib.data_ptr());
+        a.dL_dpix = fptr(dpix);
+        a.dL_dmean2D = dL_dmeans2D.data_ptr<float>(); a.dL_dconic = dL_dconic.data_ptr<float>();
+        a.dL_dopacity = dL_dopacity.data_ptr<float>(); a.dL_dcolor = dL_dcolors.data_ptr<float>();
+        a.dL_dmean3D = dL_dmeans3D.data_ptr<float>(); a.dL_dcov3D = dL_dcov3D.data_ptr<float>();
+        a.dL_dsh = M ? dL_dsh.data_ptr<float>() : nullptr;
+        a.dL_dscale = dL_dscales.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
+        a.blend_grad_scratch = scratch.data_ptr<float>();
+        a.debug = debug ? 1 : 0;
+        check(gstar_raster_backward(&a, stream));
+    }
+    return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
+}
+
+torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix)
+{
+    TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
+    const torch::Device dev = means3D.device();
+    c10::cuda::CUDAGuard guard(dev);
+    const int P = means3D.size(0);
+    torch::Tensor present = torch::full({P}, false, means3D.options().dtype(at::kBool));
+    if (P != 0) {
+        const torch::Tensor m3 = prep(means3D, dev), vm = prep(viewmatrix, dev), pm = prep(projmatrix, dev);
+        check(gstar_mark_visible(P, fptr(m3), fptr(vm), fptr(pm), reinterpret_cast<unsigned char*>(present.data_ptr<bool>()),
+                                 c10::cuda::getCurrentCUDAStream(dev.index()).stream()));
+    }
+    return present;
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+    m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
+    m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+    m.def("mark_visible", &markVisible);
+}

@@ -1,0 +1,168 @@
+/*
+ * gstar_raster.h -- C ABI of the B200-native differentiable surface-Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path of eth-ait/GauSTAR: the operator behind
+ * diff_gaussian_rasterization.GaussianRasterizer.  Each entry point replaces one static method of
+ * CudaRasterizer::Rasterizer in the reference
+ * (DGR = gaussian_splatting/submodules/diff-gaussian-rasterization):
+ *
+ *   gstar_raster_forward   <->  Rasterizer::forward    DGR/cuda_rasterizer/rasterizer.h:31-56
+ *                                                      (impl. rasterizer_impl.cu:198-336)
+ *   gstar_raster_backward  <->  Rasterizer::backward   DGR/cuda_rasterizer/rasterizer.h:58-84
+ *                                                      (impl. rasterizer_impl.cu:340-434)
+ *   gstar_mark_visible     <->  Rasterizer::markVisible DGR/cuda_rasterizer/rasterizer.h:24-29
+ *                                                      (impl. rasterizer_impl.cu:141-153)
+ *
+ * Plain pointers and sizes only: no torch types, no C++ types, no exceptions cross this boundary.
+ * All data pointers are DEVICE pointers on the current CUDA device unless stated otherwise; all
+ * work is enqueued on `stream`.  The reference binding that a maintainer would write against this
+ * header is shown in INTEGRATION.md; the torch binding shipped here is gaustar_b200/csrc/torch_ext.cpp.
+ *
+ * Return convention: >= 0 success, < 0 error (message from gstar_last_error(), thread local).
+ */
+#ifndef GSTAR_RASTER_H
+#define GSTAR_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSTAR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GSTAR_API __attribute__((visibility("default")))
+#else
+#define GSTAR_API
+#endif
+
+/* error codes */
+#define GSTAR_ERR_INVALID  (-1) /* bad argument combination */
+#define GSTAR_ERR_CUDA     (-2) /* a CUDA call failed (debug mode: after a device synchronize) */
+#define GSTAR_ERR_ALLOC    (-3) /* a buffer callback returned NULL */
+#define GSTAR_ERR_NONRGB   (-4) /* "For non-RGB, provide precomputed Gaussian colors!" rasterizer_impl.cu:242-245 */
+
+/* Resizable-buffer callback: mirrors the three std::function<char*(size_t)> of rasterizer.h:32-34
+ * (created by resizeFunctional(), DGR/rasterize_points.cu:27-33).  Must return a device pointer to
+ * at least nbytes bytes, 128-byte aligned, owned by the caller.  It may be called more than once per
+ * forward for the binning buffer (a second time, with a larger size, only if the instance count
+ * exceeded the first provision). */
+typedef char* (*gstar_alloc_fn)(void* user, size_t nbytes);
+
+/* Arguments of Rasterizer::forward, rasterizer.h:35-56, in the same order and meaning.
+ * Absent optional inputs are NULL (the reference passes data_ptr() of an empty tensor). */
+typedef struct gstar_fwd_args {
+    int P, D, M;                 /* gaussians, active SH degree, SH coeffs per gaussian */
+    const float* background;     /* [3] */
+    int width, height;
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3]   or NULL */
+    const float* opacities;      /* [P] */
+    const float* scales;         /* [P,3]   or NULL */
+    float scale_modifier;
+    const float* rotations;      /* [P,4]   or NULL */
+    const float* cov3D_precomp;  /* [P,6]   or NULL */
+    const float* viewmatrix;     /* [16] row-vector convention, auxiliary.h:58-77 */
+    const float* projmatrix;     /* [16] */
+    const float* cam_pos;        /* [3] */
+    float tan_fovx, tan_fovy;
+    int prefiltered;
+    float* out_color;            /* [3,H,W] fully written */
+    int* radii;                  /* [P] fully written (0 = culled) */
+    int debug;                   /* !=0: synchronize + check after every stage (auxiliary.h:166-173) */
+} gstar_fwd_args;
+
+/* Forward pass.  Returns num_rendered (sum of tiles touched), exactly like Rasterizer::forward. */
+GSTAR_API int gstar_raster_forward(const gstar_fwd_args* args,
+                         gstar_alloc_fn geom_alloc, void* geom_user,
+                         gstar_alloc_fn binning_alloc, void* binning_user,
+                         gstar_alloc_fn image_alloc, void* image_user,
+                         void* stream /* cudaStream_t */);
+
+/* Arguments of Rasterizer::backward, rasterizer.h:58-84. */
+typedef struct gstar_bwd_args {
+    int P, D, M, R;
+    const float* background;
+    int width, height;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy;
+    const int* radii;
+    char* geom_buffer;           /* the three opaque buffers of the matching forward call */
+    char* binning_buffer;
+    char* image_buffer;
+    const float* dL_dpix;        /* [3,H,W] */
+    /* Outputs.  Unlike the reference (which accumulates with atomics into caller-zeroed arrays,
+     * rasterize_points.cu:150-158) every output below is FULLY OVERWRITTEN; no zero-fill needed. */
+    float* dL_dmean2D;           /* [P,3] (x,y in NDC-scaled pixels, z = 0) backward.cu:545-546 */
+    float* dL_dconic;            /* [P,4] (.x,.y,.w used)                    backward.cu:549-551 */
+    float* dL_dopacity;          /* [P]                                      backward.cu:554 */
+    float* dL_dcolor;            /* [P,3]                                    backward.cu:523 */
+    float* dL_dmean3D;           /* [P,3] */
+    float* dL_dcov3D;            /* [P,6] */
+    float* dL_dsh;               /* [P,M,3] (NULL if M == 0) */
+    float* dL_dscale;            /* [P,3] */
+    float* dL_drot;              /* [P,4] */
+    /* Scratch: P * GSTAR_GRAD_SCRATCH_FLOATS floats, ZERO-FILLED by the caller. The blend
+     * backward reduces per-(gaussian,tile) partial sums into it with one vector of atomics per
+     * warp instead of the reference's nine atomics per (gaussian,pixel). */
+    float* blend_grad_scratch;
+    int debug;
+} gstar_bwd_args;
+#define GSTAR_GRAD_SCRATCH_FLOATS 12
+
+GSTAR_API int gstar_raster_backward(const gstar_bwd_args* args, void* stream);
+
+/* checkFrustum: present[i] = (view-space z > 0.2).  present is a byte array (C++ bool). */
+GSTAR_API int gstar_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                       unsigned char* present, void* stream);
+
+/* Thread-local message of the last error returned on this thread. */
+GSTAR_API const char* gstar_last_error(void);
+GSTAR_API int gstar_abi_version(void);
+
+/* ---- sizes and views of the opaque buffers (the layout is private; these are for callers that
+ * pre-provision memory and for the parity tests that compare intermediates) ---- */
+GSTAR_API size_t gstar_geom_bytes(int P);
+GSTAR_API size_t gstar_image_bytes(int width, int height);
+GSTAR_API size_t gstar_binning_bytes(size_t capacity_instances);
+
+/* Copies the per-gaussian intermediates out of a geometry buffer into reference-layout arrays
+ * (any may be NULL): depths[P], means2D[P,2], conic_opacity[P,4], rgb[P,3], tiles_touched[P],
+ * clamped[P,3] (bytes).  Mirrors GeometryState, rasterizer_impl.h:33-47. */
+GSTAR_API int gstar_geom_unpack(const char* geom_buffer, int P, float* depths, float* means2D, float* conic_opacity, float* rgb,
+                      uint32_t* tiles_touched, unsigned char* clamped, void* stream);
+/* Views into the image buffer (ImageState, rasterizer_impl.h:49-56): final_T[H*W], n_contrib[H*W],
+ * ranges[T,2] with T = ceil(W/16)*ceil(H/16). */
+GSTAR_API int gstar_image_views(char* image_buffer, int width, int height, float** final_T, uint32_t** n_contrib, uint32_t** ranges);
+/* View of the sorted instance list (BinningState::point_list, rasterizer_impl.h:58-68). */
+GSTAR_API int gstar_binning_views(char* binning_buffer, uint32_t** point_list, uint64_t* capacity);
+
+/* ---- measurement hook: record `start`/`stop` (cudaEvent_t) around kernel stage `stage` of every
+ * subsequent call on this thread (stage < 0 disables).  Stages: see gstar_stage_name(). ---- */
+GSTAR_API int gstar_profile_stage(int stage, void* start_event, void* stop_event);
+GSTAR_API const char* gstar_stage_name(int stage);
+#define GSTAR_STAGE_PREPROCESS_FWD 0
+#define GSTAR_STAGE_TILE_SCAN      1
+#define GSTAR_STAGE_EMIT           2
+#define GSTAR_STAGE_TILE_SORT      3
+#define GSTAR_STAGE_BLEND_FWD      4
+#define GSTAR_STAGE_BLEND_BWD      5
+#define GSTAR_STAGE_PREPROCESS_BWD 6
+#define GSTAR_NUM_STAGES           7
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSTAR_RASTER_H */
