@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward views/sec of the surface-Gaussian rasterizer (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic views: every rank renders
+VIEWS_PER_GPU camera views of the SAME replicated 1M mesh-bound Gaussians at 1920x1080 (forward +
+backward, SH degree 3 evaluated in-kernel), accumulates the per-Gaussian parameter gradients of its
+views into one flat buffer and (N > 1) joins the ranks with ONE NCCL sum-allreduce of that buffer.
+Per-GPU work is fixed as N grows ("weak").
+
+  value : views/s, inputs resident in HBM, calls made straight through the C ABI
+          (gaustar_b200/capi.py -> libgstar_raster.so); CUDA events, max over ranks.
+  e2e   : the same metric through the public operator API (diff_gaussian_rasterization.GaussianRasterizer
+          + autograd) with, per view, the camera and the 8-bit target image copied from pinned host
+          memory (H2D) and, per step, the loss read back (D2H) -- all inside the timed region.
+  roofline     : the dominant kernel (blend_bwd) timed live with CUDA events on the launching stream
+                 through the library's profile hook; achieved = algorithmic bytes / time.
+  cpu_baseline : the CPU oracle (oracle/, a C restatement of the reference; kind "port") on the host
+                 cores, bounded sample, rank 0 at N=1 only.  The reference rasterizer has no CPU path.
+
+--impl reference times the UNMODIFIED reference rasterizer (oracle/_ref/ref_dgr_C.so, the reference's
+own pybind module built for sm_100a by oracle/build_ref.py) on the same GPU with the same protocol.
+If that module or a GPU is unavailable it falls back to timing the CPU oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gaustar_b200 import scene  # noqa: E402
+from gaustar_b200 import dist as gdist  # noqa: E402
+
+METRIC = "fwd+bwd views/sec at 1M surface Gaussians, 1080p; HBM GB/s vs roofline"
+UNIT = "views/s"
+P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
+VIEWS_PER_GPU = 8
+CAM_POOL = 32
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(device, rank, world):
+    g = scene.surface_gaussians(P_TARGET, sh_degree=SH_DEG, seed=0)
+    cams = scene.dome_cameras(CAM_POOL, W, H)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    params = dict(means3D=t(g.means3D), scales=t(g.scales), rotations=t(g.rotations), opacities=t(g.opacities), shs=t(g.shs))
+    bg = torch.tensor([0.0, 1.0, 0.0], device=device)
+    # 8-bit targets (what a dataset on disk holds): a small pool in pinned host memory
+    rng = np.random.default_rng(1 + rank)
+    targets = [torch.from_numpy(np.clip(rng.normal(0.5, 0.2, (H, W, 3)) * 255, 0, 255).astype(np.uint8)).pin_memory() for _ in range(4)]
+    cam_host = [dict(viewmatrix=torch.from_numpy(c.viewmatrix).pin_memory(), projmatrix=torch.from_numpy(c.projmatrix).pin_memory(),
+                     campos=torch.from_numpy(c.campos).pin_memory(), tanfovx=c.tanfovx, tanfovy=c.tanfovy) for c in cams]
+    cam_dev = [dict(viewmatrix=c["viewmatrix"].to(device), projmatrix=c["projmatrix"].to(device), campos=c["campos"].to(device),
+                    tanfovx=c["tanfovx"], tanfovy=c["tanfovy"]) for c in cam_host]
+    return g, params, bg, targets, cam_host, cam_dev
+
+
+# ------------------------------------------------------------------------------------------------
+# the two implementations behind one tiny interface
+# ------------------------------------------------------------------------------------------------
+class OursCABI:
+    """Device-resident arm: straight through the C ABI."""
+    name = "gaustar_b200 (C ABI)"
+    launches_per_view = 8  # preprocess_fwd, tile_scan, emit, tile_sort, tile_sort_big, blend_fwd, blend_bwd, preprocess_bwd
+
+    def __init__(self):
+        from gaustar_b200 import capi
+        self.capi = capi
+        capi.lib()
+
+    def fwd_bwd(self, params, cam, bg, grad_fn):
+        kw = dict(means3D=params["means3D"], viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], campos=cam["campos"], bg=bg,
+                  tan_fovx=cam["tanfovx"], tan_fovy=cam["tanfovy"], shs=params["shs"], scales=params["scales"], rotations=params["rotations"],
+                  sh_degree=SH_DEG)
+        f = self.capi.forward(opacities=params["opacities"], W=W, H=H, **kw)
+        g = self.capi.backward(f, grad_fn(f["out_color"]), **kw)
+        return f["num_rendered"], int(0), g
+
+
+class RefStock:
+    """The unmodified reference through its own pybind module (stock binding, reference kernels)."""
+    name = "reference diff-gaussian-rasterization (oracle/_ref/ref_dgr_C.so, sm_100a)"
+    launches_per_view = 0
+
+    def __init__(self):
+        from oracle import refgpu
+        self.C = refgpu.stock_module()
+        self.empty = torch.Tensor([])
+
+    def fwd_bwd(self, params, cam, bg, grad_fn):
+        C, e = self.C, self.empty
+        R, color, radii, gb, bb, ib = C.rasterize_gaussians(bg, params["means3D"], e, params["opacities"], params["scales"], params["rotations"], 1.0, e,
+                                                            cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], H, W, params["shs"],
+                                                            SH_DEG, cam["campos"], False, False)
+        out = C.rasterize_gaussians_backward(bg, params["means3D"], radii, e, params["scales"], params["rotations"], 1.0, e, cam["viewmatrix"],
+                                             cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], grad_fn(color), params["shs"], SH_DEG, cam["campos"],
+                                             gb, R, bb, ib, False)
+        g = dict(dL_dmeans2D=out[0], dL_dcolors=out[1], dL_dopacity=out[2], dL_dmeans3D=out[3], dL_dcov3D=out[4], dL_dsh=out[5], dL_dscales=out[6],
+                 dL_drotations=out[7])
+        return R, 0, g
+
+
+def make_autograd_rasterizer(impl):
+    """Public-API arm.  ours: the shipped drop-in module.  reference: the reference's own wrapper logic
+    (DGR/diff_gaussian_rasterization/__init__.py:44-155) around its stock pybind module."""
+    if impl == "ours":
+        import diff_gaussian_rasterization as d
+        return d.GaussianRasterizationSettings, d.GaussianRasterizer
+    from oracle import refgpu
+    C = refgpu.stock_module()
+    import diff_gaussian_rasterization as d  # only for the settings NamedTuple (plain data)
+
+    class _RefFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+            R, color, radii, gb, bb, ib = C.rasterize_gaussians(rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                                                                cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+                                                                rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+            ctx.rs, ctx.R = rs, R
+            ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, gb, bb, ib)
+            return color, radii
+
+        @staticmethod
+        def backward(ctx, g, _):
+            rs = ctx.rs
+            colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, gb, bb, ib = ctx.saved_tensors
+            o = C.rasterize_gaussians_backward(rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                                               rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, g, sh, rs.sh_degree, rs.campos, gb, ctx.R, bb, ib,
+                                               rs.debug)
+            return o[3], o[0], o[5], o[1], o[2], o[6], o[7], o[4], None
+
+    class RefRasterizer(torch.nn.Module):
+        def __init__(self, raster_settings):
+            super().__init__()
+            self.raster_settings = raster_settings
+
+        def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+            e = torch.Tensor([])
+            return _RefFn.apply(means3D, means2D, shs if shs is not None else e, colors_precomp if colors_precomp is not None else e, opacities,
+                                scales if scales is not None else e, rotations if rotations is not None else e,
+                                cov3D_precomp if cov3D_precomp is not None else e, self.raster_settings)
+
+    return d.GaussianRasterizationSettings, RefRasterizer
+
+
+# ------------------------------------------------------------------------------------------------
+def l1_grad_fn(target_f):
+    """dL/dcolor of L = mean |render - target| (SURVEY 8d upstream gradient)."""
+    inv = 1.0 / (3 * H * W)
+    return lambda img: torch.sign(img - target_f) * inv
+
+
+def run_gpu(args, impl_name, rank, world, local):
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    g, params, bg, targets, cam_host, cam_dev = build_workload(device, rank, world)
+    P, M = g.P, g.shs.shape[1]
+    impl = OursCABI() if impl_name == "ours" else RefStock()
+    target_f = [(t.to(device).permute(2, 0, 1).float() / 255.0).contiguous() for t in targets[:2]]
+    flat = gdist.FlatGrads(P, M, device)
+    my_views = lambda step: [(step * VIEWS_PER_GPU * world + v) % CAM_POOL for v in gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)]
+
+    # ---------------- device-resident arm (value) ----------------
+    prof = None
+    if impl_name == "ours":
+        from gaustar_b200 import capi
+        n_ev = args.steps * VIEWS_PER_GPU
+        prof = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
+        for a, b in prof:
+            a.record(); b.record()
+        torch.cuda.synchronize()
+    R_sum, V_count = 0, 0
+
+    def step_value(step, timed):
+        nonlocal R_sum, V_count
+        flat.zero_()
+        for i, v in enumerate(my_views(step)):
+            if prof is not None and timed:
+                a, b = prof[(step - args.warmup) * VIEWS_PER_GPU + i]
+                capi.profile_stage(capi.STAGES.index("blend_bwd"), a, b)
+            R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]))
+            flat.accumulate(grads)
+            if timed:
+                R_sum += int(R); V_count += 1
+        flat.allreduce()
+
+    for s in range(args.warmup):
+        step_value(s, False)
+    gdist.barrier(); torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step_value(args.warmup + s, True)
+    e1.record()
+    gdist.barrier(); torch.cuda.synchronize()
+    ms_value = gdist.max_over_ranks(e0.elapsed_time(e1), device)
+    clk = clocks.stop() if rank == 0 else None
+    if prof is not None:
+        capi.profile_stage(-1)
+    views_total = VIEWS_PER_GPU * world * args.steps
+    value = views_total / (ms_value / 1e3)
+
+    roofline = None
+    if prof is not None:
+        t_bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in prof]))
+        R_avg = R_sum / max(V_count, 1)
+        alg_bytes = 40.0 * R_avg + 20.0 * W * H + 36.0 * P  # B7, V ~= P for this scene
+        peak, how = measured_peak()
+        ach = alg_bytes / (t_bwd_ms * 1e-3) / 1e9
+        roofline = {"kernel": "k_blend_bwd", "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                    "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(t_bwd_ms, 4),
+                    "avg_num_rendered": int(R_avg)}
+
+    # ---------------- public-API arm (e2e): host buffers, copies inside the timed region ----------------
+    Settings, Rasterizer = make_autograd_rasterizer(impl_name)
+    leaves = {k: params[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    name_of = {"means3D": "dL_dmeans3D", "scales": "dL_dscales", "rotations": "dL_drotations", "opacities": "dL_dopacity", "shs": "dL_dsh"}
+    for k, p in leaves.items():
+        p.grad = flat.views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
+    copy_stream = torch.cuda.Stream(device)
+    slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), vm=torch.empty(4, 4, device=device), pm=torch.empty(4, 4, device=device),
+                  cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    h2d_per_view = H * W * 3 + (16 + 16 + 3) * 4
+    means2D = torch.zeros(P, 3, device=device, requires_grad=True)
+
+    def prefetch(slot, v, i):
+        s = slots[slot]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(s["free"])
+            s["tgt"].copy_(targets[i % len(targets)], non_blocking=True)
+            s["vm"].copy_(cam_host[v]["viewmatrix"], non_blocking=True)
+            s["pm"].copy_(cam_host[v]["projmatrix"], non_blocking=True)
+            s["cp"].copy_(cam_host[v]["campos"], non_blocking=True)
+            s["ev"].record(copy_stream)
+
+    def step_e2e(step):
+        flat.zero_()
+        views = my_views(step)
+        loss_sum = torch.zeros((), device=device)
+        prefetch(0, views[0], 0)
+        cur = torch.cuda.current_stream(device)
+        for i, v in enumerate(views):
+            s = slots[i & 1]
+            if i + 1 < len(views):
+                prefetch((i + 1) & 1, views[i + 1], i + 1)
+            cur.wait_event(s["ev"])
+            rs = Settings(image_height=H, image_width=W, tanfovx=cam_host[v]["tanfovx"], tanfovy=cam_host[v]["tanfovy"], bg=bg, scale_modifier=1.0,
+                          viewmatrix=s["vm"], projmatrix=s["pm"], sh_degree=SH_DEG, campos=s["cp"], prefiltered=False, debug=False)
+            img, _radii = Rasterizer(rs)(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
+                                         scales=leaves["scales"], rotations=leaves["rotations"])
+            tgt = s["tgt"].permute(2, 0, 1).float().mul_(1.0 / 255.0)
+            loss = (img - tgt).abs().mean()
+            loss.backward()
+            loss_sum += loss.detach()
+            s["free"].record(cur)
+        flat.allreduce()
+        return float(loss_sum.item())  # D2H read of the step's result
+
+    for e in slots:
+        e["free"].record(torch.cuda.current_stream(device))
+    e2e_steps = max(1, args.steps)
+    for s in range(min(args.warmup, 3)):
+        step_e2e(s)
+    gdist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for s in range(e2e_steps):
+        step_e2e(args.warmup + s)
+    e1.record()
+    gdist.barrier(); torch.cuda.synchronize()
+    ms_e2e = gdist.max_over_ranks(e0.elapsed_time(e1), device)
+    e2e_val = VIEWS_PER_GPU * world * e2e_steps / (ms_e2e / 1e3)
+    e2e = {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_per_view * VIEWS_PER_GPU, "d2h_bytes_per_step": 4,
+           "api": "diff_gaussian_rasterization.GaussianRasterizer + autograd; target image (uint8) and camera copied from pinned host memory per view "
+                  "(prefetched on a copy stream), loss scalar read back per step"}
+    return dict(value=value, ms_per_step=ms_value / args.steps, roofline=roofline, e2e=e2e, clocks=clk, P=P, M=M, device_name=torch.cuda.get_device_name(device),
+                launches=impl.launches_per_view * VIEWS_PER_GPU * args.steps, impl_desc=impl.name, allreduce_bytes=flat.nbytes)
+
+
+def cpu_oracle_views_per_sec(n_views=1, small=False):
+    """The CPU oracle (C restatement of the reference, OpenMP) on a bounded sample of the workload."""
+    from oracle import oracle as O
+    O.build()
+    Pn, w, h = (30000, 480, 270) if small else (P_TARGET, W, H)
+    g = scene.surface_gaussians(Pn, sh_degree=SH_DEG, seed=0)
+    cams = scene.dome_cameras(CAM_POOL, w, h)
+    rng = np.random.default_rng(1)
+    t0 = time.time()
+    for v in range(n_views):
+        c = cams[v]
+        inp = O.Inputs(means3D=g.means3D, opacities=g.opacities, viewmatrix=c.viewmatrix, projmatrix=c.projmatrix, campos=c.campos,
+                       bg=np.array([0, 1, 0], np.float32), tan_fovx=c.tanfovx, tan_fovy=c.tanfovy, W=w, H=h, shs=g.shs, scales=g.scales,
+                       rotations=g.rotations, sh_degree=SH_DEG)
+        f = O.forward(inp)
+        target = np.clip(rng.normal(0.5, 0.2, (3, h, w)), 0, 1).astype(np.float32)
+        dpix = (np.sign(f.out_color - target) / (3 * h * w)).astype(np.float32)
+        O.backward(inp, f, dpix)
+    dt = time.time() - t0
+    return n_views / dt, dt, f"{n_views} view(s) fwd+bwd of P={g.P} {w}x{h} SH{SH_DEG} (same generator as the GPU workload)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local = gdist.init_from_env()
+    have_gpu = torch.cuda.is_available()
+    config = {"workload": f"surface-1M-1080p-sh3 ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
+              "gaussians": None, "resolution": [W, H], "sh_degree": SH_DEG, "views_per_step": VIEWS_PER_GPU * world,
+              "parallelism": f"view-sharded dp{world} + 1 allreduce/step", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
+
+    if args.impl == "reference":
+        use_gpu_ref = have_gpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C.so"))
+        if not use_gpu_ref:
+            if rank != 0:
+                return
+            v, dt, sample = cpu_oracle_views_per_sec(1)
+            line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                    "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": config, "device": "cpu",
+                    "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                    "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "note": "reference CUDA module unavailable here: timed the CPU oracle port instead"}
+            print(json.dumps(line), flush=True)
+            return
+    if not have_gpu:
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU oracle baseline)")
+
+    res = run_gpu(args, args.impl, rank, world, local)
+    if rank != 0:
+        return
+    config["gaussians"] = res["P"]
+    line = {"metric": METRIC, "value": round(res["value"], 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(res["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"],
+            "device": res["device_name"], "allreduce_bytes_per_step": res["allreduce_bytes"] if world > 1 else 0}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["implementation"] = res["impl_desc"]
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                "sample": "n/a: the reference rasterizer is CUDA-only (no CPU path); this arm ran it unmodified on the GPU"}
+        line["gpu_launches"] = 0
+    else:
+        line["roofline"] = res["roofline"]
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, sample = cpu_oracle_views_per_sec(1)
+            line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
+                                    "seconds": round(dt, 1)}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

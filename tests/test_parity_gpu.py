@@ -1,0 +1,284 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(gaustar_b200/capi.py -> libgstar_raster.so) or through the public operator API on top of it.
+
+Bars (SURVEY.md 8c / BASELINE.md 2.5):
+  bit-exact : radii, tiles_touched, num_rendered, depth / pixel-centre / conic bits, the sorted
+              (tile|depth, gaussian) list, tile ranges, n_contrib            [vs reference & golden]
+  fp32 tol. : out_color, final_T: rtol 1e-5 / atol 2e-6 vs the reference (same op order; observed 0);
+              atol 2e-5 vs the CPU oracle (glibc expf vs the GPU's ex2.approx-based expf)
+  gradients : max-abs error <= 1e-3 of the tensor's max magnitude vs the fp64-accumulating oracle
+              and vs the reference (whose own fp32 atomics are order-nondeterministic)
+"""
+import numpy as np
+import pytest
+import torch
+
+from gaustar_b200 import capi, scene
+from oracle import oracle as O
+from oracle import refgpu
+
+import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 1e-3
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+def run_mine(d, debug=False):
+    kw = Hh.to_torch_kwargs(d)
+    fwd = capi.forward(debug=debug, **kw)
+    torch.cuda.synchronize()
+    return kw, fwd
+
+
+def check_forward_against(fwd, kw, ref, exact_image, n_contrib_slack=0):
+    """ref: dict-like with numpy arrays in the reference layouts."""
+    P, W, H = kw["means3D"].shape[0], kw["W"], kw["H"]
+    g = {k: v.cpu().numpy() for k, v in capi.unpack_geometry(fwd, P).items()}
+    st = {k: v.cpu().numpy() for k, v in capi.image_state(fwd, W, H).items()}
+    pl = capi.point_list(fwd).cpu().numpy()
+    radii = fwd["radii"].cpu().numpy()
+    vis = ref["radii"] > 0
+    assert fwd["num_rendered"] == int(ref["num_rendered"])
+    np.testing.assert_array_equal(radii, ref["radii"])
+    np.testing.assert_array_equal(g["tiles_touched"], np.asarray(ref["tiles_touched"]).astype(np.int32))
+    np.testing.assert_array_equal(bits(g["depths"])[vis], bits(ref["depths"])[vis])
+    np.testing.assert_array_equal(bits(g["means2D"])[vis], bits(ref["means2D"])[vis])
+    np.testing.assert_array_equal(bits(g["conic_opacity"])[vis], bits(ref["conic_opacity"])[vis])
+    np.testing.assert_array_equal(pl, np.asarray(ref["point_list"]).astype(np.int32))
+    np.testing.assert_array_equal(st["ranges"], np.asarray(ref["ranges"]).astype(np.int32))
+    nc_ref = np.asarray(ref["n_contrib"]).astype(np.int32).reshape(-1)
+    assert int((st["n_contrib"] != nc_ref).sum()) <= n_contrib_slack
+    out = fwd["out_color"].cpu().numpy()
+    if exact_image:
+        np.testing.assert_allclose(out, ref["out_color"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(st["final_T"], np.asarray(ref["final_T"]).reshape(-1), rtol=1e-5, atol=1e-6)
+    else:
+        same = st["n_contrib"] == nc_ref
+        assert np.abs(out - ref["out_color"]).reshape(3, -1)[:, same].max() < 2e-5
+    return g, st
+
+
+def check_grads(mine, ref, tol=GRAD_TOL):
+    for k in Hh.GRAD_KEYS:
+        r = np.asarray(ref[k])
+        if r.size == 0:
+            continue
+        m = mine[k].cpu().numpy().reshape(r.shape)
+        assert np.isfinite(m).all(), k
+        assert Hh.rel_err(m, r) < tol, (k, Hh.rel_err(m, r))
+
+
+SCENES = {
+    "surface_sh3": lambda: Hh.scene_dict(scene.surface_gaussians(20000, 3, seed=1), scene.dome_cameras(6, 400, 225)[2]),
+    "surface_precomp": lambda: Hh.scene_dict(scene.surface_gaussians(12000, 3, seed=2), scene.dome_cameras(6, 320, 200)[4], use_sh=False,
+                                             bg=(10.0, 10.0, 10.0)),
+    "random_big_sh2": lambda: Hh.scene_dict(scene.random_gaussians(5000, 2, seed=5, scale_range=(0.01, 0.4)),
+                                            scene.look_at_camera([0.5, 1.3, 4.0], [0, 1, 0], 320, 180, fy_over_H=1.2)),
+    "random_closeup_odd": lambda: Hh.scene_dict(scene.random_gaussians(4000, 1, seed=6), scene.look_at_camera([0.2, 1.0, 0.9], [0, 1, 0], 333, 201, fy_over_H=0.9),
+                                                bg=(0.3, 0.2, 0.1)),
+    "sh_deg1_of_3": lambda: Hh.scene_dict(scene.random_gaussians(3000, 3, seed=8, scale_range=(0.01, 0.1)),
+                                          scene.look_at_camera([0.0, 1.0, 3.0], [0, 1, 0], 160, 120), sh_degree=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_against_cpu_oracle(name):
+    d = SCENES[name]()
+    kw, fwd = run_mine(d)
+    inp = Hh.oracle_inputs_from_dict(d)
+    of = O.forward(inp)
+    ref = dict(of.__dict__)
+    npix = d["W"] * d["H"]
+    g, st = check_forward_against(fwd, kw, ref, exact_image=False, n_contrib_slack=max(2, npix // 20000))
+    if "shs" in d:
+        vis = of.radii > 0
+        np.testing.assert_allclose(g["rgb"][vis], of.rgb[vis], rtol=1e-5, atol=2e-6)
+    dpix = np.random.default_rng(1).normal(0, 1, (3, d["H"], d["W"])).astype(np.float32)
+    mine = capi.backward(fwd, torch.from_numpy(dpix).cuda(), **Hh.bwd_kwargs(kw))
+    torch.cuda.synchronize()
+    # oracle backward on the GPU's own forward state so that a flipped n_contrib does not count as a gradient error
+    of.n_contrib = st["n_contrib"].astype(np.uint32)
+    of.final_T = st["final_T"].copy()
+    ob = O.backward(inp, of, dpix)
+    check_grads(mine, ob.__dict__)
+
+
+@pytest.mark.parametrize("path", Hh.golden_files() or [None])
+def test_against_reference_golden(path):
+    if path is None:
+        pytest.fail("no golden vectors in tests/golden/")
+    inp_d, rf, rb = Hh.load_golden(path)
+    d = {k: v for k, v in inp_d.items() if k != "dL_dpix"}
+    kw, fwd = run_mine(d)
+    check_forward_against(fwd, kw, rf, exact_image=True)
+    mine = capi.backward(fwd, torch.from_numpy(inp_d["dL_dpix"]).cuda(), **Hh.bwd_kwargs(kw))
+    torch.cuda.synchronize()
+    check_grads(mine, rb)
+
+
+@pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref not built (reference sources absent at build time)")
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_against_live_reference(name):
+    d = SCENES[name]()
+    kw, fwd = run_mine(d)
+    ref = refgpu.forward(**kw)
+    rnp = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in ref.items()}
+    check_forward_against(fwd, kw, rnp, exact_image=True)
+    dpix = torch.randn(3, d["H"], d["W"], device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    mine = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
+    rg = refgpu.backward(ref, dpix, **Hh.bwd_kwargs(kw))
+    check_grads(mine, {k: v.cpu().numpy() for k, v in rg.items()})
+
+
+def test_operator_api_autograd_matches_cabi():
+    """GaussianRasterizer + autograd (the call sugar_model.py:1285-1293 makes) == direct C-ABI calls,
+    including non-contiguous expanded colours (refine.py:605) and the means2D gradient the densifier reads."""
+    import diff_gaussian_rasterization as dgr
+    d = SCENES["surface_precomp"]()
+    kw = Hh.to_torch_kwargs(d)
+    P = kw["means3D"].shape[0]
+    depth_like = torch.rand(P, 1, device="cuda")
+    colors = depth_like.expand(-1, 3)  # non-contiguous
+    leaf = {k: kw[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations")}
+    col_leaf = depth_like.clone().requires_grad_(True)
+    means2D = torch.zeros(P, 3, device="cuda", requires_grad=True)
+    rs = dgr.GaussianRasterizationSettings(image_height=kw["H"], image_width=kw["W"], tanfovx=kw["tan_fovx"], tanfovy=kw["tan_fovy"], bg=kw["bg"],
+                                           scale_modifier=1.0, viewmatrix=kw["viewmatrix"].view(4, 4), projmatrix=kw["projmatrix"].view(4, 4), sh_degree=0,
+                                           campos=kw["campos"].view(1, 3), prefiltered=False, debug=False)
+    img, radii = dgr.GaussianRasterizer(rs)(means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], colors_precomp=col_leaf.expand(-1, 3),
+                                           scales=leaf["scales"], rotations=leaf["rotations"])
+    assert img.shape == (3, kw["H"], kw["W"]) and radii.dtype == torch.int32 and radii.shape == (P,)
+    w = torch.randn_like(img)
+    (img * w).sum().backward()
+    kw2 = dict(kw); kw2["colors_precomp"] = colors.contiguous()
+    fwd = capi.forward(**kw2)
+    g = capi.backward(fwd, w, **Hh.bwd_kwargs(kw2))
+    torch.cuda.synchronize()
+    assert torch.equal(img, fwd["out_color"]) and torch.equal(radii, fwd["radii"])
+    assert Hh.rel_err(leaf["means3D"].grad.cpu(), g["dL_dmeans3D"].cpu()) < GRAD_TOL
+    assert Hh.rel_err(leaf["scales"].grad.cpu(), g["dL_dscales"].cpu()) < GRAD_TOL
+    assert Hh.rel_err(leaf["rotations"].grad.cpu(), g["dL_drotations"].cpu()) < GRAD_TOL
+    assert Hh.rel_err(leaf["opacities"].grad.cpu(), g["dL_dopacity"].cpu()) < GRAD_TOL
+    assert Hh.rel_err(means2D.grad.cpu(), g["dL_dmeans2D"].cpu()) < GRAD_TOL
+    assert Hh.rel_err(col_leaf.grad.cpu(), g["dL_dcolors"].sum(1, keepdim=True).cpu()) < GRAD_TOL
+
+
+def test_operator_api_with_shs_like_gaussian_renderer():
+    """gaussian_renderer.render() passes shs=[P,16,3] (gaussian_renderer/__init__.py:85-93): dL_dsh flows."""
+    import diff_gaussian_rasterization as dgr
+    d = SCENES["surface_sh3"]()
+    kw = Hh.to_torch_kwargs(d)
+    shs = kw["shs"].clone().requires_grad_(True)
+    m3 = kw["means3D"].clone().requires_grad_(True)
+    rs = dgr.GaussianRasterizationSettings(kw["H"], kw["W"], kw["tan_fovx"], kw["tan_fovy"], kw["bg"], 1.0, kw["viewmatrix"].view(4, 4),
+                                           kw["projmatrix"].view(4, 4), 3, kw["campos"], False, True)  # debug=True: per-stage sync+check path
+    img, radii = dgr.GaussianRasterizer(rs)(means3D=m3, means2D=torch.zeros_like(m3, requires_grad=True), opacities=kw["opacities"], shs=shs,
+                                           scales=kw["scales"], rotations=kw["rotations"])
+    img.square().sum().backward()
+    assert shs.grad.shape == shs.shape and torch.isfinite(shs.grad).all() and shs.grad.abs().max() > 0
+    assert torch.isfinite(m3.grad).all()
+    assert (shs.grad[radii == 0] == 0).all()
+
+
+def test_edge_empty_and_culled():
+    import diff_gaussian_rasterization as dgr
+    dev = "cuda"
+    rs = dgr.GaussianRasterizationSettings(40, 56, 0.5, 0.5, torch.tensor([0.1, 0.2, 0.3], device=dev), 1.0, torch.eye(4, device=dev),
+                                           torch.eye(4, device=dev), 0, torch.zeros(3, device=dev), False, False)
+    r = dgr.GaussianRasterizer(rs)
+    # P == 0: zeros image (rasterize_points.cu:66,81), empty radii
+    z3, z4, z1 = torch.zeros(0, 3, device=dev), torch.zeros(0, 4, device=dev), torch.zeros(0, 1, device=dev)
+    img, radii = r(z3, z3, z1, colors_precomp=z3, scales=z3, rotations=z4)
+    assert img.shape == (3, 40, 56) and float(img.abs().max()) == 0.0 and radii.numel() == 0
+    # every Gaussian behind the near plane: image == background, no instances, zero grads
+    P = 100
+    m = torch.randn(P, 3, device=dev)
+    m[:, 2] = -5.0
+    m.requires_grad_(True)
+    rot = torch.zeros(P, 4, device=dev); rot[:, 0] = 1
+    img, radii = r(m, torch.zeros_like(m), torch.full((P, 1), 0.5, device=dev), colors_precomp=torch.rand(P, 3, device=dev),
+                   scales=torch.full((P, 3), 0.1, device=dev), rotations=rot)
+    assert (radii == 0).all()
+    assert torch.allclose(img, torch.tensor([0.1, 0.2, 0.3], device=dev).view(3, 1, 1).expand_as(img))
+    img.sum().backward()
+    assert float(m.grad.abs().max()) == 0.0
+
+
+def test_mark_visible():
+    d = SCENES["random_closeup_odd"]()
+    kw = Hh.to_torch_kwargs(d)
+    got = capi.mark_visible(kw["means3D"], kw["viewmatrix"], kw["projmatrix"]).cpu().numpy()
+    np.testing.assert_array_equal(got, O.mark_visible(d["means3D"], d["viewmatrix"]))
+    assert 0 < got.sum() < len(got)
+
+
+@pytest.mark.parametrize("P,size", [(7000, 32), (40000, 16)])
+def test_long_tile_lists_sort_paths(P, size):
+    """Tile lists longer than the small sort kernel (4096) and longer than shared memory (24576)."""
+    g = scene.random_gaussians(P, 0, seed=9, scale_range=(0.3, 0.6), extent=0.3)
+    g.opacities[:] = 0.02
+    cam = scene.look_at_camera([0.0, 1.0, 3.0], [0, 1, 0], size, size, fy_over_H=1.0)
+    d = Hh.scene_dict(g, cam, use_sh=False)
+    kw, fwd = run_mine(d)
+    of = O.forward(Hh.oracle_inputs_from_dict(d))
+    assert (of.ranges[:, 1] - of.ranges[:, 0]).max() > (4096 if P < 20000 else 24576)
+    check_forward_against(fwd, kw, dict(of.__dict__), exact_image=False, n_contrib_slack=4)
+
+
+def test_capacity_regrow_path():
+    """A call whose instance count exceeds the provision made from the previous call must still be exact."""
+    small = SCENES["sh_deg1_of_3"]()
+    big = SCENES["random_big_sh2"]()
+    for d in (small, big, small, big):
+        kw, fwd = run_mine(d)
+        of = O.forward(Hh.oracle_inputs_from_dict(d), blend=False)
+        assert fwd["num_rendered"] == of.num_rendered
+        np.testing.assert_array_equal(capi.point_list(fwd).cpu().numpy(), of.point_list.astype(np.int32))
+
+
+def test_full_size_properties():
+    """BASELINE headline size (1M Gaussians, 1920x1080): size-independent properties."""
+    g = scene.surface_gaussians(1_000_000, 3, seed=0)
+    cam = scene.dome_cameras(8, 1920, 1080)[5]
+    d = Hh.scene_dict(g, cam)
+    kw, fwd = run_mine(d)
+    P, W, H = g.P, 1920, 1080
+    geo = capi.unpack_geometry(fwd, P)
+    st = capi.image_state(fwd, W, H)
+    pl = capi.point_list(fwd).long()
+    R = fwd["num_rendered"]
+    assert int(geo["tiles_touched"].sum()) == R == pl.numel()
+    rng = st["ranges"].long()
+    n = rng[:, 1] - rng[:, 0]
+    assert int(n.sum()) == R
+    nz = n > 0
+    order = rng[nz, 0].argsort()
+    starts, lens = rng[nz, 0][order], n[nz][order]
+    tile_ids = torch.arange(rng.shape[0], device="cuda")[nz][order]
+    assert int(starts[0]) == 0 and torch.equal(starts[1:], (starts + lens)[:-1]) and int((starts + lens)[-1]) == R  # ranges tile the list
+    assert bool((tile_ids[1:] > tile_ids[:-1]).all())  # in ascending tile order
+    # per-tile lists are sorted by (depth bits, index): check globally with the tile id of every instance
+    tile_of = torch.repeat_interleave(tile_ids, lens)
+    key = (tile_of << 32) | geo["depths"].view(torch.int32)[pl].long()
+    assert bool((key[1:] >= key[:-1]).all())
+    tie = key[1:] == key[:-1]
+    assert bool((pl[1:][tie] > pl[:-1][tie]).all())
+    # every instance lies in a tile of its Gaussian's rect; counts per Gaussian match tiles_touched
+    assert torch.equal(torch.bincount(pl, minlength=P).int(), geo["tiles_touched"])
+    out = fwd["out_color"]
+    assert torch.isfinite(out).all() and float(st["final_T"].min()) >= 0 and float(st["final_T"].max()) <= 1
+    # idempotence: a second call is bit-identical (deterministic forward)
+    _, fwd2 = run_mine(d)
+    assert torch.equal(fwd2["out_color"], out) and torch.equal(capi.point_list(fwd2).long(), pl)
+    # linearity of the backward in the upstream gradient
+    dpix = torch.randn(3, H, W, device="cuda") / (W * H)
+    g1 = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
+    g2 = capi.backward(fwd, 2.0 * dpix, **Hh.bwd_kwargs(kw))
+    for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales"):
+        assert torch.isfinite(g1[k]).all()
+        assert Hh.rel_err((2.0 * g1[k]).cpu(), g2[k].cpu()) < 1e-4, k
