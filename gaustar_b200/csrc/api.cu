@@ -80,6 +80,7 @@ int get_ctx(DevCtx** out)
         CU_OK(cudaHostGetDevicePointer((void**)&c.host_counts_dev, c.host_counts, 0));
         CU_OK(cudaEventCreateWithFlags(&c.scan_done, cudaEventDisableTiming));
         CU_OK((cudaError_t)gstar::tile_sort_setup());
+        CU_OK((cudaError_t)gstar::preprocess_setup());
         c.inited = true;
     }
     *out = &c;
@@ -88,7 +89,7 @@ int get_ctx(DevCtx** out)
 
 // ---- private layouts of the three opaque buffers ----
 struct ImgLayout {
-    size_t hdr, final_T, n_contrib, ranges, tile_count, tile_cursor, big_tiles, total;
+    size_t hdr, final_T, n_contrib, ranges, tile_count, tile_cursor, big_tiles, tile_order, total;
 };
 ImgLayout img_layout(int W, int H)
 {
@@ -103,6 +104,7 @@ ImgLayout img_layout(int W, int H)
     L.tile_count = o; o = align_up(o + T * 4, 128);
     L.tile_cursor = o; o = align_up(o + T * 4, 128);
     L.big_tiles = o; o = align_up(o + T * 4, 128);
+    L.tile_order = o; o = align_up(o + T * 4, 128);
     L.total = o;
     return L;
 }
@@ -214,11 +216,12 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bp.tile_cursor = (uint32_t*)(img + IL.tile_cursor);
     bp.ranges = (uint32_t*)(img + IL.ranges);
     bp.big_tiles = (uint32_t*)(img + IL.big_tiles);
+    bp.tile_order = (uint32_t*)(img + IL.tile_order);
     bp.host_counts = ctx->host_counts_dev;
 
     BlendParams bl;
     bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
-    bl.recs = (const GRec*)geom; bl.hdr = hdr; bl.ranges = bp.ranges; bl.bg = a->background;
+    bl.recs = (const GRec*)geom; bl.hdr = hdr; bl.ranges = bp.ranges; bl.tile_order = bp.tile_order; bl.bg = a->background;
     bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
     bl.dL_dpix = nullptr; bl.gacc = nullptr;
 
@@ -307,6 +310,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
         bl.recs = (const GRec*)geom; bl.hdr = (const GHeader*)(img + IL.hdr);
         bl.ranges = (const uint32_t*)(img + IL.ranges);
+        bl.tile_order = (const uint32_t*)(img + IL.tile_order);
         bl.point_list = (const uint32_t*)aligned128(a->binning_buffer);
         bl.bg = a->background;
         bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);

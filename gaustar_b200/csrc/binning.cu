@@ -19,21 +19,51 @@ namespace gstar {
 
 constexpr int SCAN_THREADS = 1024;
 constexpr uint32_t SORT_SMALL_CAP = 4096;          // keys (32 KB) handled by the 256-thread kernel
-constexpr uint32_t SORT_BIG_CAP = 24576;           // keys (192 KB) handled in shared memory by the big kernel
+constexpr uint32_t SORT_BIG_CAP = 16384;           // keys (128 KB, a power of two) per shared-memory chunk of the big kernel
 constexpr int SORT_BIG_THREADS = 1024;
+constexpr int LPT_BUCKETS = 132;                   // quarter-octave size classes for the longest-first tile order
+
+__device__ __forceinline__ int lpt_bucket(uint32_t c)
+{
+    if (c == 0) return 0;
+    const int lg = 31 - __clz(c);
+    const int sub = (int)((c >> max(lg - 2, 0)) & 3u);
+    return 1 + lg * 4 + sub;
+}
+
+// One atomic per distinct tile per warp instead of one per lane: neighbouring Gaussians of a mesh land in
+// the same tile, so plain per-lane atomics serialise on a handful of addresses.  Returns the lane's slot.
+__device__ __forceinline__ uint32_t warp_aggregated_add(uint32_t* counters, uint32_t tile, bool active)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, active ? tile : 0xffffffffu);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (active && (int)lane == leader) base = atomicAdd(counters + tile, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
 
 // ---- K2: exclusive scan over the per-tile histogram; one CTA --------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
 {
     __shared__ uint32_t s_part[SCAN_THREADS];
     __shared__ uint32_t s_nbig, s_max;
+    __shared__ uint32_t s_hist[LPT_BUCKETS];
     const int tid = threadIdx.x;
     const int T = p.num_tiles;
     const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
     const int t0 = tid * per, t1 = min(T, t0 + per);
     if (tid == 0) { s_nbig = 0; s_max = 0; }
+    for (int b = tid; b < LPT_BUCKETS; b += SCAN_THREADS) s_hist[b] = 0;
+    __syncthreads();
     uint32_t sum = 0, mx = 0;
-    for (int t = t0; t < t1; t++) { const uint32_t c = p.tile_count[t]; sum += c; mx = max(mx, c); }
+    for (int t = t0; t < t1; t++) {
+        const uint32_t c = p.tile_count[t];
+        sum += c;
+        mx = max(mx, c);
+        atomicAdd(&s_hist[lpt_bucket(c)], 1u);
+    }
     s_part[tid] = sum;
     __syncthreads();
     // Hillis-Steele inclusive scan of 1024 partials
@@ -56,6 +86,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         run += c;
     }
     __syncthreads();
+    // longest-processing-time-first order of the tiles for the blend kernels: counting sort on the size class,
+    // largest class first; empty tiles last (the forward still has to paint them with the background)
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int b = LPT_BUCKETS - 1; b >= 0; b--) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }
+    }
+    __syncthreads();
+    for (int t = t0; t < t1; t++) p.tile_order[atomicAdd(&s_hist[lpt_bucket(p.tile_count[t])], 1u)] = (uint32_t)t;
     if (tid == 0) {
         const uint32_t total = s_part[SCAN_THREADS - 1];
         const uint32_t ovf = total > p.capacity ? 1u : 0u;
@@ -93,13 +131,15 @@ __global__ void __launch_bounds__(256) k_emit(BinParams p)
     uint2* ent = p.entries;
     const int gx = p.gx;
     const unsigned lane = threadIdx.x & 31;
-    // small rects: every lane scatters its own <=4 instances
-    if (vis && w * h <= 4) {
-        for (uint32_t t = 0; t < w * h; t++) {
-            const uint32_t tile = (miny + t / w) * gx + (minx + t % w);
-            const uint32_t slot = atomicAdd(cur + tile, 1u);
-            ent[slot] = make_uint2((uint32_t)idx, dbits);
-        }
+    // small rects (<= 4 tiles): warp-aggregated slot allocation, one atomic per distinct tile per warp
+    const bool small = vis && w * h <= 4;
+    const uint32_t nsmall = small ? w * h : 0u;
+    const uint32_t rounds = __reduce_max_sync(0xffffffffu, nsmall);
+    for (uint32_t t = 0; t < rounds; t++) {
+        const bool act = t < nsmall;
+        const uint32_t tile = act ? (miny + t / w) * gx + (minx + t % w) : 0u;
+        const uint32_t slot = warp_aggregated_add(cur, tile, act);
+        if (act) ent[slot] = make_uint2((uint32_t)idx, dbits);
     }
     // large rects: the whole warp drains one Gaussian's rect at a time (warp-cooperative emission)
     unsigned big = __ballot_sync(0xffffffffu, vis && w * h > 4);
@@ -168,8 +208,23 @@ __global__ void __launch_bounds__(256) k_tile_sort(BinParams p)
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)s_keys[i];
 }
 
-// Long tile lists: persistent CTAs with ~192 KB of shared memory pull tiles from the work list; a list
-// that does not even fit there is sorted in place in global memory (L2-resident) by the same network.
+// disperse stages j = jstart, jstart/2, ..., 1 of the network on a (shared-memory) array
+__device__ __forceinline__ void bitonic_disperse(uint64_t* a, uint32_t n, uint32_t jstart, uint32_t pairs, uint32_t tid, uint32_t nthreads)
+{
+    for (uint32_t j = jstart; j > 0; j >>= 1) {
+        const uint32_t jshift = 31 - __clz(j);
+        for (uint32_t t = tid; t < pairs; t += nthreads) {
+            const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
+            if (l < n) cmpxchg(a, i, l);
+        }
+        __syncthreads();
+    }
+}
+
+// Long tile lists: persistent CTAs with 128 KB of shared memory pull tiles from the work list.  A list of up
+// to 16384 keys is sorted entirely in shared memory.  A longer one is sorted chunk-wise in shared memory and
+// finished with the classic hybrid schedule: only the few network stages whose partners lie in different
+// chunks run on global memory (L2-resident), every remaining stage runs on a chunk staged in shared memory.
 __global__ void __launch_bounds__(SORT_BIG_THREADS) k_tile_sort_big(BinParams p)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -177,9 +232,11 @@ __global__ void __launch_bounds__(SORT_BIG_THREADS) k_tile_sort_big(BinParams p)
     __shared__ uint32_t s_work;
     if (p.hdr->overflow) return;
     const uint32_t n_big = p.hdr->n_big;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    constexpr uint32_t CH = SORT_BIG_CAP;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_work = atomicAdd(&p.hdr->big_cursor, 1u);
+        if (tid == 0) s_work = atomicAdd(&p.hdr->big_cursor, 1u);
         __syncthreads();
         const uint32_t wi = s_work;
         if (wi >= n_big) break;
@@ -187,15 +244,52 @@ __global__ void __launch_bounds__(SORT_BIG_THREADS) k_tile_sort_big(BinParams p)
         const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
         const uint32_t n = end - start;
         uint64_t* g = reinterpret_cast<uint64_t*>(p.entries) + start;
-        if (n <= SORT_BIG_CAP) {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = g[i];
+        if (n <= CH) {
+            for (uint32_t i = tid; i < n; i += nt) s_keys[i] = g[i];
             __syncthreads();
-            bitonic_sort(s_keys, n, threadIdx.x, blockDim.x);
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)s_keys[i];
-        } else {
-            bitonic_sort(g, n, threadIdx.x, blockDim.x);
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)g[i];
+            bitonic_sort(s_keys, n, tid, nt);
+            for (uint32_t i = tid; i < n; i += nt) p.point_list[start + i] = (uint32_t)s_keys[i];
+            continue;
         }
+        uint32_t npad = CH;
+        while (npad < n) npad <<= 1;
+        const uint32_t nchunks = (n + CH - 1) / CH;
+        // phase 0: every chunk fully sorted in shared memory
+        for (uint32_t c = 0; c < nchunks; c++) {
+            const uint32_t base = c * CH, m = min(CH, n - base);
+            for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
+            __syncthreads();
+            bitonic_sort(s_keys, m, tid, nt);
+            for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
+            __syncthreads();
+        }
+        // merge levels k = 2*CH .. npad
+        for (uint32_t k = 2 * CH; k <= npad; k <<= 1) {
+            const uint32_t half = k >> 1, hshift = 31 - __clz(half);
+            for (uint32_t t = tid; t < (npad >> 1); t += nt) {  // flip stage (global)
+                const uint32_t blk = t >> hshift, off = t & (half - 1);
+                const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+                if (l < n) cmpxchg(g, i, l);
+            }
+            __syncthreads();
+            for (uint32_t j = k >> 2; j >= CH; j >>= 1) {  // disperse stages that still cross chunks (global)
+                const uint32_t jshift = 31 - __clz(j);
+                for (uint32_t t = tid; t < (npad >> 1); t += nt) {
+                    const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
+                    if (l < n) cmpxchg(g, i, l);
+                }
+                __syncthreads();
+            }
+            for (uint32_t c = 0; c < nchunks; c++) {  // remaining stages j = CH/2 .. 1 are chunk-local (shared)
+                const uint32_t base = c * CH, m = min(CH, n - base);
+                for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
+                __syncthreads();
+                bitonic_disperse(s_keys, m, CH >> 1, CH >> 1, tid, nt);
+                for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = tid; i < n; i += nt) p.point_list[start + i] = (uint32_t)g[i];
     }
 }
 

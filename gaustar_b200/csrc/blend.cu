@@ -52,6 +52,31 @@ __device__ __forceinline__ bool bbox_overlaps(const unsigned char* rec, const Wa
     return bx0 <= g.rx1 && bx1 >= g.rx0 && by0 <= g.ry1 && by1 >= g.ry0;
 }
 
+// Bounding box (absolute pixel coordinates) of the lanes set in `live` (lane = 8*row + col of the warp's 8x4 block).
+// Culling against the box of the pixels that can still change -- instead of the whole block -- is what keeps
+// silhouette tiles cheap: there a handful of never-saturating background pixels would otherwise drag the whole
+// warp through tens of thousands of records that only touch finished pixels.
+struct LiveBox {
+    int x0, x1, y0, y1;
+};
+__device__ __forceinline__ LiveBox live_box(unsigned live, const WarpGeom& g)
+{
+    const unsigned cols = (live | (live >> 8) | (live >> 16) | (live >> 24)) & 0xffu;
+    LiveBox b;
+    b.x0 = g.rx0 + __ffs(cols) - 1;
+    b.x1 = g.rx0 + 31 - __clz(cols);
+    b.y0 = g.ry0 + ((__ffs(live) - 1) >> 3);
+    b.y1 = g.ry0 + ((31 - __clz(live)) >> 3);
+    return b;
+}
+__device__ __forceinline__ bool bbox_overlaps_box(const unsigned char* rec, const LiveBox& b)
+{
+    const uint2 bb = *reinterpret_cast<const uint2*>(rec + 32);
+    const int bx0 = (int)(short)(bb.x & 0xffffu), bx1 = (int)(short)(bb.x >> 16);
+    const int by0 = (int)(short)(bb.y & 0xffffu), by1 = (int)(short)(bb.y >> 16);
+    return bx0 <= b.x1 && bx1 >= b.x0 && by0 <= b.y1 && by1 >= b.y0;
+}
+
 // forward.cu:332-335 in the operation order of the reference SASS
 __device__ __forceinline__ float eval_power(float gx, float gy, float A, float B, float C, float pxf, float pyf, float& dx, float& dy)
 {
@@ -66,7 +91,7 @@ __global__ void __launch_bounds__(256) k_blend_fwd(BlendParams p)
     __shared__ __align__(128) unsigned char s_rec[2][GSTAR_BATCH * RS];
     __shared__ __align__(8) uint64_t s_bar[2];
     if (p.hdr->overflow) return;
-    const int tile = blockIdx.x;
+    const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     const int n = (int)(re - rs);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -112,41 +137,54 @@ __global__ void __launch_bounds__(256) k_blend_fwd(BlendParams p)
                 const unsigned char* buf = s_rec[b & 1];
                 const int cnt = min(GSTAR_BATCH, n - b * GSTAR_BATCH);
                 for (int r0 = 0; r0 < cnt; r0 += 32) {
+                    const unsigned live = __ballot_sync(FULL, !done);
+                    if (live == 0) {
+                        warp_done = true;
+                        break;
+                    }
+                    const LiveBox lb = live_box(live, g);
                     const int j = r0 + lane;
-                    const bool ov = (j < cnt) && bbox_overlaps(buf + j * RS, g);
+                    const bool ov = (j < cnt) && bbox_overlaps_box(buf + j * RS, lb);
                     unsigned m = __ballot_sync(FULL, ov);
+                    // Survivors are taken four at a time: the four alpha evaluations (loads, exp) are independent and
+                    // overlap; only the short T recurrence below is serial.  Same arithmetic, same order per pixel.
                     while (m) {
-                        const int k = __ffs(m) - 1;
-                        m &= m - 1;
-                        const unsigned char* rp = buf + (r0 + k) * RS;
-                        const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
-                        const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
-                        const float cb = *reinterpret_cast<const float*>(rp + 40);    // b
-                        if (!done) {
+                        int ks[4];
+                        bool ok[4];
+                        float al[4], cr[4], cg[4], cbv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const bool have = m != 0;
+                            ks[u] = have ? __ffs(m) - 1 : 0;
+                            m &= m - 1;
+                            const unsigned char* rp = buf + (r0 + ks[u]) * RS;
+                            const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
+                            const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
+                            cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
+                            cr[u] = q1.z; cg[u] = q1.w;
                             float dx, dy;
                             const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
-                            if (!(power > 0.0f)) {
-                                const float alpha = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
-                                if (!(alpha < 1.0f / 255.0f)) {
-                                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                                    if (test_T < 0.0001f) {
-                                        done = true;
-                                    } else {
-                                        C0 = __fmaf_rn(T, __fmul_rn(alpha, q1.z), C0);
-                                        C1 = __fmaf_rn(T, __fmul_rn(alpha, q1.w), C1);
-                                        C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
-                                        T = test_T;
-                                        last = (uint32_t)(b * GSTAR_BATCH + r0 + k + 1);
-                                    }
+                            al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
+                            ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (ok[u] && !done) {
+                                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
+                                if (test_T < 0.0001f) {
+                                    done = true;
+                                } else {
+                                    C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
+                                    C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
+                                    C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
+                                    T = test_T;
+                                    last = (uint32_t)(b * GSTAR_BATCH + r0 + ks[u] + 1);
                                 }
                             }
                         }
                     }
-                    if (__all_sync(FULL, done)) {
-                        warp_done = true;
-                        break;
-                    }
                 }
+                if (!warp_done && __all_sync(FULL, done)) warp_done = true;
             }
             all_done = __syncthreads_and(warp_done);
         }
@@ -177,7 +215,7 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_kmax;
     if (p.hdr->overflow) return;
-    const int tile = blockIdx.x;
+    const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     if (re == rs) return;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -236,69 +274,91 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
         const int kbase = total - 1 - b * GSTAR_BATCH;
         if (kbase - (cnt - 1) < warp_kmax) {  // some entry of this batch is in front of this warp's last contributor
             for (int r0 = 0; r0 < cnt; r0 += 32) {
+                // pixels that can receive gradient from some entry of this round: last_contributor > smallest k of the round
+                const unsigned live = __ballot_sync(FULL, last_contributor > kbase - r0 - 31);
+                if (live == 0) continue;
+                const LiveBox lb = live_box(live, g);
                 const int j = r0 + lane;
-                const bool ov = (j < cnt) && (kbase - j < warp_kmax) && bbox_overlaps(buf + j * RS, g);
+                const bool ov = (j < cnt) && (kbase - j < warp_kmax) && bbox_overlaps_box(buf + j * RS, lb);
                 unsigned m = __ballot_sync(FULL, ov);
+                // Survivors are taken two at a time (A = further back, then B): the two alpha evaluations overlap, the
+                // per-pixel state is advanced A then B exactly as the reference does, and both records' nine partial
+                // sums go through ONE 16-value butterfly (lanes 0-15 end up with A's sums, 16-31 with B's).
                 while (m) {
-                    const int s = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int slot = r0 + s;
-                    const int k = kbase - slot;  // == reference `contributor` after its decrement
-                    const unsigned char* rp = buf + slot * RS;
-                    const float4 q0 = *reinterpret_cast<const float4*>(rp);
-                    const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);
-                    const float cb = *reinterpret_cast<const float*>(rp + 40);
-                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
-                    bool contrib = false;
-                    if (k < last_contributor) {
-                        float dx, dy;
-                        const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
-                        if (!(power > 0.0f)) {
-                            const float G = expf(power);
-                            const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                contrib = true;
-                                T = __fdiv_rn(T, __fsub_rn(1.f, alpha));
-                                const float dchannel_dcolor = alpha * T;
-                                float dL_dalpha = 0.0f;
-                                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = q1.z; dL_dalpha += (q1.z - acc0) * dpx0;
-                                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = q1.w; dL_dalpha += (q1.w - acc1) * dpx1;
-                                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cb;   dL_dalpha += (cb - acc2) * dpx2;
-                                v5 = dchannel_dcolor * dpx0;
-                                v6 = dchannel_dcolor * dpx1;
-                                v7 = dchannel_dcolor * dpx2;
-                                dL_dalpha *= T;
-                                last_alpha = alpha;
-                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                                const float dL_dG = q1.y * dL_dalpha;
-                                const float gdx = G * dx, gdy = G * dy;
-                                const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-                                const float dG_ddely = -gdy * q1.x - gdx * q0.w;
-                                v0 = dL_dG * dG_ddelx * ddelx_dx;
-                                v1 = dL_dG * dG_ddely * ddely_dy;
-                                v2 = -0.5f * gdx * dx * dL_dG;
-                                v3 = -0.5f * gdx * dy * dL_dG;
-                                v4 = -0.5f * gdy * dy * dL_dG;
-                                v8 = G * dL_dalpha;
-                            }
+                    int slot[2];
+                    bool pass[2];
+                    float G[2], alpha[2], ddx[2], ddy[2];
+                    float4 q0[2], q1[2];
+                    float cbv[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const bool have = m != 0;
+                        slot[u] = r0 + (have ? __ffs(m) - 1 : 0);
+                        m &= m - 1;
+                        const unsigned char* rp = buf + slot[u] * RS;
+                        q0[u] = *reinterpret_cast<const float4*>(rp);
+                        q1[u] = *reinterpret_cast<const float4*>(rp + 16);
+                        cbv[u] = *reinterpret_cast<const float*>(rp + 40);
+                        const float power = eval_power(q0[u].x, q0[u].y, q0[u].z, q0[u].w, q1[u].x, pxf, pyf, ddx[u], ddy[u]);
+                        G[u] = expf(power);
+                        alpha[u] = fminf(0.99f, __fmul_rn(q1[u].y, G[u]));
+                        // kbase - slot == the reference's `contributor` after its decrement (backward.cu:486-488)
+                        pass[u] = have && (kbase - slot[u] < last_contributor) && !(power > 0.0f) && !(alpha[u] < 1.0f / 255.0f);
+                    }
+                    float v[2][9];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) v[u][c] = 0.f;
+                        if (pass[u]) {
+                            const float al = alpha[u], dx = ddx[u], dy = ddy[u];
+                            T = __fdiv_rn(T, __fsub_rn(1.f, al));
+                            const float dchannel_dcolor = al * T;
+                            float dL_dalpha = 0.0f;
+                            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = q1[u].z; dL_dalpha += (q1[u].z - acc0) * dpx0;
+                            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = q1[u].w; dL_dalpha += (q1[u].w - acc1) * dpx1;
+                            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cbv[u];  dL_dalpha += (cbv[u] - acc2) * dpx2;
+                            v[u][5] = dchannel_dcolor * dpx0;
+                            v[u][6] = dchannel_dcolor * dpx1;
+                            v[u][7] = dchannel_dcolor * dpx2;
+                            dL_dalpha *= T;
+                            last_alpha = al;
+                            dL_dalpha += (-T_final / (1.f - al)) * bg_dot;
+                            const float dL_dG = q1[u].y * dL_dalpha;
+                            const float gdx = G[u] * dx, gdy = G[u] * dy;
+                            const float dG_ddelx = -gdx * q0[u].z - gdy * q0[u].w;
+                            const float dG_ddely = -gdy * q1[u].x - gdx * q0[u].w;
+                            v[u][0] = dL_dG * dG_ddelx * ddelx_dx;
+                            v[u][1] = dL_dG * dG_ddely * ddely_dy;
+                            v[u][2] = -0.5f * gdx * dx * dL_dG;
+                            v[u][3] = -0.5f * gdx * dy * dL_dG;
+                            v[u][4] = -0.5f * gdy * dy * dL_dG;
+                            v[u][8] = G[u] * dL_dalpha;
                         }
                     }
-                    if (__any_sync(FULL, contrib)) {
-                        // 8 values: three halving exchange steps, then two plain steps; lane 4*i ends with sum of v_i
-                        const float w0 = bfly_pair(v0, v4, 16, lane), w1 = bfly_pair(v1, v5, 16, lane);
-                        const float w2 = bfly_pair(v2, v6, 16, lane), w3 = bfly_pair(v3, v7, 16, lane);
-                        const float u0 = bfly_pair(w0, w2, 8, lane), u1 = bfly_pair(w1, w3, 8, lane);
-                        float t = bfly_pair(u0, u1, 4, lane);
-                        t += __shfl_xor_sync(FULL, t, 2);
+                    const unsigned anyA = __ballot_sync(FULL, pass[0]), anyB = __ballot_sync(FULL, pass[1]);
+                    if (anyA | anyB) {
+                        float x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) x[c] = bfly_pair(v[0][c], v[1][c], 16, lane);
+                        const float y0 = bfly_pair(x[0], x[4], 8, lane), y1 = bfly_pair(x[1], x[5], 8, lane);
+                        const float y2 = bfly_pair(x[2], x[6], 8, lane), y3 = bfly_pair(x[3], x[7], 8, lane);
+                        const float z0 = bfly_pair(y0, y2, 4, lane), z1 = bfly_pair(y1, y3, 4, lane);
+                        float t = bfly_pair(z0, z1, 2, lane);
                         t += __shfl_xor_sync(FULL, t, 1);
-                        v8 += __shfl_xor_sync(FULL, v8, 16);
-                        v8 += __shfl_xor_sync(FULL, v8, 8);
-                        v8 += __shfl_xor_sync(FULL, v8, 4);
-                        v8 += __shfl_xor_sync(FULL, v8, 2);
-                        v8 += __shfl_xor_sync(FULL, v8, 1);
-                        float* dst = p.gacc + (size_t)ids[slot] * GSTAR_GACC;
-                        if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), t);
-                        else if (lane == 1) atomicAdd(dst + 8, v8);
+                        float o = bfly_pair(v[0][8], v[1][8], 16, lane);
+                        o += __shfl_xor_sync(FULL, o, 8);
+                        o += __shfl_xor_sync(FULL, o, 4);
+                        o += __shfl_xor_sync(FULL, o, 2);
+                        o += __shfl_xor_sync(FULL, o, 1);
+                        // lane L: record = L>>4, value index = 4*bit3 + 2*bit2 + bit1
+                        const int rsel = lane >> 4;
+                        const bool any_mine = rsel ? (anyB != 0) : (anyA != 0);
+                        if (any_mine) {
+                            float* dst = p.gacc + (size_t)ids[slot[rsel]] * GSTAR_GACC;
+                            if ((lane & 1) == 0) atomicAdd(dst + (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)), t);
+                            else if ((lane & 15) == 1) atomicAdd(dst + 8, o);
+                        }
                     }
                 }
             }

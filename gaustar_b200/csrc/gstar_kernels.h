@@ -62,6 +62,7 @@ struct BinParams {
     uint32_t* tile_cursor; // [T] running write position per tile
     uint32_t* ranges;      // [T][2]
     uint32_t* big_tiles;   // [T] worklist of tiles too long for the small sort kernel
+    uint32_t* tile_order;  // [T] all tiles, longest list first (work order of the blend kernels)
     uint2* entries;        // [capacity] (depth bits, idx), tile-segmented
     uint32_t* point_list;  // [capacity] sorted gaussian ids
     uint32_t capacity;
@@ -74,6 +75,7 @@ struct BlendParams {
     const GHeader* hdr;
     const uint32_t* ranges;
     const uint32_t* point_list;
+    const uint32_t* tile_order;
     const float* bg;
     // forward
     float* out_color;
@@ -94,6 +96,7 @@ void launch_tile_scan(const BinParams& p, cudaStream_t s);
 void launch_emit(const BinParams& p, cudaStream_t s);
 void launch_tile_sort(const BinParams& p, cudaStream_t s);
 int  tile_sort_setup();  // one-time cudaFuncSetAttribute calls; returns cudaError_t
+int  preprocess_setup();
 
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s);
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s);

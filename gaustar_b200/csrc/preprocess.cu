@@ -114,29 +114,84 @@ __device__ __forceinline__ void get_rect(float px, float py, int radius, int gx,
     maxy = min((uint32_t)gy, (uint32_t)max(0, (int)__fmul_rn(__fsub_rn(__fadd_rn(__fadd_rn(py, r), 16.0f), 1.0f), 0.0625f)));
 }
 
-// forward.cu:20-71. sh points at this Gaussian's [M][3] coefficients.
-__device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restrict__ sh, float3 pos, float3 campos, uint32_t& clamp_bits)
+// ---- SH rows staged through shared memory ------------------------------------------------------------
+// A Gaussian's SH row is 12*M contiguous bytes (192 B for degree 3).  One thread per Gaussian reading its
+// own row touches 32 different cache lines per load instruction; instead each warp copies the 32 rows of
+// its Gaussians with fully coalesced loads into padded shared-memory rows (stride 3M+4 floats when rows
+// are 16-byte aligned, else 3M+1: both conflict-free for one-row-per-lane access) and every lane then
+// reads -- and in the backward pass overwrites with dL_dsh -- only its own row.
+constexpr int SH_MAX_M = 16;
+constexpr int SH_ROW_STRIDE_MAX = 3 * SH_MAX_M + 4;                 // floats
+constexpr int SH_WARP_FLOATS = 32 * SH_ROW_STRIDE_MAX;              // per warp
+constexpr int SH_SMEM_BYTES = 8 * SH_WARP_FLOATS * (int)sizeof(float);  // per 256-thread CTA
+
+struct ShStage {
+    float* rows;   // this warp's shared-memory region
+    int stride;    // floats between rows
+    bool vec;      // rows are 16-byte aligned multiples of 16 bytes
+};
+
+__device__ __forceinline__ ShStage sh_stage_make(float* smem_cta, const float* shs, int M)
+{
+    ShStage st;
+    st.rows = smem_cta + (threadIdx.x >> 5) * SH_WARP_FLOATS;
+    st.vec = ((3 * M) % 4 == 0) && ((((size_t)shs) & 15) == 0);
+    st.stride = st.vec ? 3 * M + 4 : 3 * M + 1;
+    return st;
+}
+
+// coalesced global -> shared copy of the rows selected by need_mask (bit g = row of lane g)
+__device__ __forceinline__ void sh_stage_load(const ShStage& st, const float* __restrict__ shs, int M, long long first_row, int P, unsigned need_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const int rowf = 3 * M;
+    const float* base = shs + (size_t)first_row * rowf;
+    if (st.vec) {
+        const int row4 = rowf >> 2, str4 = st.stride >> 2;
+        const float4* b4 = reinterpret_cast<const float4*>(base);
+        float4* r4 = reinterpret_cast<float4*>(st.rows);
+        for (int q = lane; q < 32 * row4; q += 32) {
+            const int g = q / row4, j = q - g * row4;
+            if (((need_mask >> g) & 1u) && first_row + g < P) r4[g * str4 + j] = ldg_nc_f4(b4 + q);
+        }
+    } else {
+        for (int q = lane; q < 32 * rowf; q += 32) {
+            const int g = q / rowf, j = q - g * rowf;
+            if (((need_mask >> g) & 1u) && first_row + g < P) st.rows[g * st.stride + j] = __ldg(base + q);
+        }
+    }
+    __syncwarp();
+}
+
+// coalesced shared -> global copy of all rows (dL_dsh is fully overwritten)
+__device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restrict__ dst, int M, long long first_row, int P)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int rowf = 3 * M;
+    float* base = dst + (size_t)first_row * rowf;
+    if (st.vec && ((((size_t)dst) & 15) == 0)) {
+        const int row4 = rowf >> 2, str4 = st.stride >> 2;
+        float4* b4 = reinterpret_cast<float4*>(base);
+        const float4* r4 = reinterpret_cast<const float4*>(st.rows);
+        for (int q = lane; q < 32 * row4; q += 32) {
+            const int g = q / row4, j = q - g * row4;
+            if (first_row + g < P) b4[q] = r4[g * str4 + j];
+        }
+    } else {
+        for (int q = lane; q < 32 * rowf; q += 32) {
+            const int g = q / rowf, j = q - g * rowf;
+            if (first_row + g < P) base[q] = st.rows[g * st.stride + j];
+        }
+    }
+}
+
+// forward.cu:20-71.  `c` = this Gaussian's coefficients [M][3] (shared-memory row or global memory).
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* c, float3 pos, float3 campos, uint32_t& clamp_bits)
 {
     float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
     const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
     dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
-    // 128-bit loads of the coefficient row (row is 12*M bytes, M in {1,4,9,16}: 16B aligned only for M%4==0)
-    float c[48];
-    const int nfl = 3 * (deg + 1) * (deg + 1);
-    // vector path only when the padded read stays inside this Gaussian's own row
-    if ((((size_t)sh) & 15) == 0 && 4 * ((nfl + 3) / 4) <= 3 * M) {
-        const float4* s4 = reinterpret_cast<const float4*>(sh);
-#pragma unroll
-        for (int i = 0; i < 12; i++)
-            if (4 * i < nfl) {
-                const float4 v = ldg_nc_f4(s4 + i);
-                c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
-            }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 48; i++)
-            if (i < nfl) c[i] = __ldg(sh + i);
-    }
 #define SHK(k) make_float3(c[3 * (k)], c[3 * (k) + 1], c[3 * (k) + 2])
 #define ACC(w, k) { const float w_ = (w); const float3 s_ = SHK(k); res.x += w_ * s_.x; res.y += w_ * s_.y; res.z += w_ * s_.z; }
     float3 res = {c_SH_C0 * c[0], c_SH_C0 * c[1], c_SH_C0 * c[2]};
@@ -170,34 +225,15 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restr
     return make_float3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
 }
 
-// One warp walks the tile rect of every lane whose rect is larger than `small_limit`, so a huge
-// splat costs the warp ceil(area/32) iterations instead of stalling one lane for `area` iterations.
-template <typename F>
-__device__ __forceinline__ void for_each_tile_warp(bool active, uint32_t minx, uint32_t miny, uint32_t w, uint32_t h, F&& f)
-{
-    const uint32_t area = w * h;
-    const unsigned lane = threadIdx.x & 31;
-    const bool small = active && area <= 4;
-    if (small) {
-        for (uint32_t t = 0; t < area; t++) f(minx + t % w, miny + t / w, t, (int)lane);
-    }
-    unsigned big = __ballot_sync(0xffffffffu, active && area > 4);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t bx = __shfl_sync(0xffffffffu, minx, src), by = __shfl_sync(0xffffffffu, miny, src);
-        const uint32_t bw = __shfl_sync(0xffffffffu, w, src), ba = __shfl_sync(0xffffffffu, area, src);
-        for (uint32_t t = lane; t < ba; t += 32) f(bx + t % bw, by + t / bw, t, src);
-    }
-}
-
 __global__ void __launch_bounds__(256) k_preprocess_fwd(PreFwdParams p)
 {
+    extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_vm[16], s_pm[16];
     if (threadIdx.x < 16) s_vm[threadIdx.x] = p.viewmatrix[threadIdx.x];
     else if (threadIdx.x < 32) s_pm[threadIdx.x - 16] = p.projmatrix[threadIdx.x - 16];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
     const bool valid = idx < p.P;
     GRec rec;
     {
@@ -207,9 +243,10 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(PreFwdParams p)
     }
     uint32_t minx = 0, miny = 0, maxx = 0, maxy = 0;
     bool visible = false;
+    float px = 0.f, py = 0.f, pz = 0.f;
     if (valid) {
         do {
-            const float px = p.means3D[3 * idx], py = p.means3D[3 * idx + 1], pz = p.means3D[3 * idx + 2];
+            px = p.means3D[3 * (size_t)idx]; py = p.means3D[3 * (size_t)idx + 1]; pz = p.means3D[3 * (size_t)idx + 2];
             const float pvz = xform_row(s_vm, 2, px, py, pz);  // auxiliary.h:152-154
             if (pvz <= 0.2f) {
                 if (p.prefiltered) {
@@ -248,48 +285,83 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(PreFwdParams p)
             if ((maxx - minx) * (maxy - miny) == 0) break;
             visible = true;
             const float opac = p.opacities[idx];
-            uint32_t clamp_bits = 0;
-            float3 col;
-            if (p.colors_precomp) {
-                col = make_float3(p.colors_precomp[3 * (size_t)idx], p.colors_precomp[3 * (size_t)idx + 1], p.colors_precomp[3 * (size_t)idx + 2]);
-            } else {
-                col = sh_to_rgb(p.D, p.M, p.shs + (size_t)3 * p.M * idx, make_float3(px, py, pz), make_float3(p.campos[0], p.campos[1], p.campos[2]),
-                                clamp_bits);
-            }
-            // Exact-conservative pixel bounds of {alpha >= 1/255}: alpha = o*exp(-q/2) with q >= dx^2/cov_xx,
-            // so |dx| > sqrt(2 ln(255 o) cov_xx) can never pass the reference's alpha test (forward.cu:343-345).
+            // Exact-conservative pixel bounds of {alpha >= 1/255}: alpha = o*exp(-q/2) with q >= dx^2/cov_xx, so a pixel
+            // with |dx| > sqrt(2 ln(255 o) cov_xx) can never pass the reference's alpha test (forward.cu:343-345).
+            // Margins (1e-3 on the log, 5e-4 relative + 2e-3 px on the extent) dwarf every fp32 rounding involved.
             int bx0 = -32768, bx1 = 32767, by0 = -32768, by1 = 32767;
             if (opac < (1.0f / 255.0f)) {
                 bx0 = 1; bx1 = 0; by0 = 1; by1 = 0;  // o*G <= o < 1/255 : never blended
             } else if (det > 0.0f && cv.a > 0.0f && cv.c > 0.0f && opac <= 1e30f) {
-                const float tau = logf(255.0f * opac) * 1.02f + 0.02f;
-                const float ex = sqrtf(2.0f * tau * cv.a) * 1.01f + 0.51f;
-                const float ey = sqrtf(2.0f * tau * cv.c) * 1.01f + 0.51f;
+                const float tau = logf(255.0f * opac) * 1.001f + 0.001f;
+                const float ex = sqrtf(2.0f * tau * cv.a) * 1.0005f + 0.002f;
+                const float ey = sqrtf(2.0f * tau * cv.c) * 1.0005f + 0.002f;
                 bx0 = (int)fmaxf(-32768.f, fminf(32767.f, ceilf(pix - ex)));
                 bx1 = (int)fmaxf(-32768.f, fminf(32767.f, floorf(pix + ex)));
                 by0 = (int)fmaxf(-32768.f, fminf(32767.f, ceilf(piy - ey)));
                 by1 = (int)fmaxf(-32768.f, fminf(32767.f, floorf(piy + ey)));
             }
             rec.x = pix; rec.y = piy; rec.A = conx; rec.B = cony; rec.C = conz; rec.o = opac;
-            rec.r = col.x; rec.g = col.y; rec.b = col.z;
             rec.bbox_x = ((uint32_t)bx0 & 0xffffu) | ((uint32_t)bx1 << 16);
             rec.bbox_y = ((uint32_t)by0 & 0xffffu) | ((uint32_t)by1 << 16);
-            rec.flags = clamp_bits;
             rec.depth = pvz;
             rec.rect_min = minx | (miny << 16);
             rec.rect_max = maxx | (maxy << 16);
             rec.radius = radius;
         } while (0);
+    }
+    // colour: colors_precomp, or SH -> RGB with the warp's SH rows staged through shared memory
+    if (p.colors_precomp) {
+        if (visible) {
+            rec.r = p.colors_precomp[3 * (size_t)idx]; rec.g = p.colors_precomp[3 * (size_t)idx + 1]; rec.b = p.colors_precomp[3 * (size_t)idx + 2];
+        }
+    } else {
+        const unsigned need = __ballot_sync(0xffffffffu, visible);
+        const int nfl = 3 * (p.D + 1) * (p.D + 1);
+        const bool staged = p.M <= SH_MAX_M && 2 * nfl >= 3 * p.M;  // reading whole rows pays off only if most of a row is used
+        const float3 campos = make_float3(p.campos[0], p.campos[1], p.campos[2]);
+        uint32_t clamp_bits = 0;
+        float3 col = {0.f, 0.f, 0.f};
+        if (staged) {
+            if (need) {
+                const ShStage st = sh_stage_make(s_sh, p.shs, p.M);
+                sh_stage_load(st, p.shs, p.M, (long long)idx - lane, p.P, need);
+                if (visible) col = sh_to_rgb(p.D, st.rows + lane * st.stride, make_float3(px, py, pz), campos, clamp_bits);
+            }
+        } else if (visible) {
+            float c[48];
+            const float* sh = p.shs + (size_t)3 * p.M * idx;
+            for (int i = 0; i < 48; i++)
+                if (i < nfl) c[i] = __ldg(sh + i);
+            col = sh_to_rgb(p.D, c, make_float3(px, py, pz), campos, clamp_bits);
+        }
+        if (visible) { rec.r = col.x; rec.g = col.y; rec.b = col.z; rec.flags = clamp_bits; }
+    }
+    if (valid) {
         float4* dst = reinterpret_cast<float4*>(p.recs + idx);
         const float4* src = reinterpret_cast<const float4*>(&rec);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
         p.radii[idx] = rec.radius;
     }
-    // per-tile histogram (first digit of the MSD tile|depth sort)
+    // per-tile histogram (first digit of the MSD tile|depth sort): one atomic per distinct tile per warp
     uint32_t* cnt = p.tile_count;
     const int gx = p.gx;
-    for_each_tile_warp(visible, minx, miny, maxx - minx, maxy - miny,
-                       [&](uint32_t x, uint32_t y, uint32_t, int) { atomicAdd(cnt + y * gx + x, 1u); });
+    const uint32_t w = maxx - minx, h = maxy - miny;
+    const uint32_t nsmall = (visible && w * h <= 4) ? w * h : 0u;
+    const uint32_t rounds = __reduce_max_sync(0xffffffffu, nsmall);
+    for (uint32_t t = 0; t < rounds; t++) {
+        const bool act = t < nsmall;
+        const uint32_t tile = act ? (miny + t / w) * gx + (minx + t % w) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, tile);
+        if (act && (int)lane == __ffs(peers) - 1) atomicAdd(cnt + tile, (uint32_t)__popc(peers));
+    }
+    unsigned big = __ballot_sync(0xffffffffu, visible && w * h > 4);
+    while (big) {  // large rects: the whole warp walks one Gaussian's rect at a time
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t bx = __shfl_sync(0xffffffffu, minx, src), by = __shfl_sync(0xffffffffu, miny, src);
+        const uint32_t bw = __shfl_sync(0xffffffffu, w, src), ba = bw * __shfl_sync(0xffffffffu, h, src);
+        for (uint32_t t = lane; t < ba; t += 32) atomicAdd(cnt + (by + t / bw) * gx + (bx + t % bw), 1u);
+    }
 }
 
 // rasterizer_impl.cu:54-66 checkFrustum
@@ -323,8 +395,10 @@ __global__ void k_geom_unpack(const GRec* __restrict__ recs, int P, float* depth
 // ------------------------------------------------------------------------------------------------
 // K8: fused per-Gaussian backward.  backward.cu:144-274 (cov2D), :346-396 (projection, SH, cov3D).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sh_backward(int deg, int M, const float* __restrict__ sh, float3 pos, float3 campos, uint32_t clamp_bits,
-                                            float3 dL_dcolor, float3& dmean_add, float* __restrict__ dL_dsh)
+// `sh` and `dL_dsh` may alias (the staged shared-memory row is overwritten in place: every coefficient is
+// read before the first gradient is written)
+__device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, float3 pos, float3 campos, uint32_t clamp_bits,
+                                            float3 dL_dcolor, float3& dmean_add, float* dL_dsh)
 {
     const float3 dorig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
     const float len = sqrtf(dorig.x * dorig.x + dorig.y * dorig.y + dorig.z * dorig.z);
@@ -335,7 +409,7 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* __restr
     if (clamp_bits & 4) g.z = 0;
     float3 dx = {0, 0, 0}, dy = {0, 0, 0}, dz = {0, 0, 0};
     float w[16];
-#define SHK(k) make_float3(__ldg(sh + 3 * (k)), __ldg(sh + 3 * (k) + 1), __ldg(sh + 3 * (k) + 2))
+#define SHK(k) make_float3(sh[3 * (k)], sh[3 * (k) + 1], sh[3 * (k) + 2])
 #define AXPY(d, a, v) { const float a_ = (a); d.x += a_ * v.x; d.y += a_ * v.y; d.z += a_ * v.z; }
     w[0] = c_SH_C0;
     if (deg > 0) {
@@ -388,17 +462,29 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* __restr
 
 __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
 {
+    extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_vm[16], s_pm[16];
     if (threadIdx.x < 16) s_vm[threadIdx.x] = p.viewmatrix[threadIdx.x];
     else if (threadIdx.x < 32) s_pm[threadIdx.x - 16] = p.projmatrix[threadIdx.x - 16];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
-    const size_t i = (size_t)idx;
+    const unsigned lane = threadIdx.x & 31;
+    const bool valid = idx < p.P;
+    const size_t i = (size_t)(valid ? idx : 0);
     const int M = p.M;
     const float* vm = s_vm;
     const float* proj = s_pm;
-    const int radius = p.radii ? p.radii[idx] : p.recs[idx].radius;
+    const int radius = valid ? (p.radii ? p.radii[idx] : p.recs[idx].radius) : 0;
+    // SH rows of the warp staged in shared memory: coalesced loads now, coalesced dL_dsh stores at the end
+    const bool sh_staged = p.shs && p.dL_dsh && M > 0 && M <= SH_MAX_M;
+    ShStage st;
+    st.rows = nullptr; st.stride = 0; st.vec = false;
+    if (sh_staged) {
+        st = sh_stage_make(s_sh, p.shs, M);
+        const unsigned need = __ballot_sync(0xffffffffu, valid && radius > 0 && p.D > 0);
+        if (need) sh_stage_load(st, p.shs, M, (long long)idx - lane, p.P, need);
+    }
+    if (valid) {
     float acc[9];
     {
         const float4* a4 = reinterpret_cast<const float4*>(p.gacc + i * GSTAR_GACC);
@@ -476,8 +562,10 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
         dmean[2] += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
         if (p.shs) {
             float3 add;
-            sh_backward(p.D, M, p.shs + (size_t)3 * M * i, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]),
-                        p.recs[idx].flags, make_float3(acc[5], acc[6], acc[7]), add, p.dL_dsh + (size_t)3 * M * i);
+            const float* sh_in = sh_staged ? st.rows + lane * st.stride : p.shs + (size_t)3 * M * i;
+            float* sh_out = sh_staged ? st.rows + lane * st.stride : p.dL_dsh + (size_t)3 * M * i;
+            sh_backward(p.D, M, sh_in, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]), p.recs[idx].flags,
+                        make_float3(acc[5], acc[6], acc[7]), add, sh_out);
             dmean[0] += add.x; dmean[1] += add.y; dmean[2] += add.z;
         }
         if (p.scales) {
@@ -510,7 +598,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
             drot[3] = 2 * r * (D[0][1] - D[1][0]) + 2 * x * (D[2][0] + D[0][2]) + 2 * y * (D[1][2] + D[2][1]) - 4 * z * (D[1][1] + D[0][0]);
         }
     } else if (p.dL_dsh) {
-        float* d = p.dL_dsh + (size_t)3 * M * i;
+        float* d = sh_staged ? st.rows + lane * st.stride : p.dL_dsh + (size_t)3 * M * i;
         for (int k = 0; k < 3 * M; k++) d[k] = 0.f;
     }
     p.dL_dmean3D[3 * i] = dmean[0]; p.dL_dmean3D[3 * i + 1] = dmean[1]; p.dL_dmean3D[3 * i + 2] = dmean[2];
@@ -518,10 +606,26 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
     for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
     if (p.dL_dscale) { p.dL_dscale[3 * i] = dscale[0]; p.dL_dscale[3 * i + 1] = dscale[1]; p.dL_dscale[3 * i + 2] = dscale[2]; }
     if (p.dL_drot) *reinterpret_cast<float4*>(p.dL_drot + 4 * i) = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    }  // valid
+    if (sh_staged) sh_stage_store(st, p.dL_dsh, M, (long long)idx - lane, p.P);
 }
 
-void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s) { k_preprocess_fwd<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
-void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s) { k_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
+int preprocess_setup()
+{
+    cudaError_t e = cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES);
+}
+void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s)
+{
+    const int smem = (p.shs && !p.colors_precomp) ? SH_SMEM_BYTES : 0;
+    k_preprocess_fwd<<<(p.P + 255) / 256, 256, smem, s>>>(p);
+}
+void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s)
+{
+    const int smem = (p.shs && p.dL_dsh) ? SH_SMEM_BYTES : 0;
+    k_preprocess_bwd<<<(p.P + 255) / 256, 256, smem, s>>>(p);
+}
 void launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present, cudaStream_t s)
 {
     k_mark_visible<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vm, present);

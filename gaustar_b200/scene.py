@@ -29,29 +29,85 @@ _BARY6 = np.array(
 _CIRCLE_RADIUS6 = 1.0 / (4.0 + 2.0 * math.sqrt(3.0))
 
 
-def capsule_mesh(n_faces: int, seed: int = 0, radius: float = 0.35, stretch_y: float = 1.8, center=(0.0, 1.0, 0.0)):
-    """Closed genus-0 'capsule' (UV sphere stretched in y) with exactly n_faces triangles."""
-    # faces of a UV sphere: 2*n_lon*(n_lat-1); pick n_lon ~ 2*n_lat
+def _uv_sphere(n_faces):
+    """Plain UV sphere (constant longitude count): clusters tiny triangles at the poles. Stress-test only."""
     n_lat = max(3, int(math.ceil(math.sqrt(n_faces / 4.0))) + 1)
     n_lon = max(3, int(math.ceil(n_faces / (2.0 * (n_lat - 1)))))
     while 2 * n_lon * (n_lat - 1) < n_faces:
         n_lon += 1
     th = np.linspace(0, np.pi, n_lat + 1)[1:-1]
-    ph = np.linspace(0, 2 * np.pi, n_lon, endpoint=False)
-    ring = np.stack([np.outer(np.sin(th), np.cos(ph)), np.outer(np.cos(th), np.ones_like(ph)), np.outer(np.sin(th), np.sin(ph))], -1)
-    verts = np.concatenate([[[0, 1, 0]], ring.reshape(-1, 3), [[0, -1, 0]]], 0)
+    rings = [np.stack([np.sin(t) * np.cos(ph), np.full_like(ph, np.cos(t)), np.sin(t) * np.sin(ph)], -1)
+             for t in th for ph in [np.linspace(0, 2 * np.pi, n_lon, endpoint=False)]]
+    return rings
+
+
+def _band_sphere(n_faces):
+    """Latitude rings whose vertex count is proportional to sin(latitude): near-uniform triangles everywhere."""
+    L = max(4, int(math.ceil(math.sqrt(n_faces / 1.7))))
+    while True:
+        th = np.linspace(0, np.pi, L + 1)[1:-1]
+        counts = np.maximum(5, np.round(1.3333 * L * np.sin(th)).astype(int))
+        faces = counts[0] + counts[-1] + int((counts[:-1] + counts[1:]).sum())
+        if faces >= n_faces:
+            break
+        L += 1
+    rings = []
+    for i, (t, c) in enumerate(zip(th, counts)):
+        ph = np.linspace(0, 2 * np.pi, c, endpoint=False) + (0.5 * i) * 2 * np.pi / c
+        rings.append(np.stack([np.sin(t) * np.cos(ph), np.full_like(ph, np.cos(t)), np.sin(t) * np.sin(ph)], -1))
+    return rings
+
+
+def _zip_band(off_a, ang_a, off_b, ang_b):
+    """Triangulate the band between two rings with different vertex counts by walking both rings in angle order.
+    ang_* are the ascending longitudes of the rings' vertices in [0, 2pi)."""
+    na, nb = len(ang_a), len(ang_b)
+    # start ring b at its first vertex at or after ring a's first vertex
+    sb = int(np.searchsorted(ang_b, ang_a[0])) % nb
+    ib = (np.arange(nb) + sb) % nb
+    pa = np.concatenate([ang_a - ang_a[0], [2 * np.pi]])
+    pb = np.mod(ang_b[ib] - ang_a[0], 2 * np.pi)
+    pb = np.concatenate([pb, [pb[0] + 2 * np.pi]])
     faces = []
-    idx = lambda i, j: 1 + i * n_lon + (j % n_lon)
-    for j in range(n_lon):
-        faces.append([0, idx(0, j + 1), idx(0, j)])
-    for i in range(n_lat - 2):
-        for j in range(n_lon):
-            faces.append([idx(i, j), idx(i, j + 1), idx(i + 1, j)])
-            faces.append([idx(i, j + 1), idx(i + 1, j + 1), idx(i + 1, j)])
-    last = len(verts) - 1
-    for j in range(n_lon):
-        faces.append([last, idx(n_lat - 2, j), idx(n_lat - 2, j + 1)])
+    i = j = 0
+    while i < na or j < nb:
+        if j >= nb or (i < na and pa[i + 1] <= pb[j + 1]):
+            faces.append([off_a + i % na, off_a + (i + 1) % na, off_b + ib[j % nb]])
+            i += 1
+        else:
+            faces.append([off_a + i % na, off_b + ib[(j + 1) % nb], off_b + ib[j % nb]])
+            j += 1
+    return faces
+
+
+def capsule_mesh(n_faces: int, seed: int = 0, radius: float = 0.35, stretch_y: float = 1.8, center=(0.0, 1.0, 0.0), uniform: bool = True):
+    """Closed genus-0 'capsule' (sphere stretched in y) with exactly n_faces triangles.
+
+    uniform=True (default): latitude bands with vertex count ~ sin(latitude), i.e. near-uniform triangle size like
+    a reconstructed body mesh (TSDF + decimation).  uniform=False: plain UV sphere, whose pole singularity piles
+    thousands of tiny triangles into a few pixels -- kept as a stress test for very long tile lists."""
+    rings = _band_sphere(n_faces) if uniform else _uv_sphere(n_faces)
+    verts = [np.array([[0.0, 1.0, 0.0]])] + rings + [np.array([[0.0, -1.0, 0.0]])]
+    offs = np.cumsum([0] + [len(v) for v in verts])
+    lon = [np.mod(np.arctan2(r[:, 2], r[:, 0]), 2 * np.pi) for r in rings]
+    faces = []
+    n0 = len(rings[0])
+    faces += [[0, offs[1] + (j + 1) % n0, offs[1] + j] for j in range(n0)]
+    for k in range(len(rings) - 1):
+        oa, ob = np.argsort(lon[k]), np.argsort(lon[k + 1])
+        fz = _zip_band(0, lon[k][oa], 1 << 40, lon[k + 1][ob])
+        for tri in fz:
+            faces.append([offs[k + 2] + ob[v - (1 << 40)] if v >= (1 << 40) else offs[k + 1] + oa[v] for v in tri])
+    last = offs[-1] - 1
+    nl = len(rings[-1])
+    faces += [[last, offs[-3] + j, offs[-3] + (j + 1) % nl] for j in range(nl)]
+    verts = np.concatenate(verts, 0)
     faces = np.asarray(faces, dtype=np.int64)
+    # consistent outward orientation
+    fv = verts[faces]
+    nrm = np.cross(fv[:, 1] - fv[:, 0], fv[:, 2] - fv[:, 0])
+    flip = (nrm * fv.mean(1)).sum(-1) < 0
+    faces[flip] = faces[flip][:, [0, 2, 1]]
     rng = np.random.default_rng(seed)
     # drop random surplus faces so the face count is exact (tiny holes; irrelevant to the op)
     if len(faces) > n_faces:
@@ -132,10 +188,10 @@ def bind_gaussians(verts, faces, sh_degree=3, seed=0, opacity="trained", extent=
     return Gaussians(f32(pts), f32(scales), f32(quat), f32(op), f32(shs))
 
 
-def surface_gaussians(P: int, sh_degree=3, seed=0, opacity="trained") -> Gaussians:
+def surface_gaussians(P: int, sh_degree=3, seed=0, opacity="trained", uniform=True) -> Gaussians:
     """ceil(P/6) faces -> 6*ceil(P/6) Gaussians."""
     F = (P + 5) // 6
-    verts, faces = capsule_mesh(F, seed)
+    verts, faces = capsule_mesh(F, seed, uniform=uniform)
     return bind_gaussians(verts, faces, sh_degree, seed, opacity)
 
 
