@@ -4,10 +4,12 @@
 // (DGR/cuda_rasterizer/backward.cu:399-557).  Same per-pixel arithmetic and thresholds
 // (power>0 skip, alpha=min(0.99,o*exp(power)), alpha<1/255 skip, T<1e-4 stop), re-mapped for B200:
 //
-//  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block;
-//  * the tile's depth-sorted Gaussian list is streamed through shared memory in batches of 256
-//    48-byte records, each fetched by its own TMA bulk copy (cp.async.bulk -> UBLKCP) that signals
-//    an mbarrier; two stages, the next batch is in flight while the current one is composited;
+//  * one CTA per 16x16 tile: 8 consumer warps, each owning an 8x4 pixel block, plus one producer warp;
+//  * the tile's depth-sorted Gaussian list is streamed through a 3-stage shared-memory ring in batches of
+//    256 48-byte records, each fetched by its own TMA bulk copy (cp.async.bulk -> UBLKCP) issued by the
+//    producer warp and completing on the stage's `full` mbarrier; consumers release a stage through its
+//    `empty` mbarrier.  There is no __syncthreads in the loop: warps whose pixels need few records (or are
+//    done) run ahead instead of waiting for the slowest warp of the tile at every batch;
 //  * every record carries exact-conservative pixel bounds of {alpha >= 1/255}; a warp first tests 32
 //    records against its 8x4 block (one record per lane + ballot) and only walks the survivors.
 //    Surface Gaussians cover ~5x5 pixels, so ~3/4 of the (record, warp) pairs of a tile are skipped
@@ -23,6 +25,9 @@ namespace gstar {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int RS = GSTAR_REC_SMEM;
+constexpr int NSTAGE = 3;                 // ring depth (3 x 12 KB stays within static shared memory)
+constexpr int NCONS = 8;                  // consumer warps (8x4 pixel blocks of a 16x16 tile)
+constexpr int BLEND_THREADS = (NCONS + 1) * 32;  // + one producer warp
 
 struct WarpGeom {
     int rx0, ry0, rx1, ry1, px, py;
@@ -86,15 +91,45 @@ __device__ __forceinline__ float eval_power(float gx, float gy, float A, float B
     return __fmaf_rn(q, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, B)));
 }
 
-__global__ void __launch_bounds__(256) k_blend_fwd(BlendParams p)
+
+// ---- shared producer: streams records of list positions pos(b, slot) into the ring -------------------------------
+struct Ring {
+    unsigned char* rec;   // [NSTAGE][GSTAR_BATCH * RS]
+    uint32_t* idx;        // [NSTAGE][GSTAR_BATCH] gaussian ids (backward only; may be null)
+    uint64_t* full;       // [NSTAGE]
+    uint64_t* empty;      // [NSTAGE]
+};
+
+template <bool REVERSE, bool WITH_IDX>
+__device__ __forceinline__ void produce_batch(const Ring& r, int b, int total, const uint32_t* __restrict__ plist, const unsigned char* __restrict__ recs,
+                                              int lane)
 {
-    __shared__ __align__(128) unsigned char s_rec[2][GSTAR_BATCH * RS];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    const int s = b % NSTAGE;
+    const int cnt = min(GSTAR_BATCH, total - b * GSTAR_BATCH);
+    if (b >= NSTAGE) mbar_wait(&r.empty[s], (uint32_t)((b / NSTAGE) - 1) & 1u);  // all 8 consumers released the stage
+    unsigned char* dst = r.rec + (size_t)s * GSTAR_BATCH * RS;
+#pragma unroll 1
+    for (int slot = lane; slot < cnt; slot += 32) {
+        const int pos = REVERSE ? (total - 1 - (b * GSTAR_BATCH + slot)) : (b * GSTAR_BATCH + slot);
+        const uint32_t id = __ldg(plist + pos);
+        if (WITH_IDX) r.idx[s * GSTAR_BATCH + slot] = id;
+        bulk_g2s(dst + slot * RS, recs + (size_t)id * GSTAR_REC_BYTES, RS, &r.full[s]);
+    }
+    __syncwarp();  // idx stores of all lanes ordered before the releasing arrive below
+    if (lane == 0) mbar_arrive_expect_tx(&r.full[s], (uint32_t)cnt * RS);
+}
+
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
+{
+    __shared__ __align__(128) unsigned char s_rec[NSTAGE * GSTAR_BATCH * RS];
+    __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
+    __shared__ int s_done_warps;
+    __shared__ volatile int s_stop;
     if (p.hdr->overflow) return;
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     const int n = (int)(re - rs);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WarpGeom g = warp_geom(tile, p.gx, p.W, p.H);
     const float pxf = (float)g.px, pyf = (float)g.py;
 
@@ -104,92 +139,103 @@ __global__ void __launch_bounds__(256) k_blend_fwd(BlendParams p)
 
     if (n > 0) {
         if (tid == 0) {
-            mbar_init(&s_bar[0], 1);
-            mbar_init(&s_bar[1], 1);
+            for (int s = 0; s < NSTAGE; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NCONS); }
+            s_done_warps = 0;
+            s_stop = 0;
             fence_mbar_init();
         }
         __syncthreads();
         const int nb = (n + GSTAR_BATCH - 1) / GSTAR_BATCH;
-        const uint32_t* plist = p.point_list + rs;
-        const unsigned char* recs = reinterpret_cast<const unsigned char*>(p.recs);
-        auto issue = [&](int b) {
-            const int cnt = min(GSTAR_BATCH, n - b * GSTAR_BATCH);
-            uint64_t* bar = &s_bar[b & 1];
-            if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * RS);
-            if (tid < cnt) {
-                const uint32_t id = __ldg(plist + b * GSTAR_BATCH + tid);
-                bulk_g2s(&s_rec[b & 1][tid * RS], recs + (size_t)id * GSTAR_REC_BYTES, RS, bar);
+        Ring ring{s_rec, nullptr, s_full, s_empty};
+        if (warp == NCONS) {
+            // ===== producer warp =====
+            const uint32_t* plist = p.point_list + rs;
+            const unsigned char* recs = reinterpret_cast<const unsigned char*>(p.recs);
+#pragma unroll 1
+            for (int b = 0; b < nb; b++) {
+                if (*(volatile int*)&s_done_warps == NCONS) {
+                    // every pixel of the tile is finished: stop streaming and release anyone waiting for batch b
+                    s_stop = 1;
+                    __threadfence_block();
+                    if (lane == 0) mbar_arrive_expect_tx(&s_full[b % NSTAGE], 0);
+                    break;
+                }
+                produce_batch<false, false>(ring, b, n, plist, recs, lane);
             }
-        };
-        issue(0);
-        bool warp_done = __all_sync(FULL, done);
-        int all_done = __syncthreads_and(warp_done);
-        for (int b = 0; b < nb; b++) {
-            uint64_t* bar = &s_bar[b & 1];
-            const uint32_t parity = (uint32_t)(b >> 1) & 1u;
-            if (all_done) {  // batch b is still in flight: it must land before the CTA may exit
-                mbar_wait(bar, parity);
-                break;
-            }
-            if (b + 1 < nb) issue(b + 1);
-            mbar_wait(bar, parity);
-            if (!warp_done) {
-                const unsigned char* buf = s_rec[b & 1];
-                const int cnt = min(GSTAR_BATCH, n - b * GSTAR_BATCH);
-                for (int r0 = 0; r0 < cnt; r0 += 32) {
-                    const unsigned live = __ballot_sync(FULL, !done);
-                    if (live == 0) {
-                        warp_done = true;
-                        break;
-                    }
-                    const LiveBox lb = live_box(live, g);
-                    const int j = r0 + lane;
-                    const bool ov = (j < cnt) && bbox_overlaps_box(buf + j * RS, lb);
-                    unsigned m = __ballot_sync(FULL, ov);
-                    // Survivors are taken four at a time: the four alpha evaluations (loads, exp) are independent and
-                    // overlap; only the short T recurrence below is serial.  Same arithmetic, same order per pixel.
-                    while (m) {
-                        int ks[4];
-                        bool ok[4];
-                        float al[4], cr[4], cg[4], cbv[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const bool have = m != 0;
-                            ks[u] = have ? __ffs(m) - 1 : 0;
-                            m &= m - 1;
-                            const unsigned char* rp = buf + (r0 + ks[u]) * RS;
-                            const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
-                            const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
-                            cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
-                            cr[u] = q1.z; cg[u] = q1.w;
-                            float dx, dy;
-                            const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
-                            al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
-                            ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+        } else {
+            // ===== consumer warps =====
+            bool warp_done = __all_sync(FULL, done);
+            bool counted = false;
+#pragma unroll 1
+            for (int b = 0; b < nb; b++) {
+                if (warp_done && !counted) {
+                    if (lane == 0) atomicAdd(&s_done_warps, 1);
+                    counted = true;
+                }
+                const int s = b % NSTAGE;
+                mbar_wait(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
+                if (s_stop) break;
+                if (!warp_done) {
+                    const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS;
+                    const int cnt = min(GSTAR_BATCH, n - b * GSTAR_BATCH);
+#pragma unroll 1
+                    for (int r0 = 0; r0 < cnt; r0 += 32) {
+                        const unsigned live = __ballot_sync(FULL, !done);
+                        if (live == 0) {
+                            warp_done = true;
+                            break;
                         }
+                        const LiveBox lb = live_box(live, g);
+                        const int j = r0 + lane;
+                        const bool ov = (j < cnt) && bbox_overlaps_box(buf + j * RS, lb);
+                        unsigned m = __ballot_sync(FULL, ov);
+                        // Survivors are taken four at a time: the four alpha evaluations (loads, exp) are independent and
+                        // overlap; only the short T recurrence below is serial.  Same arithmetic, same order per pixel.
+#pragma unroll 1
+                        while (m) {
+                            int ks[4];
+                            bool ok[4];
+                            float al[4], cr[4], cg[4], cbv[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            if (ok[u] && !done) {
-                                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
-                                if (test_T < 0.0001f) {
-                                    done = true;
-                                } else {
-                                    C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
-                                    C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
-                                    C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
-                                    T = test_T;
-                                    last = (uint32_t)(b * GSTAR_BATCH + r0 + ks[u] + 1);
+                            for (int u = 0; u < 4; u++) {
+                                const bool have = m != 0;
+                                ks[u] = have ? __ffs(m) - 1 : 0;
+                                m &= m - 1;
+                                const unsigned char* rp = buf + (r0 + ks[u]) * RS;
+                                const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
+                                const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
+                                cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
+                                cr[u] = q1.z; cg[u] = q1.w;
+                                float dx, dy;
+                                const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
+                                al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
+                                ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (ok[u] && !done) {
+                                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
+                                    if (test_T < 0.0001f) {
+                                        done = true;
+                                    } else {
+                                        C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
+                                        C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
+                                        C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
+                                        T = test_T;
+                                        last = (uint32_t)(b * GSTAR_BATCH + r0 + ks[u] + 1);
+                                    }
                                 }
                             }
                         }
                     }
+                    if (!warp_done && __all_sync(FULL, done)) warp_done = true;
                 }
-                if (!warp_done && __all_sync(FULL, done)) warp_done = true;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[s]);
             }
-            all_done = __syncthreads_and(warp_done);
         }
     }
-    if (g.inside) {
+    if (g.inside && warp < NCONS) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pid = (size_t)g.py * p.W + g.px;
         p.final_T[pid] = T;
@@ -208,26 +254,28 @@ __device__ __forceinline__ float bfly_pair(float a, float b, unsigned m, unsigne
     return keep + __shfl_xor_sync(FULL, send, m);
 }
 
-__global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
 {
-    __shared__ __align__(128) unsigned char s_rec[2][GSTAR_BATCH * RS];
-    __shared__ uint32_t s_idx[2][GSTAR_BATCH];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(128) unsigned char s_rec[NSTAGE * GSTAR_BATCH * RS];
+    __shared__ uint32_t s_idx[NSTAGE * GSTAR_BATCH];
+    __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
     __shared__ int s_kmax;
     if (p.hdr->overflow) return;
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     if (re == rs) return;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool consumer = warp < NCONS;
     const WarpGeom g = warp_geom(tile, p.gx, p.W, p.H);
     const float pxf = (float)g.px, pyf = (float)g.py;
     const size_t HW = (size_t)p.H * p.W;
     const size_t pid = (size_t)g.py * p.W + g.px;
+    const bool inside = g.inside && consumer;
 
-    const float T_final = g.inside ? p.final_T[pid] : 0.f;
-    const int last_contributor = g.inside ? (int)p.n_contrib[pid] : 0;
+    const float T_final = inside ? p.final_T[pid] : 0.f;
+    const int last_contributor = inside ? (int)p.n_contrib[pid] : 0;
     float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f;
-    if (g.inside) { dpx0 = p.dL_dpix[pid]; dpx1 = p.dL_dpix[HW + pid]; dpx2 = p.dL_dpix[2 * HW + pid]; }
+    if (inside) { dpx0 = p.dL_dpix[pid]; dpx1 = p.dL_dpix[HW + pid]; dpx2 = p.dL_dpix[2 * HW + pid]; }
     float bg_dot = 0.f;  // backward.cu:531-533
     bg_dot += __ldg(p.bg + 0) * dpx0;
     bg_dot += __ldg(p.bg + 1) * dpx1;
@@ -236,8 +284,7 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
 
     if (tid == 0) {
         s_kmax = 0;
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NCONS); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -246,33 +293,31 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
     __syncthreads();
     const int total = s_kmax;  // entries [0,total) of the tile list can matter; the rest is behind every pixel's last contributor
     if (total == 0) return;
-
+    const int nb = (total + GSTAR_BATCH - 1) / GSTAR_BATCH;
+    Ring ring{s_rec, s_idx, s_full, s_empty};
+    if (!consumer) {
+        // ===== producer warp: slot s of batch b  <->  list position k = total-1 - (b*256+s)  (back to front, backward.cu:472)
+        const uint32_t* plist = p.point_list + rs;
+        const unsigned char* recs = reinterpret_cast<const unsigned char*>(p.recs);
+#pragma unroll 1
+        for (int b = 0; b < nb; b++) produce_batch<true, true>(ring, b, total, plist, recs, lane);
+        return;
+    }
+    // ===== consumer warps =====
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-    const int nb = (total + GSTAR_BATCH - 1) / GSTAR_BATCH;
-    const uint32_t* plist = p.point_list + rs;
-    const unsigned char* recs = reinterpret_cast<const unsigned char*>(p.recs);
-    // slot s of batch b  <->  list position k = total-1 - (b*256+s)   (back to front, backward.cu:472)
-    auto issue = [&](int b) {
-        const int cnt = min(GSTAR_BATCH, total - b * GSTAR_BATCH);
-        uint64_t* bar = &s_bar[b & 1];
-        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * RS);
-        if (tid < cnt) {
-            const uint32_t id = __ldg(plist + (total - 1 - (b * GSTAR_BATCH + tid)));
-            s_idx[b & 1][tid] = id;
-            bulk_g2s(&s_rec[b & 1][tid * RS], recs + (size_t)id * GSTAR_REC_BYTES, RS, bar);
-        }
-    };
-    issue(0);
+#pragma unroll 1
     for (int b = 0; b < nb; b++) {
-        if (b + 1 < nb) issue(b + 1);
-        mbar_wait(&s_bar[b & 1], (uint32_t)(b >> 1) & 1u);
-        __syncthreads();  // s_idx of this batch visible to all warps
-        const unsigned char* buf = s_rec[b & 1];
-        const uint32_t* ids = s_idx[b & 1];
+        const int s = b % NSTAGE;
         const int cnt = min(GSTAR_BATCH, total - b * GSTAR_BATCH);
         const int kbase = total - 1 - b * GSTAR_BATCH;
+        // Every consumer waits for every batch -- even one it will skip -- so that it can never arrive twice on the
+        // same phase of a stage's `empty` barrier (the ring keeps all warps within NSTAGE batches of each other).
+        mbar_wait(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
         if (kbase - (cnt - 1) < warp_kmax) {  // some entry of this batch is in front of this warp's last contributor
+            const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS;
+            const uint32_t* ids = s_idx + s * GSTAR_BATCH;
+#pragma unroll 1
             for (int r0 = 0; r0 < cnt; r0 += 32) {
                 // pixels that can receive gradient from some entry of this round: last_contributor > smallest k of the round
                 const unsigned live = __ballot_sync(FULL, last_contributor > kbase - r0 - 31);
@@ -284,6 +329,7 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
                 // Survivors are taken two at a time (A = further back, then B): the two alpha evaluations overlap, the
                 // per-pixel state is advanced A then B exactly as the reference does, and both records' nine partial
                 // sums go through ONE 16-value butterfly (lanes 0-15 end up with A's sums, 16-31 with B's).
+#pragma unroll 1
                 while (m) {
                     int slot[2];
                     bool pass[2];
@@ -312,18 +358,20 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
                         for (int c = 0; c < 9; c++) v[u][c] = 0.f;
                         if (pass[u]) {
                             const float al = alpha[u], dx = ddx[u], dy = ddy[u];
-                            T = __fdiv_rn(T, __fsub_rn(1.f, al));
+                            const float inv1ma = __frcp_rn(__fsub_rn(1.f, al));
+                            T = T * inv1ma;  // backward.cu:503 (T / (1 - alpha))
                             const float dchannel_dcolor = al * T;
                             float dL_dalpha = 0.0f;
-                            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = q1[u].z; dL_dalpha += (q1[u].z - acc0) * dpx0;
-                            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = q1[u].w; dL_dalpha += (q1[u].w - acc1) * dpx1;
-                            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cbv[u];  dL_dalpha += (cbv[u] - acc2) * dpx2;
+                            const float oml = 1.f - last_alpha;
+                            acc0 = last_alpha * lc0 + oml * acc0; lc0 = q1[u].z; dL_dalpha += (q1[u].z - acc0) * dpx0;
+                            acc1 = last_alpha * lc1 + oml * acc1; lc1 = q1[u].w; dL_dalpha += (q1[u].w - acc1) * dpx1;
+                            acc2 = last_alpha * lc2 + oml * acc2; lc2 = cbv[u];  dL_dalpha += (cbv[u] - acc2) * dpx2;
                             v[u][5] = dchannel_dcolor * dpx0;
                             v[u][6] = dchannel_dcolor * dpx1;
                             v[u][7] = dchannel_dcolor * dpx2;
                             dL_dalpha *= T;
                             last_alpha = al;
-                            dL_dalpha += (-T_final / (1.f - al)) * bg_dot;
+                            dL_dalpha += (-T_final * inv1ma) * bg_dot;
                             const float dL_dG = q1[u].y * dL_dalpha;
                             const float gdx = G[u] * dx, gdy = G[u] * dy;
                             const float dG_ddelx = -gdx * q0[u].z - gdy * q0[u].w;
@@ -363,11 +411,12 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BlendParams p)
                 }
             }
         }
-        __syncthreads();  // everyone is done with stage b&1 before batch b+2 overwrites it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
     }
 }
 
-void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, 256, 0, s>>>(p); }
-void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, 256, 0, s>>>(p); }
+void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
+void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
 
 }  // namespace gstar
