@@ -139,12 +139,14 @@ class OursCABI:
         self.capi = capi
         capi.lib()
 
-    def fwd_bwd(self, params, cam, bg, grad_fn):
+    fused_accumulate = True  # K8 adds each view's parameter gradients straight into the flat allreduce buffer
+
+    def fwd_bwd(self, params, cam, bg, grad_fn, flat=None):
         kw = dict(means3D=params["means3D"], viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], campos=cam["campos"], bg=bg,
                   tan_fovx=cam["tanfovx"], tan_fovy=cam["tanfovy"], shs=params["shs"], scales=params["scales"], rotations=params["rotations"],
                   sh_degree=SH_DEG)
         f = self.capi.forward(opacities=params["opacities"], W=W, H=H, **kw)
-        g = self.capi.backward(f, grad_fn(f["out_color"]), **kw)
+        g = self.capi.backward(f, grad_fn(f["out_color"]), accumulate_into=flat.views if flat is not None else None, **kw)
         return f["num_rendered"], int(0), g
 
 
@@ -158,7 +160,9 @@ class RefStock:
         self.C = refgpu.stock_module()
         self.empty = torch.Tensor([])
 
-    def fwd_bwd(self, params, cam, bg, grad_fn):
+    fused_accumulate = False
+
+    def fwd_bwd(self, params, cam, bg, grad_fn, flat=None):
         C, e = self.C, self.empty
         R, color, radii, gb, bb, ib = C.rasterize_gaussians(bg, params["means3D"], e, params["opacities"], params["scales"], params["rotations"], 1.0, e,
                                                             cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], H, W, params["shs"],
@@ -249,8 +253,11 @@ def run_gpu(args, impl_name, rank, world, local):
             if prof is not None and timed:
                 a, b = prof[(step - args.warmup) * VIEWS_PER_GPU + i]
                 capi.profile_stage(capi.STAGES.index("blend_bwd"), a, b)
-            R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]))
-            flat.accumulate(grads)
+            if impl.fused_accumulate:
+                R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]), flat)
+            else:
+                R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]))
+                flat.accumulate(grads)
             if timed:
                 R_sum += int(R); V_count += 1
         flat.allreduce()

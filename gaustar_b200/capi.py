@@ -51,7 +51,7 @@ class BwdArgs(C.Structure):
         ("dL_dpix", C.c_void_p),
         ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dcolor", C.c_void_p),
         ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
-        ("dL_drot", C.c_void_p), ("blend_grad_scratch", C.c_void_p), ("debug", C.c_int),
+        ("dL_drot", C.c_void_p), ("blend_grad_scratch", C.c_void_p), ("debug", C.c_int), ("accumulate_param_grads", C.c_int),
     ]
 
 
@@ -78,7 +78,7 @@ def lib():
         L.gstar_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gstar_geom_unpack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.gstar_image_views.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
-        L.gstar_binning_views.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.gstar_binning_views.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.gstar_profile_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -143,8 +143,10 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,
-             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False):
-    """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts)."""
+             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None):
+    """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts).
+    accumulate_into: optional dict with dL_dmeans3D/dL_dscales/dL_drotations/dL_dopacity/dL_dsh tensors; the
+    parameter gradients are then ADDED to them inside the kernel (accumulate_param_grads=1)."""
     L = lib()
     dev = means3D.device
     keep = [_f32(x, dev) for x in (means3D, viewmatrix, projmatrix, campos, bg, shs, colors_precomp, scales, rotations, cov3D_precomp, dL_dout_color)]
@@ -155,12 +157,17 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     g = dict(dL_dmeans2D=e(P, 3), dL_dconic=e(P, 4), dL_dopacity=e(P, 1), dL_dcolors=e(P, 3), dL_dmeans3D=e(P, 3), dL_dcov3D=e(P, 6),
              dL_dsh=e(P, M, 3), dL_dscales=e(P, 3), dL_drotations=e(P, 4))
+    if accumulate_into is not None:
+        for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh"):
+            t = accumulate_into[k]
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == g[k].numel(), k
+            g[k] = t
     scratch = torch.zeros(P, 12, dtype=torch.float32, device=dev)
     a = BwdArgs(P, sh_degree, M, int(fwd["num_rendered"]), _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(sc), scale_modifier, _ptr(rot),
                 _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]), _ptr(fwd["binning"]),
                 _ptr(fwd["image"]), _ptr(dpix), _ptr(g["dL_dmeans2D"]), _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolors"]),
                 _ptr(g["dL_dmeans3D"]), _ptr(g["dL_dcov3D"]), _ptr(g["dL_dsh"]), _ptr(g["dL_dscales"]), _ptr(g["dL_drotations"]),
-                _ptr(scratch), int(debug))
+                _ptr(scratch), int(debug), int(accumulate_into is not None))
     with torch.cuda.device(dev):
         _check(L.gstar_raster_backward(C.byref(a), _stream(dev)))
     g["_keep"] = keep + [scratch]
@@ -210,7 +217,7 @@ def point_list(fwd):
         return torch.zeros(0, dtype=torch.int32, device=fwd["geom"].device)
     pl = C.c_void_p()
     cap = C.c_uint64()
-    _check(lib().gstar_binning_views(_ptr(fwd["binning"]), C.byref(pl), C.byref(cap)))
+    _check(lib().gstar_binning_views(_ptr(fwd["binning"]), _ptr(fwd["image"]), C.byref(pl), C.byref(cap)))
     return _view(fwd["binning"], pl.value, R * 4, torch.int32)
 
 

@@ -81,6 +81,7 @@ int get_ctx(DevCtx** out)
         CU_OK(cudaEventCreateWithFlags(&c.scan_done, cudaEventDisableTiming));
         CU_OK((cudaError_t)gstar::tile_sort_setup());
         CU_OK((cudaError_t)gstar::preprocess_setup());
+        CU_OK((cudaError_t)gstar::blend_setup());
         c.inited = true;
     }
     *out = &c;
@@ -109,13 +110,14 @@ ImgLayout img_layout(int W, int H)
     return L;
 }
 struct BinLayout {
-    size_t point_list, entries, total;
+    size_t packed, point_list, entries, total;
 };
 BinLayout bin_layout(size_t cap)
 {
     BinLayout L;
-    L.point_list = 0;  // first, so that backward needs no capacity to find it
-    L.entries = align_up(cap * 4, 128);
+    L.packed = 0;  // first, so that backward needs no capacity to find it
+    L.point_list = align_up(cap * GSTAR_REC_SMEM, 128);
+    L.entries = align_up(L.point_list + cap * 4, 128);
     L.total = align_up(L.entries + cap * 8, 128);
     return L;
 }
@@ -238,8 +240,9 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
         const BinLayout BL = bin_layout(cap);
         bp.capacity = (uint32_t)cap;
         bp.point_list = bin ? (uint32_t*)(bin + BL.point_list) : nullptr;
+        bp.packed = bin ? (unsigned char*)(bin + BL.packed) : nullptr;
         bp.entries = bin ? (uint2*)(bin + BL.entries) : nullptr;
-        bl.point_list = bp.point_list;
+        bl.packed = bp.packed;
         {
             StageScope sc(GSTAR_STAGE_TILE_SCAN, stream);
             launch_tile_scan(bp, stream);
@@ -280,7 +283,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             // cheapest correct path: run blend with empty ranges
             char* bin = binning_alloc(binning_user, gstar_binning_bytes(1));
             if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
-            bl.point_list = (uint32_t*)aligned128(bin);
+            bl.packed = (unsigned char*)aligned128(bin);
             bp.capacity = 1;
             launch_tile_scan(bp, stream);
             launch_blend_fwd(bl, stream);
@@ -311,7 +314,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         bl.recs = (const GRec*)geom; bl.hdr = (const GHeader*)(img + IL.hdr);
         bl.ranges = (const uint32_t*)(img + IL.ranges);
         bl.tile_order = (const uint32_t*)(img + IL.tile_order);
-        bl.point_list = (const uint32_t*)aligned128(a->binning_buffer);
+        bl.packed = (const unsigned char*)aligned128(a->binning_buffer);
         bl.bg = a->background;
         bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
         bl.dL_dpix = a->dL_dpix; bl.gacc = a->blend_grad_scratch;
@@ -332,6 +335,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
     pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;
     pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = (a->M > 0) ? a->dL_dsh : nullptr;
     pb.dL_dscale = a->dL_dscale; pb.dL_drot = a->dL_drot;
+    pb.accumulate = a->accumulate_param_grads;
     if (!pb.dL_dmean2D || !pb.dL_dopacity || !pb.dL_dcolor || !pb.dL_dmean3D || !pb.dL_dcov3D)
         return fail(GSTAR_ERR_INVALID, "missing gradient output");
     if (a->shs && a->M > 0 && !a->dL_dsh) return fail(GSTAR_ERR_INVALID, "missing dL_dsh");
@@ -377,11 +381,15 @@ int gstar_image_views(char* image_buffer, int width, int height, float** final_T
     return 0;
 }
 
-int gstar_binning_views(char* binning_buffer, uint32_t** point_list, uint64_t* capacity)
+int gstar_binning_views(char* binning_buffer, char* image_buffer, uint32_t** point_list, uint64_t* capacity)
 {
-    if (!binning_buffer) return fail(GSTAR_ERR_INVALID, "null binning buffer");
-    if (point_list) *point_list = (uint32_t*)aligned128(binning_buffer);
-    if (capacity) *capacity = 0;
+    if (!binning_buffer || !image_buffer) return fail(GSTAR_ERR_INVALID, "null buffer");
+    GHeader h;
+    cudaError_t e = cudaMemcpy(&h, aligned128(image_buffer), sizeof(GHeader), cudaMemcpyDeviceToHost);  // test helper: synchronous
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
+    const BinLayout BL = bin_layout(h.capacity);
+    if (point_list) *point_list = (uint32_t*)(aligned128(binning_buffer) + BL.point_list);
+    if (capacity) *capacity = h.capacity;
     return 0;
 }
 

@@ -18,9 +18,8 @@
 namespace gstar {
 
 constexpr int SCAN_THREADS = 1024;
-constexpr uint32_t SORT_SMALL_CAP = 4096;          // keys (32 KB) handled by the 256-thread kernel
-constexpr uint32_t SORT_BIG_CAP = 16384;           // keys (128 KB, a power of two) per shared-memory chunk of the big kernel
-constexpr int SORT_BIG_THREADS = 1024;
+constexpr uint32_t SORT_CAP = 8192;                // keys (64 KB, a power of two) one CTA sorts in shared memory
+constexpr int SORT_THREADS = 512;
 constexpr int LPT_BUCKETS = 132;                   // quarter-octave size classes for the longest-first tile order
 
 __device__ __forceinline__ int lpt_bucket(uint32_t c)
@@ -82,7 +81,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         // identifyTileRanges leaves untouched tiles at the memset value (0,0): rasterizer_impl.cu:310
         p.ranges[2 * t] = c ? run : 0u;
         p.ranges[2 * t + 1] = c ? run + c : 0u;
-        if (c > SORT_SMALL_CAP) p.big_tiles[atomicAdd(&s_nbig, 1u)] = (uint32_t)t;
+        if (c > SORT_CAP) p.big_tiles[atomicAdd(&s_nbig, 1u)] = (uint32_t)t;  // statistics only
         run += c;
     }
     __syncthreads();
@@ -159,154 +158,188 @@ __global__ void __launch_bounds__(256) k_emit(BinParams p)
 }
 
 // ---- K4: per-tile sort of (depth_bits<<32 | idx) ----------------------------------------------------
-// Bitonic network in its "flip/disperse" form: every compare-exchange is ascending, so the virtual
-// +inf padding up to the next power of two never moves and out-of-range partners are simply skipped.
+// Bitonic network in its "flip/disperse" form: every compare-exchange is ascending, so the virtual +inf
+// padding up to the next power of two never moves and out-of-range partners are simply skipped.
+// Stages whose partners are < 8 apart run on 8 keys held in registers (levels 2,4,8 completely, and the
+// j = 4,2,1 tail of every later level), which removes about a third of the shared-memory round trips and
+// barriers of the textbook network.
 __device__ __forceinline__ void cmpxchg(uint64_t* a, uint32_t i, uint32_t l)
 {
     const uint64_t x = a[i], y = a[l];
     if (x > y) { a[i] = y; a[l] = x; }
 }
-
-__device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, uint32_t tid, uint32_t nthreads)
+__device__ __forceinline__ void cx(uint64_t& x, uint64_t& y)
 {
-    if (n < 2) return;
-    uint32_t npad = 1;
-    while (npad < n) npad <<= 1;
+    const uint64_t lo = x < y ? x : y, hi = x < y ? y : x;
+    x = lo; y = hi;
+}
+__device__ __forceinline__ void load8(const uint64_t* a, uint32_t base, uint32_t n, uint64_t v[8])
+{
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = (base + e < n) ? a[base + e] : ~0ull;
+}
+__device__ __forceinline__ void store8(uint64_t* a, uint32_t base, uint32_t n, const uint64_t v[8])
+{
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+        if (base + e < n) a[base + e] = v[e];
+}
+__device__ __forceinline__ void tail421(uint64_t v[8])
+{
+    cx(v[0], v[4]); cx(v[1], v[5]); cx(v[2], v[6]); cx(v[3], v[7]);
+    cx(v[0], v[2]); cx(v[1], v[3]); cx(v[4], v[6]); cx(v[5], v[7]);
+    cx(v[0], v[1]); cx(v[2], v[3]); cx(v[4], v[5]); cx(v[6], v[7]);
+}
+__device__ __forceinline__ void sort8(uint64_t v[8])
+{
+    cx(v[0], v[1]); cx(v[2], v[3]); cx(v[4], v[5]); cx(v[6], v[7]);                      // k=2
+    cx(v[0], v[3]); cx(v[1], v[2]); cx(v[4], v[7]); cx(v[5], v[6]);                      // k=4 flip
+    cx(v[0], v[1]); cx(v[2], v[3]); cx(v[4], v[5]); cx(v[6], v[7]);                      //     j=1
+    cx(v[0], v[7]); cx(v[1], v[6]); cx(v[2], v[5]); cx(v[3], v[4]);                      // k=8 flip
+    cx(v[0], v[2]); cx(v[1], v[3]); cx(v[4], v[6]); cx(v[5], v[7]);                      //     j=2
+    cx(v[0], v[1]); cx(v[2], v[3]); cx(v[4], v[5]); cx(v[6], v[7]);                      //     j=1
+}
+
+// disperse stages j = jstart .. 8 on the array, then the register tail (4,2,1); npad = padded length (multiple of 8)
+__device__ __forceinline__ void disperse_and_tail(uint64_t* a, uint32_t n, uint32_t npad, uint32_t jstart, uint32_t tid, uint32_t nt)
+{
     const uint32_t pairs = npad >> 1;
-    for (uint32_t k = 2; k <= npad; k <<= 1) {
-        const uint32_t half = k >> 1;
-        const uint32_t hshift = 31 - __clz(half);
-        for (uint32_t t = tid; t < pairs; t += nthreads) {
-            const uint32_t blk = t >> hshift, off = t & (half - 1);
-            const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
-            if (l < n) cmpxchg(a, i, l);
-        }
-        __syncthreads();
-        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-            const uint32_t jshift = 31 - __clz(j);
-            for (uint32_t t = tid; t < pairs; t += nthreads) {
-                const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
-                if (l < n) cmpxchg(a, i, l);
-            }
-            __syncthreads();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_tile_sort(BinParams p)
-{
-    __shared__ uint64_t s_keys[SORT_SMALL_CAP];
-    if (p.hdr->overflow) return;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
-    const uint32_t n = end - start;
-    if (n == 0 || n > SORT_SMALL_CAP) return;
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(p.entries) + start;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = src[i];
-    __syncthreads();
-    bitonic_sort(s_keys, n, threadIdx.x, blockDim.x);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.point_list[start + i] = (uint32_t)s_keys[i];
-}
-
-// disperse stages j = jstart, jstart/2, ..., 1 of the network on a (shared-memory) array
-__device__ __forceinline__ void bitonic_disperse(uint64_t* a, uint32_t n, uint32_t jstart, uint32_t pairs, uint32_t tid, uint32_t nthreads)
-{
-    for (uint32_t j = jstart; j > 0; j >>= 1) {
+    for (uint32_t j = jstart; j >= 8; j >>= 1) {
         const uint32_t jshift = 31 - __clz(j);
-        for (uint32_t t = tid; t < pairs; t += nthreads) {
+        for (uint32_t t = tid; t < pairs; t += nt) {
             const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
             if (l < n) cmpxchg(a, i, l);
         }
         __syncthreads();
     }
+    for (uint32_t gidx = tid; gidx < (npad >> 3); gidx += nt) {
+        const uint32_t base = gidx << 3;
+        if (base + 1 < n) {
+            uint64_t v[8];
+            load8(a, base, n, v);
+            tail421(v);
+            store8(a, base, n, v);
+        }
+    }
+    __syncthreads();
 }
 
-// Long tile lists: persistent CTAs with 128 KB of shared memory pull tiles from the work list.  A list of up
-// to 16384 keys is sorted entirely in shared memory.  A longer one is sorted chunk-wise in shared memory and
-// finished with the classic hybrid schedule: only the few network stages whose partners lie in different
-// chunks run on global memory (L2-resident), every remaining stage runs on a chunk staged in shared memory.
-__global__ void __launch_bounds__(SORT_BIG_THREADS) k_tile_sort_big(BinParams p)
+__device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, uint32_t tid, uint32_t nt)
+{
+    if (n < 2) return;
+    uint32_t npad = 8;
+    while (npad < n) npad <<= 1;
+    for (uint32_t gidx = tid; gidx < (npad >> 3); gidx += nt) {  // levels 2,4,8 in registers
+        const uint32_t base = gidx << 3;
+        if (base + 1 < n) {
+            uint64_t v[8];
+            load8(a, base, n, v);
+            sort8(v);
+            store8(a, base, n, v);
+        }
+    }
+    __syncthreads();
+    const uint32_t pairs = npad >> 1;
+    for (uint32_t k = 16; k <= npad; k <<= 1) {
+        const uint32_t half = k >> 1, hshift = 31 - __clz(half);
+        for (uint32_t t = tid; t < pairs; t += nt) {  // flip stage
+            const uint32_t blk = t >> hshift, off = t & (half - 1);
+            const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+            if (l < n) cmpxchg(a, i, l);
+        }
+        __syncthreads();
+        disperse_and_tail(a, n, npad, k >> 2, tid, nt);
+    }
+}
+
+// One CTA per tile, tiles taken longest-first.  Lists up to SORT_CAP keys are sorted entirely in shared memory;
+// longer ones chunk-wise in shared memory and finished with the hybrid schedule: only the few network stages whose
+// partners lie in different chunks run on global memory (L2-resident), every other stage on a staged chunk.
+// Write the sorted list of one tile: point_list (the reference's sorted value list) and the tile-contiguous packed
+// record stream the blend kernels read with one TMA bulk copy per 256 entries: the first 44 bytes of the Gaussian's
+// GRec followed by its index.  Random 48-byte reads hit the L2-resident GRec array; writes are contiguous.
+__device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t start, const uint64_t* keys, uint32_t n, uint32_t tid, uint32_t nt)
+{
+    const float4* recs = reinterpret_cast<const float4*>(p.recs);
+    float4* out = reinterpret_cast<float4*>(p.packed + (size_t)start * GSTAR_REC_SMEM);
+    for (uint32_t i = tid; i < n; i += nt) {
+        const uint32_t id = (uint32_t)keys[i];
+        p.point_list[start + i] = id;
+        const float4 a = recs[(size_t)id * 4], b = recs[(size_t)id * 4 + 1];
+        float4 c = recs[(size_t)id * 4 + 2];
+        c.w = __uint_as_float(id);
+        out[(size_t)i * 3] = a; out[(size_t)i * 3 + 1] = b; out[(size_t)i * 3 + 2] = c;
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);
-    __shared__ uint32_t s_work;
     if (p.hdr->overflow) return;
-    const uint32_t n_big = p.hdr->n_big;
+    const uint32_t tile = p.tile_order[blockIdx.x];
+    const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
+    const uint32_t n = end - start;
+    if (n == 0) return;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    constexpr uint32_t CH = SORT_BIG_CAP;
-    for (;;) {
+    uint64_t* g = reinterpret_cast<uint64_t*>(p.entries) + start;
+    constexpr uint32_t CH = SORT_CAP;
+    if (n <= CH) {
+        for (uint32_t i = tid; i < n; i += nt) s_keys[i] = g[i];
         __syncthreads();
-        if (tid == 0) s_work = atomicAdd(&p.hdr->big_cursor, 1u);
+        bitonic_sort(s_keys, n, tid, nt);
+        write_sorted(p, start, s_keys, n, tid, nt);
+        return;
+    }
+    uint32_t npad = CH;
+    while (npad < n) npad <<= 1;
+    const uint32_t nchunks = (n + CH - 1) / CH;
+    for (uint32_t c = 0; c < nchunks; c++) {  // phase 0: every chunk fully sorted in shared memory
+        const uint32_t base = c * CH, m = min(CH, n - base);
+        for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
         __syncthreads();
-        const uint32_t wi = s_work;
-        if (wi >= n_big) break;
-        const uint32_t tile = p.big_tiles[wi];
-        const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
-        const uint32_t n = end - start;
-        uint64_t* g = reinterpret_cast<uint64_t*>(p.entries) + start;
-        if (n <= CH) {
-            for (uint32_t i = tid; i < n; i += nt) s_keys[i] = g[i];
-            __syncthreads();
-            bitonic_sort(s_keys, n, tid, nt);
-            for (uint32_t i = tid; i < n; i += nt) p.point_list[start + i] = (uint32_t)s_keys[i];
-            continue;
+        bitonic_sort(s_keys, m, tid, nt);
+        for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
+        __syncthreads();
+    }
+    for (uint32_t k = 2 * CH; k <= npad; k <<= 1) {  // merge levels
+        const uint32_t half = k >> 1, hshift = 31 - __clz(half);
+        for (uint32_t t = tid; t < (npad >> 1); t += nt) {  // flip stage (global)
+            const uint32_t blk = t >> hshift, off = t & (half - 1);
+            const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+            if (l < n) cmpxchg(g, i, l);
         }
-        uint32_t npad = CH;
-        while (npad < n) npad <<= 1;
-        const uint32_t nchunks = (n + CH - 1) / CH;
-        // phase 0: every chunk fully sorted in shared memory
-        for (uint32_t c = 0; c < nchunks; c++) {
-            const uint32_t base = c * CH, m = min(CH, n - base);
-            for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
-            __syncthreads();
-            bitonic_sort(s_keys, m, tid, nt);
-            for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
-            __syncthreads();
-        }
-        // merge levels k = 2*CH .. npad
-        for (uint32_t k = 2 * CH; k <= npad; k <<= 1) {
-            const uint32_t half = k >> 1, hshift = 31 - __clz(half);
-            for (uint32_t t = tid; t < (npad >> 1); t += nt) {  // flip stage (global)
-                const uint32_t blk = t >> hshift, off = t & (half - 1);
-                const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+        __syncthreads();
+        for (uint32_t j = k >> 2; j >= CH; j >>= 1) {  // disperse stages that still cross chunks (global)
+            const uint32_t jshift = 31 - __clz(j);
+            for (uint32_t t = tid; t < (npad >> 1); t += nt) {
+                const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
                 if (l < n) cmpxchg(g, i, l);
             }
             __syncthreads();
-            for (uint32_t j = k >> 2; j >= CH; j >>= 1) {  // disperse stages that still cross chunks (global)
-                const uint32_t jshift = 31 - __clz(j);
-                for (uint32_t t = tid; t < (npad >> 1); t += nt) {
-                    const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
-                    if (l < n) cmpxchg(g, i, l);
-                }
-                __syncthreads();
-            }
-            for (uint32_t c = 0; c < nchunks; c++) {  // remaining stages j = CH/2 .. 1 are chunk-local (shared)
-                const uint32_t base = c * CH, m = min(CH, n - base);
-                for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
-                __syncthreads();
-                bitonic_disperse(s_keys, m, CH >> 1, CH >> 1, tid, nt);
-                for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
-                __syncthreads();
-            }
         }
-        for (uint32_t i = tid; i < n; i += nt) p.point_list[start + i] = (uint32_t)g[i];
+        for (uint32_t c = 0; c < nchunks; c++) {  // stages j = CH/2 .. 1 are chunk-local (shared memory)
+            const uint32_t base = c * CH, m = min(CH, n - base);
+            for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
+            __syncthreads();
+            disperse_and_tail(s_keys, m, CH, CH >> 1, tid, nt);
+            for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
+            __syncthreads();
+        }
     }
+    write_sorted(p, start, g, n, tid, nt);
 }
 
 int tile_sort_setup()
 {
-    return (int)cudaFuncSetAttribute(k_tile_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_BIG_CAP * sizeof(uint64_t)));
+    return (int)cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_CAP * sizeof(uint64_t)));
 }
 
 void launch_tile_scan(const BinParams& p, cudaStream_t s) { k_tile_scan<<<1, SCAN_THREADS, 0, s>>>(p); }
 void launch_emit(const BinParams& p, cudaStream_t s) { k_emit<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
 void launch_tile_sort(const BinParams& p, cudaStream_t s)
 {
-    k_tile_sort<<<p.num_tiles, 256, 0, s>>>(p);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    k_tile_sort_big<<<sms, SORT_BIG_THREADS, SORT_BIG_CAP * sizeof(uint64_t), s>>>(p);
+    k_tile_sort<<<p.num_tiles, SORT_THREADS, SORT_CAP * sizeof(uint64_t), s>>>(p);
 }
 
 }  // namespace gstar

@@ -28,6 +28,7 @@ constexpr int RS = GSTAR_REC_SMEM;
 constexpr int NSTAGE = 3;                 // ring depth (3 x 12 KB stays within static shared memory)
 constexpr int NCONS = 8;                  // consumer warps (8x4 pixel blocks of a 16x16 tile)
 constexpr int BLEND_THREADS = (NCONS + 1) * 32;  // + one producer warp
+constexpr int QCAP = 64;                   // per-pixel hit-queue capacity (entries) between two flushes
 
 struct WarpGeom {
     int rx0, ry0, rx1, ry1, px, py;
@@ -82,6 +83,30 @@ __device__ __forceinline__ bool bbox_overlaps_box(const unsigned char* rec, cons
     return bx0 <= b.x1 && bx1 >= b.x0 && by0 <= b.y1 && by1 >= b.y0;
 }
 
+// 32-bit mask (bit = 8*row + col of the warp's 8x4 block) of the block pixels inside a record's alpha-bounds.
+__device__ __forceinline__ unsigned block_pixel_mask(const unsigned char* rec, const WarpGeom& g)
+{
+    const uint2 bb = *reinterpret_cast<const uint2*>(rec + 32);
+    const int cx0 = max((int)(short)(bb.x & 0xffffu) - g.rx0, 0), cx1 = min((int)(short)(bb.x >> 16) - g.rx0, 7);
+    const int cy0 = max((int)(short)(bb.y & 0xffffu) - g.ry0, 0), cy1 = min((int)(short)(bb.y >> 16) - g.ry0, 3);
+    if (cx0 > cx1 || cy0 > cy1) return 0u;
+    const unsigned cols = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);                       // 8 bits
+    const unsigned rows = (0xffffffffu >> (8 * (3 - cy1))) & (0xffffffffu << (8 * cy0));  // whole bytes
+    return (cols * 0x01010101u) & rows;
+}
+
+// Transpose a 32x32 bit matrix held one row per lane: afterwards lane p holds column p (bit j = row j's bit p).
+__device__ __forceinline__ unsigned transpose32(unsigned x, unsigned lane)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const unsigned m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+    }
+    return x;
+}
+
 // forward.cu:332-335 in the operation order of the reference SASS
 __device__ __forceinline__ float eval_power(float gx, float gy, float A, float B, float C, float pxf, float pyf, float& dx, float& dy)
 {
@@ -92,36 +117,34 @@ __device__ __forceinline__ float eval_power(float gx, float gy, float A, float B
 }
 
 
-// ---- shared producer: streams records of list positions pos(b, slot) into the ring -------------------------------
+// ---- producer: one TMA bulk copy per batch -----------------------------------------------------------------------
+// The sort kernel left the tile's records contiguous and in blend order (BinParams::packed), so a batch of up to 256
+// records is ONE cp.async.bulk of <= 12 KB issued by one lane (SASS: UBLKCP) that completes on the stage's `full` mbarrier.
 struct Ring {
     unsigned char* rec;   // [NSTAGE][GSTAR_BATCH * RS]
-    uint32_t* idx;        // [NSTAGE][GSTAR_BATCH] gaussian ids (backward only; may be null)
     uint64_t* full;       // [NSTAGE]
     uint64_t* empty;      // [NSTAGE]
 };
 
-template <bool REVERSE, bool WITH_IDX>
-__device__ __forceinline__ void produce_batch(const Ring& r, int b, int total, const uint32_t* __restrict__ plist, const unsigned char* __restrict__ recs,
-                                              int lane)
+// first_pos = list position (relative to the tile's range start) of the batch's lowest entry, cnt = entries
+__device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_pos, int cnt, const unsigned char* __restrict__ tile_packed, int lane)
 {
     const int s = b % NSTAGE;
-    const int cnt = min(GSTAR_BATCH, total - b * GSTAR_BATCH);
     if (b >= NSTAGE) mbar_wait(&r.empty[s], (uint32_t)((b / NSTAGE) - 1) & 1u);  // all 8 consumers released the stage
-    unsigned char* dst = r.rec + (size_t)s * GSTAR_BATCH * RS;
-#pragma unroll 1
-    for (int slot = lane; slot < cnt; slot += 32) {
-        const int pos = REVERSE ? (total - 1 - (b * GSTAR_BATCH + slot)) : (b * GSTAR_BATCH + slot);
-        const uint32_t id = __ldg(plist + pos);
-        if (WITH_IDX) r.idx[s * GSTAR_BATCH + slot] = id;
-        bulk_g2s(dst + slot * RS, recs + (size_t)id * GSTAR_REC_BYTES, RS, &r.full[s]);
+    if (lane == 0) {
+        mbar_arrive_expect_tx(&r.full[s], (uint32_t)cnt * RS);
+        bulk_g2s(r.rec + (size_t)s * GSTAR_BATCH * RS, tile_packed + (size_t)first_pos * RS, (uint32_t)cnt * RS, &r.full[s]);
     }
-    __syncwarp();  // idx stores of all lanes ordered before the releasing arrive below
-    if (lane == 0) mbar_arrive_expect_tx(&r.full[s], (uint32_t)cnt * RS);
+    __syncwarp();
 }
+
+constexpr int FWD_DYN_SMEM = NSTAGE * GSTAR_BATCH * RS + NCONS * QCAP * 32;  // record ring + per-pixel hit queues
 
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
 {
-    __shared__ __align__(128) unsigned char s_rec[NSTAGE * GSTAR_BATCH * RS];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    unsigned char* s_rec = s_dyn;                                                   // [NSTAGE][GSTAR_BATCH * RS]
+    unsigned char (*s_q)[QCAP][32] = reinterpret_cast<unsigned char (*)[QCAP][32]>(s_dyn + NSTAGE * GSTAR_BATCH * RS);  // [warp][pos][lane]
     __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
     __shared__ int s_done_warps;
     __shared__ volatile int s_stop;
@@ -146,11 +169,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
         }
         __syncthreads();
         const int nb = (n + GSTAR_BATCH - 1) / GSTAR_BATCH;
-        Ring ring{s_rec, nullptr, s_full, s_empty};
+        Ring ring{s_rec, s_full, s_empty};
         if (warp == NCONS) {
             // ===== producer warp =====
-            const uint32_t* plist = p.point_list + rs;
-            const unsigned char* recs = reinterpret_cast<const unsigned char*>(p.recs);
+            const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
 #pragma unroll 1
             for (int b = 0; b < nb; b++) {
                 if (*(volatile int*)&s_done_warps == NCONS) {
@@ -160,7 +182,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
                     if (lane == 0) mbar_arrive_expect_tx(&s_full[b % NSTAGE], 0);
                     break;
                 }
-                produce_batch<false, false>(ring, b, n, plist, recs, lane);
+                produce_batch(ring, b, b * GSTAR_BATCH, min(GSTAR_BATCH, n - b * GSTAR_BATCH), tile_packed, lane);
             }
         } else {
             // ===== consumer warps =====
@@ -178,30 +200,25 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
                 if (!warp_done) {
                     const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS;
                     const int cnt = min(GSTAR_BATCH, n - b * GSTAR_BATCH);
+                    // Per-pixel hit queues.  Per round of 32 records every lane turns ITS record's alpha-bounds into a
+                    // 32-bit mask of the block's pixels; a 32x32 bit-matrix transpose hands every pixel the mask of the
+                    // records that can touch it, and the set bits are appended (in list order) to that pixel's queue.
+                    // The queues are then drained with every lane working on its own next hit: no lane evaluates a
+                    // record whose bounds exclude its pixel.  Order per pixel == list order, arithmetic unchanged.
+                    int qn = 0;
+                    unsigned char* qrow = &s_q[warp][0][lane];
+                    auto drain = [&]() {
+                        const int maxn = __reduce_max_sync(FULL, qn);
 #pragma unroll 1
-                    for (int r0 = 0; r0 < cnt; r0 += 32) {
-                        const unsigned live = __ballot_sync(FULL, !done);
-                        if (live == 0) {
-                            warp_done = true;
-                            break;
-                        }
-                        const LiveBox lb = live_box(live, g);
-                        const int j = r0 + lane;
-                        const bool ov = (j < cnt) && bbox_overlaps_box(buf + j * RS, lb);
-                        unsigned m = __ballot_sync(FULL, ov);
-                        // Survivors are taken four at a time: the four alpha evaluations (loads, exp) are independent and
-                        // overlap; only the short T recurrence below is serial.  Same arithmetic, same order per pixel.
-#pragma unroll 1
-                        while (m) {
-                            int ks[4];
+                        for (int i0 = 0; i0 < maxn; i0 += 4) {
+                            int sl[4];
                             bool ok[4];
                             float al[4], cr[4], cg[4], cbv[4];
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
-                                const bool have = m != 0;
-                                ks[u] = have ? __ffs(m) - 1 : 0;
-                                m &= m - 1;
-                                const unsigned char* rp = buf + (r0 + ks[u]) * RS;
+                                const bool have = i0 + u < qn;
+                                sl[u] = have ? (int)qrow[(i0 + u) * 32] : 0;
+                                const unsigned char* rp = buf + sl[u] * RS;
                                 const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
                                 const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
                                 cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
@@ -222,12 +239,33 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
                                         C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
                                         C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
                                         T = test_T;
-                                        last = (uint32_t)(b * GSTAR_BATCH + r0 + ks[u] + 1);
+                                        last = (uint32_t)(b * GSTAR_BATCH + sl[u] + 1);
                                     }
                                 }
                             }
                         }
+                        qn = 0;
+                    };
+#pragma unroll 1
+                    for (int r0 = 0; r0 < cnt; r0 += 32) {
+                        const unsigned live = __ballot_sync(FULL, !done);
+                        if (live == 0) {
+                            warp_done = true;
+                            break;
+                        }
+                        const int j = r0 + lane;
+                        const unsigned pm = (j < cnt) ? (block_pixel_mask(buf + j * RS, g) & live) : 0u;
+                        if (!__any_sync(FULL, pm != 0u)) continue;
+                        unsigned word = transpose32(pm, lane);  // bit k: record r0+k may touch my pixel
+                        while (word) {
+                            const int k = __ffs(word) - 1;
+                            word &= word - 1;
+                            qrow[qn * 32] = (unsigned char)(r0 + k);
+                            qn++;
+                        }
+                        if (__any_sync(FULL, qn > QCAP - 32)) drain();
                     }
+                    if (!warp_done) drain();
                     if (!warp_done && __all_sync(FULL, done)) warp_done = true;
                 }
                 __syncwarp();
@@ -257,7 +295,6 @@ __device__ __forceinline__ float bfly_pair(float a, float b, unsigned m, unsigne
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
 {
     __shared__ __align__(128) unsigned char s_rec[NSTAGE * GSTAR_BATCH * RS];
-    __shared__ uint32_t s_idx[NSTAGE * GSTAR_BATCH];
     __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
     __shared__ int s_kmax;
     if (p.hdr->overflow) return;
@@ -294,13 +331,16 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
     const int total = s_kmax;  // entries [0,total) of the tile list can matter; the rest is behind every pixel's last contributor
     if (total == 0) return;
     const int nb = (total + GSTAR_BATCH - 1) / GSTAR_BATCH;
-    Ring ring{s_rec, s_idx, s_full, s_empty};
+    Ring ring{s_rec, s_full, s_empty};
     if (!consumer) {
-        // ===== producer warp: slot s of batch b  <->  list position k = total-1 - (b*256+s)  (back to front, backward.cu:472)
-        const uint32_t* plist = p.point_list + rs;
-        const unsigned char* recs = reinterpret_cast<const unsigned char*>(p.recs);
+        // ===== producer warp: batch b holds list positions [total-(b*256+cnt), total-b*256) in ascending order; consumers
+        // walk a batch from its last entry to its first (back to front, backward.cu:472)
+        const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
 #pragma unroll 1
-        for (int b = 0; b < nb; b++) produce_batch<true, true>(ring, b, total, plist, recs, lane);
+        for (int b = 0; b < nb; b++) {
+            const int cnt = min(GSTAR_BATCH, total - b * GSTAR_BATCH);
+            produce_batch(ring, b, total - b * GSTAR_BATCH - cnt, cnt, tile_packed, lane);
+        }
         return;
     }
     // ===== consumer warps =====
@@ -315,8 +355,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
         // same phase of a stage's `empty` barrier (the ring keeps all warps within NSTAGE batches of each other).
         mbar_wait(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
         if (kbase - (cnt - 1) < warp_kmax) {  // some entry of this batch is in front of this warp's last contributor
-            const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS;
-            const uint32_t* ids = s_idx + s * GSTAR_BATCH;
+            // slot j of the batch (j-th entry from the back) sits at buffer position cnt-1-j
+            const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS + (size_t)(cnt - 1) * RS;
 #pragma unroll 1
             for (int r0 = 0; r0 < cnt; r0 += 32) {
                 // pixels that can receive gradient from some entry of this round: last_contributor > smallest k of the round
@@ -324,7 +364,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
                 if (live == 0) continue;
                 const LiveBox lb = live_box(live, g);
                 const int j = r0 + lane;
-                const bool ov = (j < cnt) && (kbase - j < warp_kmax) && bbox_overlaps_box(buf + j * RS, lb);
+                const bool ov = (j < cnt) && (kbase - j < warp_kmax) && bbox_overlaps_box(buf - j * RS, lb);
                 unsigned m = __ballot_sync(FULL, ov);
                 // Survivors are taken two at a time (A = further back, then B): the two alpha evaluations overlap, the
                 // per-pixel state is advanced A then B exactly as the reference does, and both records' nine partial
@@ -341,7 +381,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
                         const bool have = m != 0;
                         slot[u] = r0 + (have ? __ffs(m) - 1 : 0);
                         m &= m - 1;
-                        const unsigned char* rp = buf + slot[u] * RS;
+                        const unsigned char* rp = buf - slot[u] * RS;
                         q0[u] = *reinterpret_cast<const float4*>(rp);
                         q1[u] = *reinterpret_cast<const float4*>(rp + 16);
                         cbv[u] = *reinterpret_cast<const float*>(rp + 40);
@@ -403,7 +443,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
                         const int rsel = lane >> 4;
                         const bool any_mine = rsel ? (anyB != 0) : (anyA != 0);
                         if (any_mine) {
-                            float* dst = p.gacc + (size_t)ids[slot[rsel]] * GSTAR_GACC;
+                            const uint32_t gid = *reinterpret_cast<const uint32_t*>(buf - slot[rsel] * RS + 44);
+                            float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
                             if ((lane & 1) == 0) atomicAdd(dst + (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)), t);
                             else if ((lane & 15) == 1) atomicAdd(dst + 8, o);
                         }
@@ -416,7 +457,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
     }
 }
 
-void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
+int blend_setup() { return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM); }
+void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, BLEND_THREADS, FWD_DYN_SMEM, s>>>(p); }
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
 
 }  // namespace gstar

@@ -52,6 +52,7 @@ struct PreBwdParams {
     float* dL_dsh;
     float* dL_dscale;
     float* dL_drot;
+    int accumulate;  // += into the parameter gradients (mean3D, scale, rot, sh, opacity)
 };
 
 struct BinParams {
@@ -65,6 +66,7 @@ struct BinParams {
     uint32_t* tile_order;  // [T] all tiles, longest list first (work order of the blend kernels)
     uint2* entries;        // [capacity] (depth bits, idx), tile-segmented
     uint32_t* point_list;  // [capacity] sorted gaussian ids
+    unsigned char* packed; // [capacity][48] tile-contiguous packed records (GRec[0:44] + gaussian id), sorted order
     uint32_t capacity;
     volatile uint32_t* host_counts;  // mapped pinned host memory: [0]=R, [1]=overflow
 };
@@ -74,7 +76,7 @@ struct BlendParams {
     const GRec* recs;
     const GHeader* hdr;
     const uint32_t* ranges;
-    const uint32_t* point_list;
+    const unsigned char* packed;  // [R][48] tile-contiguous packed records in blend order
     const uint32_t* tile_order;
     const float* bg;
     // forward
@@ -97,6 +99,7 @@ void launch_emit(const BinParams& p, cudaStream_t s);
 void launch_tile_sort(const BinParams& p, cudaStream_t s);
 int  tile_sort_setup();  // one-time cudaFuncSetAttribute calls; returns cudaError_t
 int  preprocess_setup();
+int  blend_setup();
 
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s);
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s);

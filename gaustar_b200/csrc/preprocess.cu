@@ -163,8 +163,9 @@ __device__ __forceinline__ void sh_stage_load(const ShStage& st, const float* __
     __syncwarp();
 }
 
-// coalesced shared -> global copy of all rows (dL_dsh is fully overwritten)
-__device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restrict__ dst, int M, long long first_row, int P)
+// coalesced shared -> global copy of the rows selected by row_mask; accumulate: global += shared
+__device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restrict__ dst, int M, long long first_row, int P, unsigned row_mask,
+                                               bool accumulate)
 {
     __syncwarp();
     const int lane = threadIdx.x & 31;
@@ -176,12 +177,22 @@ __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restr
         const float4* r4 = reinterpret_cast<const float4*>(st.rows);
         for (int q = lane; q < 32 * row4; q += 32) {
             const int g = q / row4, j = q - g * row4;
-            if (first_row + g < P) b4[q] = r4[g * str4 + j];
+            if (((row_mask >> g) & 1u) && first_row + g < P) {
+                float4 v = r4[g * str4 + j];
+                if (accumulate) {
+                    const float4 o = b4[q];
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                b4[q] = v;
+            }
         }
     } else {
         for (int q = lane; q < 32 * rowf; q += 32) {
             const int g = q / rowf, j = q - g * rowf;
-            if (first_row + g < P) base[q] = st.rows[g * st.stride + j];
+            if (((row_mask >> g) & 1u) && first_row + g < P) {
+                const float v = st.rows[g * st.stride + j];
+                base[q] = accumulate ? base[q] + v : v;
+            }
         }
     }
 }
@@ -398,7 +409,7 @@ __global__ void k_geom_unpack(const GRec* __restrict__ recs, int P, float* depth
 // `sh` and `dL_dsh` may alias (the staged shared-memory row is overwritten in place: every coefficient is
 // read before the first gradient is written)
 __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, float3 pos, float3 campos, uint32_t clamp_bits,
-                                            float3 dL_dcolor, float3& dmean_add, float* dL_dsh)
+                                            float3 dL_dcolor, float3& dmean_add, float* dL_dsh, bool acc_out)
 {
     const float3 dorig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
     const float len = sqrtf(dorig.x * dorig.x + dorig.y * dorig.y + dorig.z * dorig.z);
@@ -447,7 +458,11 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
     const int ncoef = (deg + 1) * (deg + 1);
     for (int k = 0; k < M; k++) {
         const float wk = k < ncoef ? w[k] : 0.f;  // coefficients above the active degree get zero gradient
-        dL_dsh[3 * k] = wk * g.x; dL_dsh[3 * k + 1] = wk * g.y; dL_dsh[3 * k + 2] = wk * g.z;
+        if (acc_out) {  // direct-to-global path in accumulate mode
+            dL_dsh[3 * k] += wk * g.x; dL_dsh[3 * k + 1] += wk * g.y; dL_dsh[3 * k + 2] += wk * g.z;
+        } else {
+            dL_dsh[3 * k] = wk * g.x; dL_dsh[3 * k + 1] = wk * g.y; dL_dsh[3 * k + 2] = wk * g.z;
+        }
     }
     const float ddx = dx.x * g.x + dx.y * g.y + dx.z * g.z;
     const float ddy = dy.x * g.x + dy.y * g.y + dy.z * g.z;
@@ -496,7 +511,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
     p.dL_dmean2D[3 * i] = acc[0]; p.dL_dmean2D[3 * i + 1] = acc[1]; p.dL_dmean2D[3 * i + 2] = 0.f;
     if (p.dL_dconic) { p.dL_dconic[4 * i] = acc[2]; p.dL_dconic[4 * i + 1] = acc[3]; p.dL_dconic[4 * i + 2] = 0.f; p.dL_dconic[4 * i + 3] = acc[4]; }
     p.dL_dcolor[3 * i] = acc[5]; p.dL_dcolor[3 * i + 1] = acc[6]; p.dL_dcolor[3 * i + 2] = acc[7];
-    p.dL_dopacity[i] = acc[8];
+    if (p.accumulate) { if (radius > 0) p.dL_dopacity[i] += acc[8]; } else p.dL_dopacity[i] = acc[8];
     float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     const bool vis = radius > 0;
     if (vis) {
@@ -565,7 +580,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
             const float* sh_in = sh_staged ? st.rows + lane * st.stride : p.shs + (size_t)3 * M * i;
             float* sh_out = sh_staged ? st.rows + lane * st.stride : p.dL_dsh + (size_t)3 * M * i;
             sh_backward(p.D, M, sh_in, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]), p.recs[idx].flags,
-                        make_float3(acc[5], acc[6], acc[7]), add, sh_out);
+                        make_float3(acc[5], acc[6], acc[7]), add, sh_out, !sh_staged && p.accumulate != 0);
             dmean[0] += add.x; dmean[1] += add.y; dmean[2] += add.z;
         }
         if (p.scales) {
@@ -597,17 +612,32 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
             drot[2] = 2 * x * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * z * (D[1][2] + D[2][1]) - 4 * y * (D[2][2] + D[0][0]);
             drot[3] = 2 * r * (D[0][1] - D[1][0]) + 2 * x * (D[2][0] + D[0][2]) + 2 * y * (D[1][2] + D[2][1]) - 4 * z * (D[1][1] + D[0][0]);
         }
-    } else if (p.dL_dsh) {
+    } else if (p.dL_dsh && !p.accumulate) {
         float* d = sh_staged ? st.rows + lane * st.stride : p.dL_dsh + (size_t)3 * M * i;
         for (int k = 0; k < 3 * M; k++) d[k] = 0.f;
     }
-    p.dL_dmean3D[3 * i] = dmean[0]; p.dL_dmean3D[3 * i + 1] = dmean[1]; p.dL_dmean3D[3 * i + 2] = dmean[2];
+    const bool acc_mode = p.accumulate != 0;
+    if (!acc_mode) {
+        p.dL_dmean3D[3 * i] = dmean[0]; p.dL_dmean3D[3 * i + 1] = dmean[1]; p.dL_dmean3D[3 * i + 2] = dmean[2];
+        if (p.dL_dscale) { p.dL_dscale[3 * i] = dscale[0]; p.dL_dscale[3 * i + 1] = dscale[1]; p.dL_dscale[3 * i + 2] = dscale[2]; }
+        if (p.dL_drot) *reinterpret_cast<float4*>(p.dL_drot + 4 * i) = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    } else if (vis) {  // accumulate: invisible Gaussians contribute nothing and are not touched
+        p.dL_dmean3D[3 * i] += dmean[0]; p.dL_dmean3D[3 * i + 1] += dmean[1]; p.dL_dmean3D[3 * i + 2] += dmean[2];
+        if (p.dL_dscale) { p.dL_dscale[3 * i] += dscale[0]; p.dL_dscale[3 * i + 1] += dscale[1]; p.dL_dscale[3 * i + 2] += dscale[2]; }
+        if (p.dL_drot) {
+            float4* d4 = reinterpret_cast<float4*>(p.dL_drot + 4 * i);
+            float4 o = *d4;
+            o.x += drot[0]; o.y += drot[1]; o.z += drot[2]; o.w += drot[3];
+            *d4 = o;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
-    if (p.dL_dscale) { p.dL_dscale[3 * i] = dscale[0]; p.dL_dscale[3 * i + 1] = dscale[1]; p.dL_dscale[3 * i + 2] = dscale[2]; }
-    if (p.dL_drot) *reinterpret_cast<float4*>(p.dL_drot + 4 * i) = make_float4(drot[0], drot[1], drot[2], drot[3]);
     }  // valid
-    if (sh_staged) sh_stage_store(st, p.dL_dsh, M, (long long)idx - lane, p.P);
+    if (sh_staged) {
+        const unsigned rows = p.accumulate ? __ballot_sync(0xffffffffu, valid && radius > 0) : 0xffffffffu;
+        sh_stage_store(st, p.dL_dsh, M, (long long)idx - lane, p.P, rows, p.accumulate != 0);
+    }
 }
 
 int preprocess_setup()

@@ -149,6 +149,7 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
         a.dL_dscale = dL_dscales.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
         a.blend_grad_scratch = scratch.data_ptr<float>();
         a.debug = debug ? 1 : 0;
+        a.accumulate_param_grads = 0;
         check(gstar_raster_backward(&a, stream));
     }
     return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);

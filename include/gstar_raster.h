@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GSTAR_ABI_VERSION 1
+#define GSTAR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSTAR_API __attribute__((visibility("default")))
@@ -119,6 +119,11 @@ typedef struct gstar_bwd_args {
      * warp instead of the reference's nine atomics per (gaussian,pixel). */
     float* blend_grad_scratch;
     int debug;
+    /* Multi-view steps: if non-zero, the five PARAMETER gradients (dL_dmean3D, dL_dscale, dL_drot, dL_dsh,
+     * dL_dopacity) are ACCUMULATED (+=) into the given arrays instead of overwritten -- a step's views sum
+     * straight into the flat buffer that is all-reduced once per step, with no separate
+     * accumulation pass.  Invisible Gaussians are then not touched at all.  The other outputs are unaffected. */
+    int accumulate_param_grads;
 } gstar_bwd_args;
 #define GSTAR_GRAD_SCRATCH_FLOATS 12
 
@@ -146,8 +151,9 @@ GSTAR_API int gstar_geom_unpack(const char* geom_buffer, int P, float* depths, f
 /* Views into the image buffer (ImageState, rasterizer_impl.h:49-56): final_T[H*W], n_contrib[H*W],
  * ranges[T,2] with T = ceil(W/16)*ceil(H/16). */
 GSTAR_API int gstar_image_views(char* image_buffer, int width, int height, float** final_T, uint32_t** n_contrib, uint32_t** ranges);
-/* View of the sorted instance list (BinningState::point_list, rasterizer_impl.h:58-68). */
-GSTAR_API int gstar_binning_views(char* binning_buffer, uint32_t** point_list, uint64_t* capacity);
+/* View of the sorted instance list (BinningState::point_list, rasterizer_impl.h:58-68).  Synchronous (reads the
+ * provisioned capacity from the image buffer's header); meant for tests. */
+GSTAR_API int gstar_binning_views(char* binning_buffer, char* image_buffer, uint32_t** point_list, uint64_t* capacity);
 
 /* ---- measurement hook: record `start`/`stop` (cudaEvent_t) around kernel stage `stage` of every
  * subsequent call on this thread (stage < 0 disables).  Stages: see gstar_stage_name(). ---- */

@@ -282,3 +282,24 @@ def test_full_size_properties():
     for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales"):
         assert torch.isfinite(g1[k]).all()
         assert Hh.rel_err((2.0 * g1[k]).cpu(), g2[k].cpu()) < 1e-4, k
+
+
+def test_accumulate_param_grads_equals_sum_of_views():
+    """accumulate_param_grads=1 (multi-view steps): K8 adds into the flat buffer == sum of per-view gradients."""
+    from gaustar_b200 import dist as gdist
+    g = scene.surface_gaussians(15000, 3, seed=4)
+    cams = scene.dome_cameras(6, 256, 160)
+    P, M = g.P, g.shs.shape[1]
+    flat = gdist.FlatGrads(P, M, "cuda")
+    ref = gdist.FlatGrads(P, M, "cuda")
+    for ci in (1, 3, 4):
+        kw = Hh.to_torch_kwargs(Hh.scene_dict(g, cams[ci]))
+        fwd = capi.forward(**kw)
+        dpix = torch.randn(3, 160, 256, device="cuda", generator=torch.Generator("cuda").manual_seed(ci))
+        plain = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
+        ref.accumulate(plain)
+        fused = capi.backward(fwd, dpix, accumulate_into=flat.views, **Hh.bwd_kwargs(kw))
+        assert fused["dL_dsh"].data_ptr() == flat.views["dL_dsh"].data_ptr()
+    torch.cuda.synchronize()
+    for k in gdist.GRAD_FIELDS:
+        assert Hh.rel_err(flat.views[k].cpu(), ref.views[k].cpu()) < 1e-5, k
