@@ -130,8 +130,8 @@ struct Ring {
 __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_pos, int cnt, const unsigned char* __restrict__ tile_packed, int lane)
 {
     const int s = b % NSTAGE;
-    if (b >= NSTAGE) mbar_wait(&r.empty[s], (uint32_t)((b / NSTAGE) - 1) & 1u);  // all 8 consumers released the stage
     if (lane == 0) {
+        if (b >= NSTAGE) mbar_wait_sleep(&r.empty[s], (uint32_t)((b / NSTAGE) - 1) & 1u);  // all 8 consumers released the stage
         mbar_arrive_expect_tx(&r.full[s], (uint32_t)cnt * RS);
         bulk_g2s(r.rec + (size_t)s * GSTAR_BATCH * RS, tile_packed + (size_t)first_pos * RS, (uint32_t)cnt * RS, &r.full[s]);
     }
@@ -391,6 +391,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
                         // kbase - slot == the reference's `contributor` after its decrement (backward.cu:486-488)
                         pass[u] = have && (kbase - slot[u] < last_contributor) && !(power > 0.0f) && !(alpha[u] < 1.0f / 255.0f);
                     }
+                    // Per-lane partials are the raw moments of s = G*dL/dG over the pixel offsets and the colour weights
+                    //   [S, S.dx, S.dy, S.dx^2, S.dx.dy, S.dy^2, w.dpx_r, w.dpx_g, w.dpx_b]   (w = alpha*T)
+                    // The per-Gaussian factors (conic, opacity, 0.5*W, 0.5*H, -0.5) are linear and are applied once per
+                    // Gaussian in preprocess_bwd instead of once per (Gaussian, pixel) here.
                     float v[2][9];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
@@ -400,28 +404,26 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
                             const float al = alpha[u], dx = ddx[u], dy = ddy[u];
                             const float inv1ma = __frcp_rn(__fsub_rn(1.f, al));
                             T = T * inv1ma;  // backward.cu:503 (T / (1 - alpha))
-                            const float dchannel_dcolor = al * T;
+                            const float w = al * T;  // dchannel_dcolor
                             float dL_dalpha = 0.0f;
                             const float oml = 1.f - last_alpha;
                             acc0 = last_alpha * lc0 + oml * acc0; lc0 = q1[u].z; dL_dalpha += (q1[u].z - acc0) * dpx0;
                             acc1 = last_alpha * lc1 + oml * acc1; lc1 = q1[u].w; dL_dalpha += (q1[u].w - acc1) * dpx1;
                             acc2 = last_alpha * lc2 + oml * acc2; lc2 = cbv[u];  dL_dalpha += (cbv[u] - acc2) * dpx2;
-                            v[u][5] = dchannel_dcolor * dpx0;
-                            v[u][6] = dchannel_dcolor * dpx1;
-                            v[u][7] = dchannel_dcolor * dpx2;
+                            v[u][6] = w * dpx0;
+                            v[u][7] = w * dpx1;
+                            v[u][8] = w * dpx2;
                             dL_dalpha *= T;
                             last_alpha = al;
                             dL_dalpha += (-T_final * inv1ma) * bg_dot;
-                            const float dL_dG = q1[u].y * dL_dalpha;
-                            const float gdx = G[u] * dx, gdy = G[u] * dy;
-                            const float dG_ddelx = -gdx * q0[u].z - gdy * q0[u].w;
-                            const float dG_ddely = -gdy * q1[u].x - gdx * q0[u].w;
-                            v[u][0] = dL_dG * dG_ddelx * ddelx_dx;
-                            v[u][1] = dL_dG * dG_ddely * ddely_dy;
-                            v[u][2] = -0.5f * gdx * dx * dL_dG;
-                            v[u][3] = -0.5f * gdx * dy * dL_dG;
-                            v[u][4] = -0.5f * gdy * dy * dL_dG;
-                            v[u][8] = G[u] * dL_dalpha;
+                            const float sG = (q1[u].y * dL_dalpha) * G[u];  // dL_dG * G
+                            const float sx = sG * dx, sy = sG * dy;
+                            v[u][0] = sG;
+                            v[u][1] = sx;
+                            v[u][2] = sy;
+                            v[u][3] = sx * dx;
+                            v[u][4] = sx * dy;
+                            v[u][5] = sy * dy;
                         }
                     }
                     const unsigned anyA = __ballot_sync(FULL, pass[0]), anyB = __ballot_sync(FULL, pass[1]);
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
                             const uint32_t gid = *reinterpret_cast<const uint32_t*>(buf - slot[rsel] * RS + 44);
                             float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
                             if ((lane & 1) == 0) atomicAdd(dst + (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)), t);
-                            else if ((lane & 15) == 1) atomicAdd(dst + 8, o);
+                            else if ((lane & 15) == 1) atomicAdd(dst + 8, o);  // gacc row = the nine raw moments
                         }
                     }
                 }

@@ -86,6 +86,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
         if (spins > (1u << 24)) __trap();
 }
+// Waiting side of a long-latency hand-off (the producer waiting for its consumers): back off with nanosleep so
+// that the spinning warp does not steal issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity)
+{
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        __nanosleep(256);
+        if (spins > (1u << 22)) __trap();
+    }
+}
 // TMA bulk copy global -> shared (linear, 16-byte granularity), completion on an mbarrier. SASS: UBLKCP.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
 {

@@ -500,12 +500,25 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
         if (need) sh_stage_load(st, p.shs, M, (long long)idx - lane, p.P, need);
     }
     if (valid) {
+    // blend_bwd accumulated the raw moments [S, Sx, Sy, Sxx, Sxy, Syy, cr, cg, cb] of every Gaussian (see blend.cu);
+    // turn them into the reference's blend-stage gradients (backward.cu:523-554) with the per-Gaussian factors.
     float acc[9];
     {
         const float4* a4 = reinterpret_cast<const float4*>(p.gacc + i * GSTAR_GACC);
         const float4 a0 = a4[0], a1 = a4[1];
-        acc[0] = a0.x; acc[1] = a0.y; acc[2] = a0.z; acc[3] = a0.w; acc[4] = a1.x; acc[5] = a1.y; acc[6] = a1.z; acc[7] = a1.w;
-        acc[8] = p.gacc[i * GSTAR_GACC + 8];
+        const float m8 = p.gacc[i * GSTAR_GACC + 8];
+        const GRec* rc = p.recs + i;
+        const float4 r0 = *reinterpret_cast<const float4*>(rc);       // x y A B
+        const float2 r1 = *(reinterpret_cast<const float2*>(rc) + 2);  // C o
+        const float A = r0.z, B = r0.w, Cc = r1.x, o = r1.y;
+        const float S = a0.x, Sx = a0.y, Sy = a0.z, Sxx = a0.w, Sxy = a1.x, Syy = a1.y;
+        acc[0] = -(0.5f * p.W) * (A * Sx + B * Sy);   // dL_dmean2D.x  (ddelx_dx = 0.5 W)
+        acc[1] = -(0.5f * p.H) * (Cc * Sy + B * Sx);  // dL_dmean2D.y
+        acc[2] = -0.5f * Sxx;                         // dL_dconic.x
+        acc[3] = -0.5f * Sxy;                         // dL_dconic.y
+        acc[4] = -0.5f * Syy;                         // dL_dconic.w
+        acc[5] = a1.z; acc[6] = a1.w; acc[7] = m8;    // dL_dcolor
+        acc[8] = (radius > 0 && o != 0.f) ? S / o : 0.f;  // dL_dopacity = sum G*dL_dalpha = S / o
     }
     // blend-stage gradients in the reference's layouts (also outputs of the op / parity intermediates)
     p.dL_dmean2D[3 * i] = acc[0]; p.dL_dmean2D[3 * i + 1] = acc[1]; p.dL_dmean2D[3 * i + 2] = 0.f;
