@@ -140,7 +140,7 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
 
 constexpr int FWD_DYN_SMEM = NSTAGE * GSTAR_BATCH * RS + NCONS * QCAP * 32;  // record ring + per-pixel hit queues
 
-__global__ void __launch_bounds__(BLEND_THREADS) k_blend_fwd(BlendParams p)
+__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     unsigned char* s_rec = s_dyn;                                                   // [NSTAGE][GSTAR_BATCH * RS]
@@ -292,7 +292,7 @@ __device__ __forceinline__ float bfly_pair(float a, float b, unsigned m, unsigne
     return keep + __shfl_xor_sync(FULL, send, m);
 }
 
-__global__ void __launch_bounds__(BLEND_THREADS) k_blend_bwd(BlendParams p)
+__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
 {
     __shared__ __align__(128) unsigned char s_rec[NSTAGE * GSTAR_BATCH * RS];
     __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];

@@ -146,7 +146,21 @@ __device__ __forceinline__ void sh_stage_load(const ShStage& st, const float* __
     const int lane = threadIdx.x & 31;
     const int rowf = 3 * M;
     const float* base = shs + (size_t)first_row * rowf;
-    if (st.vec) {
+    if (st.vec && M == 16) {  // degree-3 rows: 12 float4 per row, padded to 13 -- constants let the division fold
+        const float4* b4 = reinterpret_cast<const float4*>(base);
+        float4* r4 = reinterpret_cast<float4*>(st.rows);
+        float4 v[12];
+#pragma unroll
+        for (int it = 0; it < 12; it++) {  // all 12 loads of the lane in flight before the first store
+            const int q = lane + 32 * it, g = q / 12;
+            v[it] = (((need_mask >> g) & 1u) && first_row + g < P) ? ldg_nc_f4(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 12; it++) {
+            const int q = lane + 32 * it, g = q / 12, j = q - g * 12;
+            r4[g * 13 + j] = v[it];
+        }
+    } else if (st.vec) {
         const int row4 = rowf >> 2, str4 = st.stride >> 2;
         const float4* b4 = reinterpret_cast<const float4*>(base);
         float4* r4 = reinterpret_cast<float4*>(st.rows);
@@ -171,7 +185,27 @@ __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restr
     const int lane = threadIdx.x & 31;
     const int rowf = 3 * M;
     float* base = dst + (size_t)first_row * rowf;
-    if (st.vec && ((((size_t)dst) & 15) == 0)) {
+    if (st.vec && M == 16 && ((((size_t)dst) & 15) == 0)) {
+        float4* b4 = reinterpret_cast<float4*>(base);
+        const float4* r4 = reinterpret_cast<const float4*>(st.rows);
+        float4 o[12];
+        if (accumulate) {
+#pragma unroll
+            for (int it = 0; it < 12; it++) {
+                const int q = lane + 32 * it, g = q / 12;
+                o[it] = (((row_mask >> g) & 1u) && first_row + g < P) ? b4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 12; it++) {
+            const int q = lane + 32 * it, g = q / 12, j = q - g * 12;
+            if (((row_mask >> g) & 1u) && first_row + g < P) {
+                float4 v = r4[g * 13 + j];
+                if (accumulate) { v.x += o[it].x; v.y += o[it].y; v.z += o[it].z; v.w += o[it].w; }
+                b4[q] = v;
+            }
+        }
+    } else if (st.vec && ((((size_t)dst) & 15) == 0)) {
         const int row4 = rowf >> 2, str4 = st.stride >> 2;
         float4* b4 = reinterpret_cast<float4*>(base);
         const float4* r4 = reinterpret_cast<const float4*>(st.rows);
@@ -236,7 +270,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* c, float3 pos,
     return make_float3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
 }
 
-__global__ void __launch_bounds__(256) k_preprocess_fwd(PreFwdParams p)
+__global__ void __launch_bounds__(256, 3) k_preprocess_fwd(PreFwdParams p)
 {
     extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_vm[16], s_pm[16];
