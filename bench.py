@@ -47,7 +47,7 @@ from gaustar_b200 import dist as gdist  # noqa: E402
 METRIC = "fwd+bwd views/sec at 1M surface Gaussians, 1080p; HBM GB/s vs roofline"
 UNIT = "views/s"
 P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
-VIEWS_PER_GPU = 8
+VIEWS_PER_GPU = 20  # BASELINE.json config #3: 160 views / 8 GPUs per step
 CAM_POOL = 32
 
 
@@ -382,7 +382,7 @@ def cpu_oracle_views_per_sec(n_views=1, small=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -435,4 +435,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        import torch.distributed as _d
+        if _d.is_available() and _d.is_initialized():
+            _d.destroy_process_group()

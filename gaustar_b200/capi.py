@@ -108,16 +108,17 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-class _Resizable:
-    """A torch uint8 tensor grown through the gstar_alloc_fn callback (cf. resizeFunctional, rasterize_points.cu:27-33)."""
+def _resizable(dev):
+    """A torch uint8 tensor grown through the gstar_alloc_fn callback (cf. resizeFunctional, rasterize_points.cu:27-33).
+    Returns (holder, callback); holder[0] is the tensor.  No reference cycle: the buffers are released as soon as the
+    caller drops them (a cycle would park ~300 MB per call until Python's cyclic GC happens to run)."""
+    holder = [torch.empty(0, dtype=torch.uint8, device=dev)]
 
-    def __init__(self, dev):
-        self.t = torch.empty(0, dtype=torch.uint8, device=dev)
-        self.cb = ALLOC_FN(self._alloc)
+    def alloc(_user, nbytes):
+        holder[0].resize_(int(nbytes))
+        return holder[0].data_ptr()
 
-    def _alloc(self, _user, nbytes):
-        self.t.resize_(int(nbytes))
-        return self.t.data_ptr()
+    return holder, ALLOC_FN(alloc)
 
 
 def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, W, H, shs=None, colors_precomp=None,
@@ -132,14 +133,14 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
     M = 0 if sh is None or sh.numel() == 0 else sh.shape[1]
     out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
     radii = torch.empty(P, dtype=torch.int32, device=dev)
-    geom, binning, image = _Resizable(dev), _Resizable(dev), _Resizable(dev)
+    (geom, geom_cb), (binning, binning_cb), (image, image_cb) = _resizable(dev), _resizable(dev), _resizable(dev)
     a = FwdArgs(P, sh_degree, M, _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(op), _ptr(sc), scale_modifier, _ptr(rot), _ptr(cov),
                 _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, int(prefiltered), _ptr(out_color), _ptr(radii), int(debug))
     with torch.cuda.device(dev):
-        R = _check(L.gstar_raster_forward(C.byref(a), geom.cb, None, binning.cb, None, image.cb, None, _stream(dev)))
+        R = _check(L.gstar_raster_forward(C.byref(a), geom_cb, None, binning_cb, None, image_cb, None, _stream(dev)))
     if P == 0:
         out_color.zero_()
-    return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom.t, binning=binning.t, image=image.t, _keep=keep)
+    return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom[0], binning=binning[0], image=image[0], _keep=keep)
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,

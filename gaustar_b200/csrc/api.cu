@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 
 #include "../../include/gstar_raster.h"
@@ -44,7 +45,8 @@ struct DevCtx {
     uint32_t* host_counts = nullptr;  // pinned + mapped: [0]=R [1]=overflow [2]=max tile
     uint32_t* host_counts_dev = nullptr;
     cudaEvent_t scan_done = nullptr;
-    double estimate = 0.0;  // running provision for R
+    double estimate = 0.0;  // running provision for R (instances)
+    int small_streak = 0;
     bool have_estimate = false;
 };
 thread_local DevCtx t_ctx[MAX_DEV];
@@ -270,9 +272,25 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
         CU_OK(cudaEventSynchronize(ctx->scan_done));
         R = ctx->host_counts[0];
         const bool overflow = R > cap;
-        // provision for the next call: 25% headroom over a slowly decaying high-water mark
-        ctx->estimate = std::max(ctx->estimate * 0.98, (double)R * 1.25 + 65536.0);
-        ctx->have_estimate = true;
+        // Provision for the next call: 25 % headroom over the high-water mark, quantised to 256 Ki instances so that
+        // the binning buffer keeps ONE size in steady state (a size that changes a little every call defeats the
+        // caller's caching allocator: every call would cudaMalloc a new block).  Shrinks only after 32 consecutive
+        // calls that needed less than half of it.
+        {
+            const double want = std::ceil(((double)R * 1.25 + 65536.0) / 262144.0) * 262144.0;
+            if (want > ctx->estimate) {
+                ctx->estimate = want;
+                ctx->small_streak = 0;
+            } else if (want * 2.0 < ctx->estimate) {
+                if (++ctx->small_streak >= 32) {
+                    ctx->estimate = want;
+                    ctx->small_streak = 0;
+                }
+            } else {
+                ctx->small_streak = 0;
+            }
+            ctx->have_estimate = true;
+        }
         if (!overflow) break;
         if (attempt == 1) return fail(GSTAR_ERR_INVALID, "instance count changed between attempts");
         cap = (size_t)R;  // exact size; tile_scan reruns to reset cursors and the device flag

@@ -51,12 +51,15 @@ class FlatGrads:
     def __init__(self, P: int, M: int, device):
         self.shapes = {"dL_dmeans3D": (P, 3), "dL_dscales": (P, 3), "dL_drotations": (P, 4), "dL_dopacity": (P, 1), "dL_dsh": (P, M, 3)}
         sizes = [int(torch.Size(s).numel()) for s in self.shapes.values()]
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        # every field starts on a 128-byte boundary: the kernels' 128-bit load/store paths need 16-byte alignment
+        starts, off = [], 0
+        for n in sizes:
+            starts.append(off)
+            off += (n + 31) // 32 * 32
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
         self.views: Dict[str, torch.Tensor] = {}
-        off = 0
-        for (k, s), n in zip(self.shapes.items(), sizes):
-            self.views[k] = self.flat[off:off + n].view(*s)
-            off += n
+        for (k, s), n, st in zip(self.shapes.items(), sizes, starts):
+            self.views[k] = self.flat[st:st + n].view(*s)
 
     def zero_(self):
         self.flat.zero_()

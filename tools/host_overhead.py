@@ -36,3 +36,33 @@ for fused in (False, True):
     tot, hf, hb = run(10, fused, sync_each=True)
     print(f"   sync each view: {tot:.3f} ms/view | host fwd {hf:.3f} bwd {hb:.3f}")
 print(torch.cuda.memory_summary(abbreviated=True)[:1500])
+
+# ---- two views in flight on two streams (independent views of one multi-view step) ----
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+flats = [gdist.FlatGrads(g.P, 16, "cuda"), gdist.FlatGrads(g.P, 16, "cuda")]
+def run2(n):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for i in range(n):
+        st = streams[i & 1]
+        with torch.cuda.stream(st):
+            kw = kws[i % len(kws)]
+            f = capi.forward(opacities=opac, W=W, H=H, **kw)
+            capi.backward(f, dpix, accumulate_into=flats[i & 1].views, **kw)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    return (t1 - t0) / n * 1e3
+run2(4)
+print(f"two streams, fused accumulate into per-stream buffers: {run2(24):.3f} ms/view wall")
+
+s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s_ev.record(); e_ev.record(); torch.cuda.synchronize()
+for fused in (False, True):
+    for st, nm in ((5, "blend_bwd"), (6, "preprocess_bwd")):
+        capi.profile_stage(st, s_ev, e_ev)
+        ts = []
+        for i in range(6):
+            kw = kws[i % len(kws)]
+            f = capi.forward(opacities=opac, W=W, H=H, **kw)
+            capi.backward(f, dpix, accumulate_into=flat.views if fused else None, **kw)
+            torch.cuda.synchronize(); ts.append(s_ev.elapsed_time(e_ev) * 1e3)
+        print(f"fused={fused} stage {nm}: {np.median(ts):.1f} us")
+capi.profile_stage(-1)
