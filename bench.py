@@ -299,12 +299,13 @@ def run_gpu(args, impl_name, rank, world, local):
     for k, p in leaves.items():
         p.grad = flat.views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
     copy_stream = torch.cuda.Stream(device)
-    slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), vm=torch.empty(4, 4, device=device), pm=torch.empty(4, 4, device=device),
-                  cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), tgt_f=torch.empty(3, H, W, device=device), vm=torch.empty(4, 4, device=device),
+                  pm=torch.empty(4, 4, device=device), cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
     h2d_per_view = H * W * 3 + (16 + 16 + 3) * 4
     means2D = torch.zeros(P, 3, device=device, requires_grad=True)
 
     def prefetch(slot, v, i):
+        """H2D of the next view's 8-bit target + camera on the copy stream, and its uint8 -> float CHW conversion there too."""
         s = slots[slot]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(s["free"])
@@ -312,6 +313,8 @@ def run_gpu(args, impl_name, rank, world, local):
             s["vm"].copy_(cam_host[v]["viewmatrix"], non_blocking=True)
             s["pm"].copy_(cam_host[v]["projmatrix"], non_blocking=True)
             s["cp"].copy_(cam_host[v]["campos"], non_blocking=True)
+            s["tgt_f"].copy_(s["tgt"].permute(2, 0, 1))
+            s["tgt_f"].mul_(1.0 / 255.0)
             s["ev"].record(copy_stream)
 
     def step_e2e(step):
@@ -329,8 +332,7 @@ def run_gpu(args, impl_name, rank, world, local):
                           viewmatrix=s["vm"], projmatrix=s["pm"], sh_degree=SH_DEG, campos=s["cp"], prefiltered=False, debug=False)
             img, _radii = Rasterizer(rs)(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
                                          scales=leaves["scales"], rotations=leaves["rotations"])
-            tgt = s["tgt"].permute(2, 0, 1).float().mul_(1.0 / 255.0)
-            loss = (img - tgt).abs().mean()
+            loss = torch.nn.functional.l1_loss(img, s["tgt_f"])
             loss.backward()
             loss_sum += loss.detach()
             s["free"].record(cur)

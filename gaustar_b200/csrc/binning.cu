@@ -56,13 +56,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
     if (tid == 0) { s_nbig = 0; s_max = 0; }
     for (int b = tid; b < LPT_BUCKETS; b += SCAN_THREADS) s_hist[b] = 0;
     __syncthreads();
-    uint32_t sum = 0, mx = 0;
+    uint32_t sum = 0, mx = 0, n_empty = 0;
     for (int t = t0; t < t1; t++) {
         const uint32_t c = p.tile_count[t];
         sum += c;
         mx = max(mx, c);
-        atomicAdd(&s_hist[lpt_bucket(c)], 1u);
+        if (c == 0) n_empty++;  // most tiles are empty: count them locally instead of hammering one shared counter
+        else atomicAdd(&s_hist[lpt_bucket(c)], 1u);
     }
+    if (n_empty) atomicAdd(&s_hist[0], n_empty);
     s_part[tid] = sum;
     __syncthreads();
     // Hillis-Steele inclusive scan of 1024 partials
@@ -92,7 +94,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         for (int b = LPT_BUCKETS - 1; b >= 0; b--) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }
     }
     __syncthreads();
-    for (int t = t0; t < t1; t++) p.tile_order[atomicAdd(&s_hist[lpt_bucket(p.tile_count[t])], 1u)] = (uint32_t)t;
+    {
+        uint32_t empty_base = n_empty ? atomicAdd(&s_hist[0], n_empty) : 0u;
+        for (int t = t0; t < t1; t++) {
+            const uint32_t c = p.tile_count[t];
+            const uint32_t pos = c ? atomicAdd(&s_hist[lpt_bucket(c)], 1u) : empty_base++;
+            p.tile_order[pos] = (uint32_t)t;
+        }
+    }
     if (tid == 0) {
         const uint32_t total = s_part[SCAN_THREADS - 1];
         const uint32_t ovf = total > p.capacity ? 1u : 0u;

@@ -126,8 +126,8 @@ def timeit(fn, n=20, warm=3):
     return s.elapsed_time(e) / n
 
 
-def speed(P, W, H, use_sh=True):
-    g = scene.surface_gaussians(P, sh_degree=3)
+def speed(P, W, H, use_sh=True, random=False):
+    g = scene.random_gaussians(P, 3, seed=1, scale_range=(0.003, 0.06)) if random else scene.surface_gaussians(P, sh_degree=3)
     cams = scene.dome_cameras(8, W, H)
     kws = [make_inputs(g, c, use_sh) for c in cams]
     dpix = torch.randn(3, H, W, device="cuda") / (W * H)
@@ -145,7 +145,7 @@ def speed(P, W, H, use_sh=True):
 
     tm = timeit(mine)
     tr = timeit(ref, n=8, warm=2)
-    print(f"== speed P={g.P} {W}x{H} sh={use_sh}: mine {tm:.3f} ms/view ({1000 / tm:.0f} views/s) | ref(shim, sync'd) {tr:.3f} ms/view "
+    print(f"== speed {'random-cloud' if random else 'surface'} P={g.P} {W}x{H} sh={use_sh}: mine {tm:.3f} ms/view ({1000 / tm:.0f} views/s) | ref(shim, sync'd) {tr:.3f} ms/view "
           f"({1000 / tr:.0f} views/s) | x{tr / tm:.2f}")
     # per-stage times of mine
     s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
@@ -182,3 +182,4 @@ if __name__ == "__main__":
         speed(1000000, 1920, 1080, True)
         speed(1000000, 1920, 1080, False)
         speed(200000, 1920, 1080, True)
+        speed(500000, 1920, 1080, True, random=True)
