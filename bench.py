@@ -73,7 +73,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -245,21 +245,48 @@ def run_gpu(args, impl_name, rank, world, local):
             a.record(); b.record()
         torch.cuda.synchronize()
     R_sum, V_count = 0, 0
+    # Our arm keeps TWO views of a step in flight on two CUDA streams (the views of a multi-view step are independent;
+    # every kernel of the library is launched on the caller's current stream).  Each stream accumulates into its own flat
+    # gradient buffer; the two are summed once per step before the single allreduce.  The reference launches on the
+    # legacy default stream and blocks on a D2H copy inside every forward, so it runs its views one after the other.
+    n_streams = 2 if impl.fused_accumulate else 1
+    side = [torch.cuda.Stream(device) for _ in range(n_streams)] if n_streams > 1 else []
+    flats = [flat] + [gdist.FlatGrads(P, M, device) for _ in range(n_streams - 1)]
+    fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in side]
+
+    def one_view(step, i, v, timed, fl):
+        nonlocal R_sum, V_count
+        if prof is not None and timed:
+            a, b = prof[(step - args.warmup) * VIEWS_PER_GPU + i]
+            capi.profile_stage(capi.STAGES.index("blend_bwd"), a, b)
+        if impl.fused_accumulate:
+            R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]), fl)
+        else:
+            R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]))
+            fl.accumulate(grads)
+        if timed:
+            R_sum += int(R); V_count += 1
 
     def step_value(step, timed):
-        nonlocal R_sum, V_count
-        flat.zero_()
-        for i, v in enumerate(my_views(step)):
-            if prof is not None and timed:
-                a, b = prof[(step - args.warmup) * VIEWS_PER_GPU + i]
-                capi.profile_stage(capi.STAGES.index("blend_bwd"), a, b)
-            if impl.fused_accumulate:
-                R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]), flat)
-            else:
-                R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]))
-                flat.accumulate(grads)
-            if timed:
-                R_sum += int(R); V_count += 1
+        for fl in flats:
+            fl.zero_()
+        views = my_views(step)
+        if not side:
+            for i, v in enumerate(views):
+                one_view(step, i, v, timed, flat)
+        else:
+            main = torch.cuda.current_stream(device)
+            fork.record(main)
+            for st in side:
+                st.wait_event(fork)
+            for i, v in enumerate(views):
+                with torch.cuda.stream(side[i % n_streams]):
+                    one_view(step, i, v, timed, flats[i % n_streams])
+            for st, ev in zip(side, joins):
+                ev.record(st)
+                main.wait_event(ev)
+            for fl in flats[1:]:
+                flat.flat.add_(fl.flat)
         flat.allreduce()
 
     for s in range(args.warmup):
@@ -294,15 +321,24 @@ def run_gpu(args, impl_name, rank, world, local):
 
     # ---------------- public-API arm (e2e): host buffers, copies inside the timed region ----------------
     Settings, Rasterizer = make_autograd_rasterizer(impl_name)
-    leaves = {k: params[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
     name_of = {"means3D": "dL_dmeans3D", "scales": "dL_dscales", "rotations": "dL_drotations", "opacities": "dL_dopacity", "shs": "dL_dsh"}
-    for k, p in leaves.items():
-        p.grad = flat.views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
+    base_leaves = {k: params[k].clone() for k in name_of}
+    # one set of autograd leaves per compute stream (same storage, separate .grad buffers = the per-stream flat buffers),
+    # so that each stream's AccumulateGrad nodes run on that stream and never touch the other stream's buffer
+    leaf_sets, m2d_sets = [], []
+    e2e_streams = side if side else [torch.cuda.current_stream(device)]
+    for si, st in enumerate(e2e_streams):
+        with torch.cuda.stream(st):
+            ls = {k: base_leaves[k].detach().requires_grad_(True) for k in name_of}
+            for k, p_ in ls.items():
+                p_.grad = flats[si].views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
+            leaf_sets.append(ls)
+            m2d_sets.append(torch.zeros(P, 3, device=device, requires_grad=True))
+    torch.cuda.synchronize()
     copy_stream = torch.cuda.Stream(device)
     slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), tgt_f=torch.empty(3, H, W, device=device), vm=torch.empty(4, 4, device=device),
                   pm=torch.empty(4, 4, device=device), cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
     h2d_per_view = H * W * 3 + (16 + 16 + 3) * 4
-    means2D = torch.zeros(P, 3, device=device, requires_grad=True)
 
     def prefetch(slot, v, i):
         """H2D of the next view's 8-bit target + camera on the copy stream, and its uint8 -> float CHW conversion there too."""
@@ -317,27 +353,44 @@ def run_gpu(args, impl_name, rank, world, local):
             s["tgt_f"].mul_(1.0 / 255.0)
             s["ev"].record(copy_stream)
 
+    loss_acc = [torch.zeros((), device=device) for _ in e2e_streams]
+
     def step_e2e(step):
-        flat.zero_()
+        main = torch.cuda.current_stream(device)
+        for fl in flats:
+            fl.zero_()
+        for la in loss_acc:
+            la.zero_()
         views = my_views(step)
-        loss_sum = torch.zeros((), device=device)
         prefetch(0, views[0], 0)
-        cur = torch.cuda.current_stream(device)
+        if side:
+            fork.record(main)
+            for st in side:
+                st.wait_event(fork)
+        ns = len(e2e_streams)
         for i, v in enumerate(views):
             s = slots[i & 1]
             if i + 1 < len(views):
                 prefetch((i + 1) & 1, views[i + 1], i + 1)
-            cur.wait_event(s["ev"])
-            rs = Settings(image_height=H, image_width=W, tanfovx=cam_host[v]["tanfovx"], tanfovy=cam_host[v]["tanfovy"], bg=bg, scale_modifier=1.0,
-                          viewmatrix=s["vm"], projmatrix=s["pm"], sh_degree=SH_DEG, campos=s["cp"], prefiltered=False, debug=False)
-            img, _radii = Rasterizer(rs)(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
-                                         scales=leaves["scales"], rotations=leaves["rotations"])
-            loss = torch.nn.functional.l1_loss(img, s["tgt_f"])
-            loss.backward()
-            loss_sum += loss.detach()
-            s["free"].record(cur)
+            st, ls = e2e_streams[i % ns], leaf_sets[i % ns]
+            with torch.cuda.stream(st):
+                st.wait_event(s["ev"])
+                rs = Settings(image_height=H, image_width=W, tanfovx=cam_host[v]["tanfovx"], tanfovy=cam_host[v]["tanfovy"], bg=bg, scale_modifier=1.0,
+                              viewmatrix=s["vm"], projmatrix=s["pm"], sh_degree=SH_DEG, campos=s["cp"], prefiltered=False, debug=False)
+                img, _radii = Rasterizer(rs)(means3D=ls["means3D"], means2D=m2d_sets[i % ns], opacities=ls["opacities"], shs=ls["shs"],
+                                             scales=ls["scales"], rotations=ls["rotations"])
+                loss = torch.nn.functional.l1_loss(img, s["tgt_f"])
+                loss.backward()
+                loss_acc[i % ns] += loss.detach()
+                s["free"].record(st)
+        if side:
+            for st, ev in zip(side, joins):
+                ev.record(st)
+                main.wait_event(ev)
+            for fl in flats[1:]:
+                flat.flat.add_(fl.flat)
         flat.allreduce()
-        return float(loss_sum.item())  # D2H read of the step's result
+        return float(sum(loss_acc).item())  # D2H read of the step's result
 
     for e in slots:
         e["free"].record(torch.cuda.current_stream(device))
@@ -354,7 +407,7 @@ def run_gpu(args, impl_name, rank, world, local):
     e2e_val = VIEWS_PER_GPU * world * e2e_steps / (ms_e2e / 1e3)
     e2e = {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_per_view * VIEWS_PER_GPU, "d2h_bytes_per_step": 4,
            "api": "diff_gaussian_rasterization.GaussianRasterizer + autograd; target image (uint8) and camera copied from pinned host memory per view "
-                  "(prefetched on a copy stream), loss scalar read back per step"}
+                  "(prefetched on a copy stream), loss scalar read back per step; compute streams: " + str(len(e2e_streams))}
     return dict(value=value, ms_per_step=ms_value / args.steps, roofline=roofline, e2e=e2e, clocks=clk, P=P, M=M, device_name=torch.cuda.get_device_name(device),
                 launches=impl.launches_per_view * VIEWS_PER_GPU * args.steps, impl_desc=impl.name, allreduce_bytes=flat.nbytes)
 
@@ -394,7 +447,7 @@ def main():
     have_gpu = torch.cuda.is_available()
     config = {"workload": f"surface-1M-1080p-sh3 ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
               "gaussians": None, "resolution": [W, H], "sh_degree": SH_DEG, "views_per_step": VIEWS_PER_GPU * world,
-              "parallelism": f"view-sharded dp{world} + 1 allreduce/step", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
+              "parallelism": f"view-sharded dp{world} + 1 allreduce/step; ours: 2 views in flight on 2 CUDA streams per GPU", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
 
     if args.impl == "reference":
         use_gpu_ref = have_gpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C.so"))

@@ -303,3 +303,53 @@ def test_accumulate_param_grads_equals_sum_of_views():
     torch.cuda.synchronize()
     for k in gdist.GRAD_FIELDS:
         assert Hh.rel_err(flat.views[k].cpu(), ref.views[k].cpu()) < 1e-5, k
+
+
+def test_two_streams_autograd_equals_single_stream():
+    """bench.py's e2e arm keeps two views in flight on two CUDA streams with one set of autograd leaves per stream
+    (same storage, separate .grad buffers).  The summed gradients must equal the single-stream result."""
+    import diff_gaussian_rasterization as dgr
+    from gaustar_b200 import dist as gdist
+    g = scene.surface_gaussians(12000, 3, seed=7)
+    cams = scene.dome_cameras(6, 320, 192)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    base = {"means3D": t(g.means3D), "scales": t(g.scales), "rotations": t(g.rotations), "opacities": t(g.opacities), "shs": t(g.shs)}
+    name_of = {"means3D": "dL_dmeans3D", "scales": "dL_dscales", "rotations": "dL_drotations", "opacities": "dL_dopacity", "shs": "dL_dsh"}
+    bg = torch.tensor([0.0, 1.0, 0.0], device="cuda")
+    targets = [torch.rand(3, 192, 320, device="cuda", generator=torch.Generator("cuda").manual_seed(i)) for i in range(4)]
+
+    def render_loss(ls, cam, tgt):
+        rs = dgr.GaussianRasterizationSettings(192, 320, cam.tanfovx, cam.tanfovy, bg, 1.0, t(cam.viewmatrix), t(cam.projmatrix), 3, t(cam.campos), False, False)
+        img, _ = dgr.GaussianRasterizer(rs)(means3D=ls["means3D"], means2D=torch.zeros_like(ls["means3D"], requires_grad=True), opacities=ls["opacities"],
+                                            shs=ls["shs"], scales=ls["scales"], rotations=ls["rotations"])
+        torch.nn.functional.l1_loss(img, tgt).backward()
+
+    def make_leaves(flat):
+        ls = {k: v.detach().requires_grad_(True) for k, v in base.items()}
+        for k, p_ in ls.items():
+            p_.grad = flat.views[name_of[k]]
+        return ls
+
+    ref = gdist.FlatGrads(g.P, 16, "cuda")
+    ls = make_leaves(ref)
+    for i in range(4):
+        render_loss(ls, cams[i], targets[i])
+    torch.cuda.synchronize()
+
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    flats = [gdist.FlatGrads(g.P, 16, "cuda"), gdist.FlatGrads(g.P, 16, "cuda")]
+    sets = []
+    for st, fl in zip(streams, flats):
+        with torch.cuda.stream(st):
+            sets.append(make_leaves(fl))
+    torch.cuda.synchronize()
+    for rep in range(3):  # repeat: a race would show up as run-to-run differences
+        for fl in flats:
+            fl.zero_()
+        torch.cuda.synchronize()
+        for i in range(4):
+            with torch.cuda.stream(streams[i & 1]):
+                render_loss(sets[i & 1], cams[i], targets[i])
+        torch.cuda.synchronize()
+        total = flats[0].flat + flats[1].flat
+        assert Hh.rel_err(total.cpu(), ref.flat.cpu()) < 1e-4, rep
