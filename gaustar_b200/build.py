@@ -4,7 +4,8 @@
   gaustar_b200/_C*.so                   torch shim exposing the reference's three pybind functions
 
 Both are plain nvcc / g++ invocations (no JIT cache): the built files travel with the repo snapshot
-to the GPU box.  ``python -m gaustar_b200.build`` builds everything.
+to the GPU box.  ``python gaustar_b200/build.py`` builds everything (run as a script: importing the package needs the
+built extension).
 """
 from __future__ import annotations
 

@@ -63,7 +63,7 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is not built; run `python -m gaustar_b200.build`")
+            raise ImportError(f"{LIB_PATH} is not built; run `python gaustar_b200/build.py`")
         L = C.CDLL(LIB_PATH)
         L.gstar_last_error.restype = C.c_char_p
         L.gstar_stage_name.restype = C.c_char_p

@@ -56,7 +56,9 @@ class FlatGrads:
         for n in sizes:
             starts.append(off)
             off += (n + 31) // 32 * 32
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        raw = torch.zeros(off + 32, dtype=torch.float32, device=device)
+        skip = (-raw.data_ptr() % 128) // 4  # CPU allocations are only 64-byte aligned; CUDA ones give skip == 0
+        self.flat = raw[skip:skip + off]
         self.views: Dict[str, torch.Tensor] = {}
         for (k, s), n, st in zip(self.shapes.items(), sizes, starts):
             self.views[k] = self.flat[st:st + n].view(*s)

@@ -17,7 +17,7 @@ try:
 except ImportError as e:  # fail loudly: there is no fallback implementation
     raise ImportError(
         "gaustar_b200._C (the sm_100a CUDA extension) is not built or cannot be loaded: "
-        f"{e}.  Run `python -m gaustar_b200.build`."
+        f"{e}.  Run `python gaustar_b200/build.py`."
     ) from e
 
 

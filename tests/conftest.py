@@ -17,7 +17,10 @@ def _native_built():
     """Build the checker (oracle) and, if missing, the product library. Building is not using."""
     from oracle import oracle as O
     O.build()
-    from gaustar_b200 import build as B
+    import importlib.util  # by path: importing the package itself requires the built extension
+    spec = importlib.util.spec_from_file_location("_gstar_build", os.path.join(ROOT, "gaustar_b200", "build.py"))
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)
     if not (os.path.exists(B.LIB) and os.path.exists(B.EXT)):
         B.build_all()
     yield
