@@ -22,7 +22,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 EXPORTED = [
     "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
     "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
-    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name",
+    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state",
 ]
 STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
@@ -80,6 +80,8 @@ def lib():
         L.gstar_image_views.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.gstar_binning_views.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.gstar_profile_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.gstar_set_hit_log.argtypes = [C.c_int]
+        L.gstar_hit_log_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -227,3 +229,15 @@ def profile_stage(stage: int, start: Optional[torch.cuda.Event] = None, stop: Op
     s = C.c_void_p(start.cuda_event) if start is not None else None
     e = C.c_void_p(stop.cuda_event) if stop is not None else None
     _check(lib().gstar_profile_stage(stage, s, e))
+
+
+def set_hit_log(mode: int) -> int:
+    """gstar_set_hit_log: 0 = walk-back backward only, 1 = hit log when it fits (default).  Returns the previous mode."""
+    return int(lib().gstar_set_hit_log(int(mode)))
+
+
+def hit_log_state(fwd):
+    """(slots_needed, slots_capacity, in_use) of one forward call -- synchronous, for tests."""
+    need, cap, used = C.c_uint64(), C.c_uint64(), C.c_int()
+    _check(lib().gstar_hit_log_state(_ptr(fwd["image"]), C.byref(need), C.byref(cap), C.byref(used)))
+    return int(need.value), int(cap.value), bool(used.value)

@@ -11,6 +11,7 @@
 // on the device flag and binning + blend are re-enqueued with an exact-size buffer.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -48,7 +49,27 @@ struct DevCtx {
     double estimate = 0.0;  // running provision for R (instances)
     int small_streak = 0;
     bool have_estimate = false;
+    double log_estimate = 0.0;  // running provision for the hit log (slots); 0 with log_have: log off for this workload
+    int log_small_streak = 0;
+    bool log_have = false;
 };
+int g_hit_log_mode = -1;  // -1: read GSTAR_HIT_LOG on first use; 0 off; 1 auto
+double g_hit_log_max_slots = 0.0;
+
+bool hit_log_enabled()
+{
+    if (g_hit_log_mode < 0) {
+        const char* e = getenv("GSTAR_HIT_LOG");
+        g_hit_log_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (g_hit_log_max_slots == 0.0) {
+        const char* e = getenv("GSTAR_HIT_LOG_MAX_MB");  // ceiling of the log (default 8 GiB of the 180 GB of HBM)
+        const double mb = e ? atof(e) : 8192.0;
+        g_hit_log_max_slots = std::max(mb, 1.0) * 1048576.0 / sizeof(GHit);
+    }
+    return g_hit_log_mode != 0;
+}
+constexpr double LOG_QUANTUM = 4194304.0;  // slots (64 MiB): keeps the binning buffer at one size in steady state
 thread_local DevCtx t_ctx[MAX_DEV];
 
 struct Profile {
@@ -92,7 +113,7 @@ int get_ctx(DevCtx** out)
 
 // ---- private layouts of the three opaque buffers ----
 struct ImgLayout {
-    size_t hdr, final_T, n_contrib, ranges, tile_count, tile_cursor, big_tiles, tile_order, total;
+    size_t hdr, final_T, n_contrib, pixstate, ranges, tile_count, tile_cursor, big_tiles, tile_order, total;
 };
 ImgLayout img_layout(int W, int H)
 {
@@ -103,6 +124,7 @@ ImgLayout img_layout(int W, int H)
     L.hdr = o; o = align_up(o + sizeof(GHeader), 128);
     L.final_T = o; o = align_up(o + npix * 4, 128);
     L.n_contrib = o; o = align_up(o + npix * 4, 128);
+    L.pixstate = o; o = align_up(o + npix * 16, 128);
     L.ranges = o; o = align_up(o + T * 8, 128);
     L.tile_count = o; o = align_up(o + T * 4, 128);
     L.tile_cursor = o; o = align_up(o + T * 4, 128);
@@ -112,15 +134,16 @@ ImgLayout img_layout(int W, int H)
     return L;
 }
 struct BinLayout {
-    size_t packed, point_list, entries, total;
+    size_t packed, point_list, entries, log, total;
 };
-BinLayout bin_layout(size_t cap)
+BinLayout bin_layout(size_t cap, size_t log_slots)
 {
     BinLayout L;
-    L.packed = 0;  // first, so that backward needs no capacity to find it
+    L.packed = 0;  // first, so that backward needs no capacity to find it (the other offsets travel in the header)
     L.point_list = align_up(cap * GSTAR_REC_SMEM, 128);
     L.entries = align_up(L.point_list + cap * 4, 128);
-    L.total = align_up(L.entries + cap * 8, 128);
+    L.log = align_up(L.entries + cap * 8, 128);
+    L.total = align_up(L.log + log_slots * sizeof(GHit), 128);
     return L;
 }
 
@@ -150,7 +173,15 @@ int gstar_abi_version(void) { return GSTAR_ABI_VERSION; }
 
 size_t gstar_geom_bytes(int P) { return align_up((size_t)std::max(P, 0) * sizeof(GRec), 128) + 128; }
 size_t gstar_image_bytes(int width, int height) { return img_layout(width, height).total + 128; }
-size_t gstar_binning_bytes(size_t cap) { return bin_layout(cap).total + 128; }
+size_t gstar_binning_bytes(size_t cap) { return bin_layout(cap, 0).total + 128; }
+
+int gstar_set_hit_log(int mode)
+{
+    hit_log_enabled();
+    const int old = g_hit_log_mode;
+    if (mode == 0 || mode == 1) g_hit_log_mode = mode;
+    return old;
+}
 
 const char* gstar_stage_name(int stage)
 {
@@ -215,7 +246,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     STAGE_CHECK("preprocess_fwd");
 
     BinParams bp;
-    bp.P = a->P; bp.gx = gx; bp.gy = gy; bp.num_tiles = T;
+    bp.P = a->P; bp.gx = gx; bp.gy = gy; bp.num_tiles = T; bp.W = W; bp.H = H;
     bp.recs = (const GRec*)geom; bp.hdr = hdr; bp.tile_count = tile_count;
     bp.tile_cursor = (uint32_t*)(img + IL.tile_cursor);
     bp.ranges = (uint32_t*)(img + IL.ranges);
@@ -228,6 +259,30 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bl.recs = (const GRec*)geom; bl.hdr = hdr; bl.ranges = bp.ranges; bl.tile_order = bp.tile_order; bl.bg = a->background;
     bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
     bl.dL_dpix = nullptr; bl.gacc = nullptr;
+    bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = ctx->host_counts_dev;
+
+    // Hit-log provision: the slots the previous view needed (published by its blend_fwd; a hint, it may lag) with the
+    // same grow-at-once / shrink-slowly / quantised policy as the instance count.  A view whose log does not fit simply
+    // takes the walk-back backward (device-side flag), so a wrong guess costs speed, never correctness.
+    const bool use_log = hit_log_enabled();
+    if (use_log) {
+        const double need = (double)(((unsigned long long)ctx->host_counts[5] << 32) | ctx->host_counts[4]);
+        if (need > 0.0) {
+            const double want = need * 1.25 > g_hit_log_max_slots ? 0.0 : std::ceil((need * 1.25 + 65536.0) / LOG_QUANTUM) * LOG_QUANTUM;
+            if (!ctx->log_have || want > ctx->log_estimate || (want == 0.0 && need > g_hit_log_max_slots)) {
+                ctx->log_estimate = want;
+                ctx->log_small_streak = 0;
+            } else if (want * 2.0 < ctx->log_estimate) {
+                if (++ctx->log_small_streak >= 32) {
+                    ctx->log_estimate = want;
+                    ctx->log_small_streak = 0;
+                }
+            } else {
+                ctx->log_small_streak = 0;
+            }
+            ctx->log_have = true;
+        }
+    }
 
     size_t cap = ctx->have_estimate ? (size_t)ctx->estimate : 0;
     uint32_t R = 0;
@@ -235,12 +290,20 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
         char* bin = nullptr;
         if (cap > 0) {
             if (cap > 0xfffffff0ull) return fail(GSTAR_ERR_INVALID, "more than 2^32 instances");
-            bin = binning_alloc(binning_user, gstar_binning_bytes(cap));
+        }
+        size_t log_slots = 0;
+        if (use_log && cap > 0) {
+            const double guess = ctx->log_have ? ctx->log_estimate : std::ceil((double)cap * 24.0 / LOG_QUANTUM) * LOG_QUANTUM;
+            log_slots = (guess <= g_hit_log_max_slots && guess < 4.0e9) ? (size_t)guess : 0;
+        }
+        const BinLayout BL = bin_layout(cap, log_slots);
+        bp.capacity = (uint32_t)cap;
+        bp.log_capacity = log_slots; bp.off_point_list = BL.point_list; bp.off_log = BL.log;
+        if (cap > 0) {
+            bin = binning_alloc(binning_user, BL.total + 128);
             if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
             bin = aligned128(bin);
         }
-        const BinLayout BL = bin_layout(cap);
-        bp.capacity = (uint32_t)cap;
         bp.point_list = bin ? (uint32_t*)(bin + BL.point_list) : nullptr;
         bp.packed = bin ? (unsigned char*)(bin + BL.packed) : nullptr;
         bp.entries = bin ? (uint2*)(bin + BL.entries) : nullptr;
@@ -302,7 +365,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             char* bin = binning_alloc(binning_user, gstar_binning_bytes(1));
             if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
             bl.packed = (unsigned char*)aligned128(bin);
-            bp.capacity = 1;
+            bp.capacity = 1; bp.log_capacity = 0; bp.off_point_list = 0; bp.off_log = 0;
             launch_tile_scan(bp, stream);
             launch_blend_fwd(bl, stream);
             STAGE_CHECK("blend_fwd(empty)");
@@ -336,8 +399,11 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         bl.bg = a->background;
         bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
         bl.dL_dpix = a->dL_dpix; bl.gacc = a->blend_grad_scratch;
+        bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = nullptr;
         {
+            // exactly one of the two does the work, decided on the device by the forward's log_overflow flag
             StageScope sc(GSTAR_STAGE_BLEND_BWD, stream);
+            launch_blend_bwd_gather(bl, stream);
             launch_blend_bwd(bl, stream);
         }
         STAGE_CHECK("blend_bwd");
@@ -405,9 +471,20 @@ int gstar_binning_views(char* binning_buffer, char* image_buffer, uint32_t** poi
     GHeader h;
     cudaError_t e = cudaMemcpy(&h, aligned128(image_buffer), sizeof(GHeader), cudaMemcpyDeviceToHost);  // test helper: synchronous
     if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
-    const BinLayout BL = bin_layout(h.capacity);
-    if (point_list) *point_list = (uint32_t*)(aligned128(binning_buffer) + BL.point_list);
+    if (point_list) *point_list = (uint32_t*)(aligned128(binning_buffer) + h.off_point_list);
     if (capacity) *capacity = h.capacity;
+    return 0;
+}
+
+int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, uint64_t* slots_capacity, int* in_use)
+{
+    if (!image_buffer) return fail(GSTAR_ERR_INVALID, "null image buffer");
+    GHeader h;
+    cudaError_t e = cudaMemcpy(&h, aligned128(image_buffer), sizeof(GHeader), cudaMemcpyDeviceToHost);  // test helper: synchronous
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
+    if (slots_needed) *slots_needed = h.log_cursor;
+    if (slots_capacity) *slots_capacity = h.log_capacity;
+    if (in_use) *in_use = h.log_overflow ? 0 : 1;
     return 0;
 }
 

@@ -111,6 +111,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         p.hdr->n_big = s_nbig;
         p.hdr->big_cursor = 0;
         p.hdr->max_tile = s_max;
+        p.hdr->log_overflow = p.log_capacity ? 0u : 1u;
+        p.hdr->log_cursor = 0ull;
+        p.hdr->log_capacity = p.log_capacity;
+        p.hdr->off_point_list = p.off_point_list;
+        p.hdr->off_log = p.off_log;
         if (p.host_counts) {  // zero-copy write of R to pinned host memory: no separate D2H memcpy
             p.host_counts[1] = ovf;
             p.host_counts[2] = s_max;
@@ -267,16 +272,64 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, uint32_t t
 // Write the sorted list of one tile: point_list (the reference's sorted value list) and the tile-contiguous packed
 // record stream the blend kernels read with one TMA bulk copy per 256 entries: the first 44 bytes of the Gaussian's
 // GRec followed by its index.  Random 48-byte reads hit the L2-resident GRec array; writes are contiguous.
-__device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t start, const uint64_t* keys, uint32_t n, uint32_t tid, uint32_t nt)
+__device__ __forceinline__ uint32_t foot_area(uint32_t bbx, uint32_t bby, int tx0, int ty0, int limx, int limy)
 {
+    const Foot f = clip_foot(bbx, bby, tx0, ty0, limx, limy);
+    return (f.w > 0 && f.h > 0) ? (uint32_t)(f.w * f.h) : 0u;
+}
+
+// The last word of a packed record is the instance's first HIT-LOG slot: every instance owns one 16-byte slot per
+// pixel of its alpha-bounds inside this tile (clip_foot).  Slots of a tile are contiguous (exclusive scan over the
+// CTA, any order), tiles take their block from a global cursor.  The cursor keeps counting when the log is too small
+// (or disabled) so that the host learns the size this view needs.
+__device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, uint32_t start, const uint64_t* keys, uint32_t n, uint32_t tid,
+                                             uint32_t nt)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ unsigned long long s_base;
     const float4* recs = reinterpret_cast<const float4*>(p.recs);
     float4* out = reinterpret_cast<float4*>(p.packed + (size_t)start * GSTAR_REC_SMEM);
+    const int tx0 = (int)(tile % (uint32_t)p.gx) * GSTAR_TILE, ty0 = (int)(tile / (uint32_t)p.gx) * GSTAR_TILE;
+    const int limx = min(GSTAR_TILE - 1, p.W - 1 - tx0), limy = min(GSTAR_TILE - 1, p.H - 1 - ty0);
+    uint32_t mine = 0;
+    for (uint32_t i = tid; i < n; i += nt) {
+        const uint32_t id = (uint32_t)keys[i];
+        const uint2 bb = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(p.recs) + (size_t)id * GSTAR_REC_BYTES + 32);
+        mine += foot_area(bb.x, bb.y, tx0, ty0, limx, limy);
+    }
+    const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < nwarps ? s_warp[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += v;
+        }
+        s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+        if (lane == 31) {
+            const unsigned long long base = atomicAdd(&p.hdr->log_cursor, (unsigned long long)wi);
+            if (base + wi > p.log_capacity) p.hdr->log_overflow = 1u;
+            s_base = base;
+        }
+    }
+    __syncthreads();
+    uint32_t slot = (uint32_t)s_base + s_warp[warp] + (incl - mine);
     for (uint32_t i = tid; i < n; i += nt) {
         const uint32_t id = (uint32_t)keys[i];
         p.point_list[start + i] = id;
         const float4 a = recs[(size_t)id * 4], b = recs[(size_t)id * 4 + 1];
         float4 c = recs[(size_t)id * 4 + 2];
-        c.w = __uint_as_float(id);
+        c.w = __uint_as_float(slot);
+        slot += foot_area(__float_as_uint(c.x), __float_as_uint(c.y), tx0, ty0, limx, limy);
         out[(size_t)i * 3] = a; out[(size_t)i * 3 + 1] = b; out[(size_t)i * 3 + 2] = c;
     }
 }
@@ -297,7 +350,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
         for (uint32_t i = tid; i < n; i += nt) s_keys[i] = g[i];
         __syncthreads();
         bitonic_sort(s_keys, n, tid, nt);
-        write_sorted(p, start, s_keys, n, tid, nt);
+        write_sorted(p, tile, start, s_keys, n, tid, nt);
         return;
     }
     uint32_t npad = CH;
@@ -336,7 +389,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
             __syncthreads();
         }
     }
-    write_sorted(p, start, g, n, tid, nt);
+    write_sorted(p, tile, start, g, n, tid, nt);
 }
 
 int tile_sort_setup()

@@ -155,6 +155,18 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WarpGeom g = warp_geom(tile, p.gx, p.W, p.H);
     const float pxf = (float)g.px, pyf = (float)g.py;
+    // hit log (see k_blend_bwd_gather): every blended (instance, pixel) pair records the transmittance in front of it
+    // and the colour accumulated up to and including it in the instance's slot for this pixel
+    const bool log_on = p.hdr->log_overflow == 0u;
+    GHit* const hitlog = reinterpret_cast<GHit*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
+    const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
+    const int lim_x = min(GSTAR_TILE - 1, p.W - 1 - tile_x0), lim_y = min(GSTAR_TILE - 1, p.H - 1 - tile_y0);
+    const int lx = g.px - tile_x0, ly = g.py - tile_y0;
+    if (blockIdx.x == 0 && tid == 0 && p.host_counts) {  // size the next call's log: slots this view needed
+        const unsigned long long need = p.hdr->log_cursor;
+        p.host_counts[4] = (uint32_t)need;
+        p.host_counts[5] = (uint32_t)(need >> 32);
+    }
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
@@ -238,6 +250,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
                                         C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
                                         C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
                                         C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
+                                        if (log_on) {
+                                            const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // bbox_x bbox_y b slot
+                                            const Foot f = clip_foot(tail.x, tail.y, tile_x0, tile_y0, lim_x, lim_y);
+                                            GHit h;
+                                            h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
+                                            hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
+                                        }
                                         T = test_T;
                                         last = (uint32_t)(b * GSTAR_BATCH + sl[u] + 1);
                                     }
@@ -278,6 +297,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
         const size_t pid = (size_t)g.py * p.W + g.px;
         p.final_T[pid] = T;
         p.n_contrib[pid] = last;
+        p.pixstate[pid] = make_float4(C0, C1, C2, T);
         p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), T, C0);  // forward.cu:372
         p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), T, C1);
         p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), T, C2);
@@ -297,7 +317,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
     __shared__ __align__(128) unsigned char s_rec[NSTAGE * GSTAR_BATCH * RS];
     __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
     __shared__ int s_kmax;
-    if (p.hdr->overflow) return;
+    if (p.hdr->overflow || p.hdr->log_overflow == 0u) return;  // with a hit log, k_blend_bwd_gather does the work
+    const uint32_t* const point_list = reinterpret_cast<const uint32_t*>(p.packed + p.hdr->off_point_list);
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     if (re == rs) return;
@@ -317,7 +338,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
     bg_dot += __ldg(p.bg + 0) * dpx0;
     bg_dot += __ldg(p.bg + 1) * dpx1;
     bg_dot += __ldg(p.bg + 2) * dpx2;
-    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;  // backward.cu:460-461
 
     if (tid == 0) {
         s_kmax = 0;
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
                         const int rsel = lane >> 4;
                         const bool any_mine = rsel ? (anyB != 0) : (anyA != 0);
                         if (any_mine) {
-                            const uint32_t gid = *reinterpret_cast<const uint32_t*>(buf - slot[rsel] * RS + 44);
+                            const uint32_t gid = point_list[rs + (uint32_t)(kbase - slot[rsel])];
                             float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
                             if ((lane & 1) == 0) atomicAdd(dst + (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)), t);
                             else if ((lane & 15) == 1) atomicAdd(dst + 8, o);  // gacc row = the nine raw moments
@@ -459,8 +479,105 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
     }
 }
 
+
+// ---- K7 (hit-log path): instance-parallel backward ------------------------------------------------------------------
+// The reference walks every pixel's list back to front because dL/dalpha of a pair needs the transmittance in front of
+// it and the colour behind it (backward.cu:472-556).  The forward blend already had both when it blended the pair and
+// left them in the hit log: T_i and C_i = sum_{j<=i} c_j alpha_j T_j.  With C_fin = sum_j c_j alpha_j T_j,
+//   dC/dalpha_i = T_i c_i - (C_fin - C_i + T_final bg) / (1 - alpha_i)
+// which is backward.cu:505-534 in closed form, so no pixel-serial recurrence is left: one thread per INSTANCE walks the
+// few pixels of its footprint in this tile, keeps the nine raw moments [S, S dx, S dy, S dx^2, S dx dy, S dy^2, w dpx_rgb]
+// (S = o G dL/dalpha, w = alpha T_i; see k_blend_bwd) in registers and issues three reductions per instance -- no
+// cross-lane reduction and no per-pixel atomics at all.  A pair was blended iff it lies in front of the pixel's last
+// contributor and passes the reference's power / alpha tests, which are re-evaluated here with the forward's arithmetic.
+constexpr int GATHER_THREADS = 256;
+__global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams p)
+{
+    __shared__ float4 s_pix[GSTAR_TILE * GSTAR_TILE];    // dL_dpix rgb, (C_fin . dpx + T_final bg . dpx)
+    __shared__ uint32_t s_nc[GSTAR_TILE * GSTAR_TILE];  // n_contrib
+    __shared__ uint32_t s_total;
+    if (p.hdr->overflow || p.hdr->log_overflow) return;
+    const int tile = (int)p.tile_order[blockIdx.x];
+    const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
+    if (re == rs) return;
+    const int tid = threadIdx.x;
+    const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
+    const int lim_x = min(GSTAR_TILE - 1, p.W - 1 - tile_x0), lim_y = min(GSTAR_TILE - 1, p.H - 1 - tile_y0);
+    {
+        const int px = tile_x0 + (tid & 15), py = tile_y0 + (tid >> 4);
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t nc = 0;
+        if (px < p.W && py < p.H) {
+            const size_t HW = (size_t)p.H * p.W, pid = (size_t)py * p.W + px;
+            nc = p.n_contrib[pid];
+            if (nc) {
+                const float d0 = p.dL_dpix[pid], d1 = p.dL_dpix[HW + pid], d2 = p.dL_dpix[2 * HW + pid];
+                const float4 st = p.pixstate[pid];
+                const float bg_dot = __ldg(p.bg + 0) * d0 + __ldg(p.bg + 1) * d1 + __ldg(p.bg + 2) * d2;
+                pv = make_float4(d0, d1, d2, st.x * d0 + st.y * d1 + st.z * d2 + st.w * bg_dot);
+            }
+        }
+        s_pix[tid] = pv;
+        s_nc[tid] = nc;
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        const uint32_t wmax = __reduce_max_sync(FULL, nc);
+        if ((tid & 31) == 0 && wmax) atomicMax(&s_total, wmax);
+        __syncthreads();
+    }
+    const uint32_t total = s_total;  // instances behind every pixel's last contributor were never blended
+    const GHit* const hitlog = reinterpret_cast<const GHit*>(p.packed + p.hdr->off_log);
+    const uint32_t* const point_list = reinterpret_cast<const uint32_t*>(p.packed + p.hdr->off_point_list);
+    const float4* const tile_packed = reinterpret_cast<const float4*>(p.packed + (size_t)rs * RS);
+    const float tx0f = (float)tile_x0, ty0f = (float)tile_y0;
+#pragma unroll 1
+    for (uint32_t i = tid; i < total; i += GATHER_THREADS) {
+        const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // bbox_x bbox_y b slot
+        const Foot f = clip_foot(__float_as_uint(q2.x), __float_as_uint(q2.y), tile_x0, tile_y0, lim_x, lim_y);
+        if (f.w <= 0 || f.h <= 0) continue;
+        const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
+        const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
+        const GHit* hrow = hitlog + __float_as_uint(q2.w);
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f;
+        bool any = false;
+        const int area = f.w * f.h;
+        int xx = 0, pl = f.y0 * GSTAR_TILE + f.x0;
+#pragma unroll 1
+        for (int s = 0; s < area; s++) {
+            const int cur_pl = pl, cur_s = s;
+            if (++xx == f.w) { xx = 0; pl += GSTAR_TILE - f.w + 1; } else pl++;
+            if (i >= s_nc[cur_pl]) continue;  // behind this pixel's last contributor
+            float dx, dy;
+            const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, tx0f + (float)(cur_pl & 15), ty0f + (float)(cur_pl >> 4), dx, dy);
+            if (power > 0.0f) continue;
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
+            if (alpha < 1.0f / 255.0f) continue;
+            const GHit h = hrow[cur_s];
+            const float4 pv = s_pix[cur_pl];
+            const float w = alpha * h.T;
+            const float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
+            const float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
+            const float dL_dalpha = h.T * cdot - behind * __frcp_rn(1.0f - alpha);
+            const float sG = (q1.y * dL_dalpha) * G;
+            const float sx = sG * dx, sy = sG * dy;
+            m0 += sG; m1 += sx; m2 += sy;
+            m3 = fmaf(sx, dx, m3); m4 = fmaf(sx, dy, m4); m5 = fmaf(sy, dy, m5);
+            m6 = fmaf(w, pv.x, m6); m7 = fmaf(w, pv.y, m7); m8 = fmaf(w, pv.z, m8);
+            any = true;
+        }
+        if (any) {
+            float* dst = p.gacc + (size_t)point_list[rs + i] * GSTAR_GACC;
+            red_add_v4(dst, m0, m1, m2, m3);
+            red_add_v4(dst + 4, m4, m5, m6, m7);
+            atomicAdd(dst + 8, m8);
+        }
+    }
+}
+
 int blend_setup() { return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM); }
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, BLEND_THREADS, FWD_DYN_SMEM, s>>>(p); }
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
+void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s) { k_blend_bwd_gather<<<p.gx * p.gy, GATHER_THREADS, 0, s>>>(p); }
 
 }  // namespace gstar

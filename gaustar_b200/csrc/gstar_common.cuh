@@ -7,6 +7,8 @@
 //   point_list[R] per-tile depth-sorted gaussian indices == the reference's sorted value list
 //                 (DGR/cuda_rasterizer/rasterizer_impl.cu:303-308).
 //   ranges[T]     [start,end) of every tile in point_list (rasterizer_impl.cu:116-138).
+//   packed[R]     48-byte records in blend order (GRec[0:44] + the instance's first hit-log slot).
+//   hitlog[A]     16-byte GHit per (instance, footprint pixel), written by blend_fwd for every blended pair.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,7 +43,19 @@ struct GHeader {
     uint32_t n_big;          // tiles whose list does not fit the small sort kernel
     uint32_t big_cursor;     // work counter of the big-tile sort kernel
     uint32_t max_tile;       // longest tile list
-    uint32_t pad[2];
+    uint32_t log_overflow;   // 1: the hit log is disabled or too small for this view -> blend_bwd walks the lists instead
+    uint32_t pad0;
+    unsigned long long log_cursor;      // hit-log slots handed out by tile_sort (= sum of clipped footprint areas)
+    unsigned long long log_capacity;    // hit-log slots the binning buffer holds
+    unsigned long long off_point_list;  // byte offsets inside the binning buffer
+    unsigned long long off_log;
+};
+static_assert(sizeof(GHeader) == 64, "GHeader layout");
+
+// One hit-log slot per (instance, pixel of its clipped footprint): what the forward blend knew when it blended the
+// pair -- transmittance in front of it and the colour accumulated up to and including it (blend.cu).
+struct __align__(16) GHit {
+    float T, c0, c1, c2;
 };
 
 namespace gstar {
@@ -101,6 +115,28 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// Footprint of a record inside one tile: its alpha-bounds (GRec::bbox_x/y) clipped to the tile and the image, in
+// tile-local pixel coordinates.  w <= 0 or h <= 0: empty.  tile_sort hands every instance w*h consecutive hit-log
+// slots; slot of local pixel (lx, ly) = base + (ly - y0) * w + (lx - x0).  lim_x = min(15, W-1-tile_x0), same for y.
+struct Foot {
+    int x0, y0, w, h;
+};
+__device__ __forceinline__ Foot clip_foot(uint32_t bbx, uint32_t bby, int tile_x0, int tile_y0, int lim_x, int lim_y)
+{
+    Foot f;
+    f.x0 = max((int)(short)(bbx & 0xffffu) - tile_x0, 0);
+    f.y0 = max((int)(short)(bby & 0xffffu) - tile_y0, 0);
+    f.w = min((int)(short)(bbx >> 16) - tile_x0, lim_x) - f.x0 + 1;
+    f.h = min((int)(short)(bby >> 16) - tile_y0, lim_y) - f.y0 + 1;
+    return f;
+}
+
+// 128-bit vector reduction to global memory (SASS: REDG.E.ADD.F32x4): four fp32 adds in one instruction
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p)

@@ -56,7 +56,7 @@ struct PreBwdParams {
 };
 
 struct BinParams {
-    int P, gx, gy, num_tiles;
+    int P, gx, gy, num_tiles, W, H;
     const GRec* recs;
     GHeader* hdr;          // device header (image buffer)
     uint32_t* tile_count;  // [T] histogram from preprocess
@@ -68,7 +68,10 @@ struct BinParams {
     uint32_t* point_list;  // [capacity] sorted gaussian ids
     unsigned char* packed; // [capacity][48] tile-contiguous packed records (GRec[0:44] + gaussian id), sorted order
     uint32_t capacity;
-    volatile uint32_t* host_counts;  // mapped pinned host memory: [0]=R, [1]=overflow
+    unsigned long long log_capacity;    // hit-log slots available behind `entries` (0: log disabled)
+    unsigned long long off_point_list;  // byte offsets inside the binning buffer, recorded in the header
+    unsigned long long off_log;
+    volatile uint32_t* host_counts;  // mapped pinned host memory: [0]=R, [1]=overflow, [2]=max tile, [4..5]=hit-log slots needed
 };
 
 struct BlendParams {
@@ -76,8 +79,10 @@ struct BlendParams {
     const GRec* recs;
     const GHeader* hdr;
     const uint32_t* ranges;
-    const unsigned char* packed;  // [R][48] tile-contiguous packed records in blend order
+    const unsigned char* packed;  // [R][48] tile-contiguous packed records in blend order (= start of the binning buffer)
     const uint32_t* tile_order;
+    float4* pixstate;             // [H*W] (C_r, C_g, C_b, T) per pixel as the forward left it (colour without background)
+    volatile uint32_t* host_counts;
     const float* bg;
     // forward
     float* out_color;
@@ -102,6 +107,7 @@ int  preprocess_setup();
 int  blend_setup();
 
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s);
-void launch_blend_bwd(const BlendParams& p, cudaStream_t s);
+void launch_blend_bwd(const BlendParams& p, cudaStream_t s);         // walk-back path (no hit log)
+void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s);  // instance-parallel path over the hit log
 
 }  // namespace gstar

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GSTAR_ABI_VERSION 2
+#define GSTAR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GSTAR_API __attribute__((visibility("default")))
@@ -154,6 +154,18 @@ GSTAR_API int gstar_image_views(char* image_buffer, int width, int height, float
 /* View of the sorted instance list (BinningState::point_list, rasterizer_impl.h:58-68).  Synchronous (reads the
  * provisioned capacity from the image buffer's header); meant for tests. */
 GSTAR_API int gstar_binning_views(char* binning_buffer, char* image_buffer, uint32_t** point_list, uint64_t* capacity);
+
+/* ---- hit log (backward strategy) ----
+ * The forward blend can record, for every blended (instance, pixel) pair, the transmittance in front of it and the
+ * colour accumulated so far ("hit log", 16 bytes per pixel of every instance's footprint, carved out of the binning
+ * buffer).  The backward blend then needs no per-pixel back-to-front walk (backward.cu:472-556 in closed form) and
+ * runs instance-parallel.  The log is sized from the previous call on this thread/device; a view whose log does not
+ * fit -- or any view when the log is switched off -- takes the walk-back kernel instead (decided on the device, same
+ * results within fp32 rounding).  Environment: GSTAR_HIT_LOG=0 disables it, GSTAR_HIT_LOG_MAX_MB caps its size
+ * (default 8192).  gstar_set_hit_log(0|1) overrides the environment (returns the previous mode; other values only
+ * query).  gstar_hit_log_state() is a synchronous test helper reading one forward call's header. */
+GSTAR_API int gstar_set_hit_log(int mode);
+GSTAR_API int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, uint64_t* slots_capacity, int* in_use);
 
 /* ---- measurement hook: record `start`/`stop` (cudaEvent_t) around kernel stage `stage` of every
  * subsequent call on this thread (stage < 0 disables).  Stages: see gstar_stage_name(). ---- */

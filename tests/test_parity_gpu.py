@@ -28,10 +28,27 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.int32)
 
 
+@pytest.fixture(params=["hitlog", "walk"], autouse=True)
+def backward_path(request):
+    """Every test runs twice: with the forward's hit log + instance-parallel backward (the default), and with the
+    log switched off (walk-back backward, also the automatic fallback when a view's log does not fit)."""
+    old = capi.set_hit_log(1 if request.param == "hitlog" else 0)
+    yield request.param
+    capi.set_hit_log(old)
+
+
 def run_mine(d, debug=False):
     kw = Hh.to_torch_kwargs(d)
     fwd = capi.forward(debug=debug, **kw)
     torch.cuda.synchronize()
+    if capi.set_hit_log(-1) == 1:
+        if not capi.hit_log_state(fwd)[2]:  # first view of a new scene: the log was sized for another one; the hint is in now
+            fwd = capi.forward(debug=debug, **kw)
+            torch.cuda.synchronize()
+        need, cap, used = capi.hit_log_state(fwd)
+        assert used and 0 < need <= cap, (need, cap, used)
+    else:
+        assert not capi.hit_log_state(fwd)[2]
     return kw, fwd
 
 
