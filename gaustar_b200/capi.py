@@ -22,7 +22,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 EXPORTED = [
     "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
     "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
-    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state",
+    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state", "gstar_debug_header",
 ]
 STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
@@ -81,6 +81,7 @@ def lib():
         L.gstar_binning_views.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.gstar_profile_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.gstar_set_hit_log.argtypes = [C.c_int]
+        L.gstar_debug_header.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.gstar_hit_log_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -241,3 +242,12 @@ def hit_log_state(fwd):
     need, cap, used = C.c_uint64(), C.c_uint64(), C.c_int()
     _check(lib().gstar_hit_log_state(_ptr(fwd["image"]), C.byref(need), C.byref(cap), C.byref(used)))
     return int(need.value), int(cap.value), bool(used.value)
+
+
+def debug_header(fwd):
+    """The forward call's device header as a dict (private layout; diagnostics only)."""
+    w = (C.c_uint32 * 24)()
+    _check(lib().gstar_debug_header(_ptr(fwd["image"]), w))
+    w = list(w)
+    return dict(num_rendered=w[0], capacity=w[1], overflow=w[2], max_tile=w[3], log_overflow=w[4], sort_fallback_tiles=w[5], sort_max_fine=w[6],
+                log_cursor=w[8] | (w[9] << 32), log_capacity=w[10] | (w[11] << 32), cls_end=w[16:20], cls_cursor=w[20:24])

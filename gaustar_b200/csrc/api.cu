@@ -476,6 +476,14 @@ int gstar_binning_views(char* binning_buffer, char* image_buffer, uint32_t** poi
     return 0;
 }
 
+int gstar_debug_header(char* image_buffer, uint32_t* words24)
+{
+    if (!image_buffer || !words24) return fail(GSTAR_ERR_INVALID, "null argument");
+    cudaError_t e = cudaMemcpy(words24, aligned128(image_buffer), sizeof(GHeader), cudaMemcpyDeviceToHost);  // test helper: synchronous
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+
 int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, uint64_t* slots_capacity, int* in_use)
 {
     if (!image_buffer) return fail(GSTAR_ERR_INVALID, "null image buffer");

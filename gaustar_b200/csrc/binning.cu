@@ -21,6 +21,9 @@ constexpr int SCAN_THREADS = 1024;
 constexpr uint32_t SORT_CAP = 8192;                // keys (64 KB, a power of two) one CTA sorts in shared memory
 constexpr int SORT_THREADS = 512;
 constexpr int LPT_BUCKETS = 132;                   // quarter-octave size classes for the longest-first tile order
+constexpr uint32_t SMALL_CAP = 2048, MED_CAP = 8192;  // list-length classes of the sort kernels (powers of two = LPT bucket edges)
+constexpr int LPT_SMALL_END = 1 + 11 * 4;          // first LPT bucket with >= 2048 instances
+constexpr int LPT_MED_END = 1 + 13 * 4;            // first LPT bucket with >= 8192 instances
 
 __device__ __forceinline__ int lpt_bucket(uint32_t c)
 {
@@ -47,13 +50,13 @@ __device__ __forceinline__ uint32_t warp_aggregated_add(uint32_t* counters, uint
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
 {
     __shared__ uint32_t s_part[SCAN_THREADS];
-    __shared__ uint32_t s_nbig, s_max;
+    __shared__ uint32_t s_max, s_cls[3];
     __shared__ uint32_t s_hist[LPT_BUCKETS];
     const int tid = threadIdx.x;
     const int T = p.num_tiles;
     const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
     const int t0 = tid * per, t1 = min(T, t0 + per);
-    if (tid == 0) { s_nbig = 0; s_max = 0; }
+    if (tid == 0) s_max = 0;
     for (int b = tid; b < LPT_BUCKETS; b += SCAN_THREADS) s_hist[b] = 0;
     __syncthreads();
     uint32_t sum = 0, mx = 0, n_empty = 0;
@@ -83,7 +86,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         // identifyTileRanges leaves untouched tiles at the memset value (0,0): rasterizer_impl.cu:310
         p.ranges[2 * t] = c ? run : 0u;
         p.ranges[2 * t + 1] = c ? run + c : 0u;
-        if (c > SORT_CAP) p.big_tiles[atomicAdd(&s_nbig, 1u)] = (uint32_t)t;  // statistics only
         run += c;
     }
     __syncthreads();
@@ -92,6 +94,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
     if (tid == 0) {
         uint32_t acc = 0;
         for (int b = LPT_BUCKETS - 1; b >= 0; b--) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }
+        // s_hist[b] = tiles in buckets > b = first position of bucket b: the class boundaries of the sort kernels
+        s_cls[0] = s_hist[LPT_MED_END - 1]; s_cls[1] = s_hist[LPT_SMALL_END - 1]; s_cls[2] = s_hist[0];
     }
     __syncthreads();
     {
@@ -108,9 +112,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         p.hdr->num_rendered = total;
         p.hdr->capacity = p.capacity;
         p.hdr->overflow = ovf;
-        p.hdr->n_big = s_nbig;
-        p.hdr->big_cursor = 0;
         p.hdr->max_tile = s_max;
+        p.hdr->pad0[0] = 0u; p.hdr->pad0[1] = 0u; p.hdr->pad0[2] = 0u;
+        for (int c = 0; c < 3; c++) { p.hdr->cls_end[c] = s_cls[c]; p.hdr->cls_cursor[c] = 0u; }
+        p.hdr->cls_end[3] = s_cls[2]; p.hdr->cls_cursor[3] = 0u;
         p.hdr->log_overflow = p.log_capacity ? 0u : 1u;
         p.hdr->log_cursor = 0ull;
         p.hdr->log_capacity = p.log_capacity;
@@ -334,16 +339,34 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
     }
 }
 
+// Next tile of list-length class `cls` (persistent CTAs; tiles were ordered longest first by tile_scan).
+__device__ __forceinline__ bool next_tile(const BinParams& p, int cls, uint32_t* s_item, uint32_t& tile, uint32_t& start, uint32_t& n)
+{
+    __syncthreads();  // everyone is done with the previous tile (shared memory, *s_item)
+    if (threadIdx.x == 0) {
+        const uint32_t lo = cls ? p.hdr->cls_end[cls - 1] : 0u;
+        *s_item = lo + atomicAdd(&p.hdr->cls_cursor[cls], 1u);
+    }
+    __syncthreads();
+    const uint32_t item = *s_item;
+    if (item >= p.hdr->cls_end[cls]) return false;
+    tile = p.tile_order[item];
+    start = p.ranges[2 * tile];
+    n = p.ranges[2 * tile + 1] - start;
+    return true;
+}
+
+// Class 0 (lists of >= 8192 instances; rare): bitonic network, chunk-wise in shared memory with the chunk-crossing stages
+// on the L2-resident keys.  Also the network the bucket kernels fall back to.
 __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ uint32_t s_item;
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);
     if (p.hdr->overflow) return;
-    const uint32_t tile = p.tile_order[blockIdx.x];
-    const uint32_t start = p.ranges[2 * tile], end = p.ranges[2 * tile + 1];
-    const uint32_t n = end - start;
-    if (n == 0) return;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    uint32_t tile, start, n;
+    while (next_tile(p, 0, &s_item, tile, start, n)) {
     uint64_t* g = reinterpret_cast<uint64_t*>(p.entries) + start;
     constexpr uint32_t CH = SORT_CAP;
     if (n <= CH) {
@@ -351,7 +374,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
         __syncthreads();
         bitonic_sort(s_keys, n, tid, nt);
         write_sorted(p, tile, start, s_keys, n, tid, nt);
-        return;
+        continue;
     }
     uint32_t npad = CH;
     while (npad < n) npad <<= 1;
@@ -390,18 +413,188 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
         }
     }
     write_sorted(p, tile, start, g, n, tid, nt);
+    }
 }
+
+// Exclusive scan of one value per thread over the CTA (NT threads, a multiple of 32).  s_w: NT/32 + 1 words.
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_w)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += u;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < NT / 32 ? s_w[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += u;
+        }
+        if (lane < NT / 32) s_w[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t r = s_w[warp] + incl - v;
+    __syncthreads();  // s_w may be reused right away
+    return r;
+}
+
+// Classes 1 and 2 (lists shorter than CAP): two-level adaptive bucket sort, O(n) and ~a dozen barriers instead of the
+// ~45 shared-memory passes of the network.  Keys stay in registers (CAP/NT per thread).
+//   1. 256 uniform coarse bins over the tile's depth range [dmin, dmax] -> histogram.
+//   2. every coarse bin is split into as many fine buckets as it holds keys (so clusters -- the front and the back
+//      layer of a surface -- get resolution where the keys are): n fine buckets, ~1 key each; counting sort into them.
+//   3. each fine bucket is finished by an insertion sort on the full (depth, index) key by one thread.
+// Both bin functions are monotone in the depth bits, equal depths share a bucket, and step 3 orders on the whole
+// 64-bit key, so the result is the reference's (tile, depth, index) order exactly.  A pathological fine bucket
+// (> MAX_FINE keys, e.g. thousands of identical depths) sends the tile through the bitonic network instead.
+template <uint32_t CAP, int NT>
+__global__ void __launch_bounds__(NT) k_tile_sort_bucket(BinParams p, int cls)
+{
+    constexpr int KPT = CAP / NT;
+    constexpr uint32_t MAX_FINE = 48;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_out = reinterpret_cast<uint64_t*>(s_raw);              // [CAP]
+    uint32_t* s_fine = reinterpret_cast<uint32_t*>(s_raw + CAP * 8);   // [CAP + KPT] fine-bucket counts, then offsets
+    __shared__ uint32_t s_coarse[256], s_cbase[256], s_w[NT / 32 + 1];
+    __shared__ uint32_t s_item, s_dmin, s_dmax, s_flag;
+    if (p.hdr->overflow) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    uint32_t tile, start, n;
+    while (next_tile(p, cls, &s_item, tile, start, n)) {
+        const uint64_t* g = reinterpret_cast<const uint64_t*>(p.entries) + start;
+        uint64_t k[KPT];
+        uint32_t dmin = 0xffffffffu, dmax = 0u;
+#pragma unroll
+        for (int e = 0; e < KPT; e++) {
+            const uint32_t i = tid + e * NT;
+            k[e] = i < n ? g[i] : ~0ull;
+            if (i < n) { dmin = min(dmin, (uint32_t)(k[e] >> 32)); dmax = max(dmax, (uint32_t)(k[e] >> 32)); }
+        }
+        if (tid == 0) { s_dmin = 0xffffffffu; s_dmax = 0u; s_flag = 0u; }
+        if (tid < 256) s_coarse[tid] = 0u;
+#pragma unroll
+        for (int e = 0; e <= KPT; e++) {
+            const uint32_t i = tid + e * NT;
+            if (i < CAP + KPT) s_fine[i] = 0u;
+        }
+        __syncthreads();
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0) { atomicMin(&s_dmin, dmin); atomicMax(&s_dmax, dmax); }
+        __syncthreads();
+        dmin = s_dmin; dmax = s_dmax;
+        const float scale = 256.0f / ((float)(dmax - dmin) + 1.0f);
+        uint32_t cb[KPT];
+#pragma unroll
+        for (int e = 0; e < KPT; e++) {
+            const uint32_t i = tid + e * NT;
+            const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
+            cb[e] = min(255u, (uint32_t)x);
+            // neighbouring keys of a surface fall into few coarse bins: one shared-memory atomic per distinct bin per warp
+            const unsigned peers = __match_any_sync(0xffffffffu, i < n ? cb[e] : 0xffffffffu);
+            if (i < n && (int)lane == __ffs(peers) - 1) atomicAdd(&s_coarse[cb[e]], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        {
+            const uint32_t c = tid < 256 ? s_coarse[tid] : 0u;
+            const uint32_t ex = block_excl_scan<NT>(c, s_w);
+            if (tid < 256) s_cbase[tid] = ex;
+        }
+        __syncthreads();
+        uint32_t fb[KPT], rk[KPT];
+#pragma unroll
+        for (int e = 0; e < KPT; e++) {
+            const uint32_t i = tid + e * NT;
+            fb[e] = 0u; rk[e] = 0u;
+            if (i < n) {
+                const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
+                const uint32_t cnt = s_coarse[cb[e]];
+                const float frac = fminf(fmaxf(x - (float)cb[e], 0.0f), 1.0f);
+                fb[e] = s_cbase[cb[e]] + min(cnt - 1u, (uint32_t)(frac * (float)cnt));
+                rk[e] = atomicAdd(&s_fine[fb[e]], 1u);
+            }
+        }
+        __syncthreads();
+        {   // counts -> exclusive offsets, KPT consecutive fine buckets per thread (the n fine buckets fit: n < CAP)
+            uint32_t c[KPT], sum = 0u;
+#pragma unroll
+            for (int e = 0; e < KPT; e++) { c[e] = s_fine[tid * KPT + e]; sum += c[e]; }
+            uint32_t run = block_excl_scan<NT>(sum, s_w);
+#pragma unroll
+            for (int e = 0; e < KPT; e++) { s_fine[tid * KPT + e] = run; run += c[e]; }
+            if (tid == NT - 1) s_fine[CAP] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < KPT; e++)
+            if (tid + e * NT < n) s_out[s_fine[fb[e]] + rk[e]] = k[e];
+        __syncthreads();
+        for (uint32_t b = tid; b < n; b += NT) {
+            const uint32_t o = s_fine[b], c = s_fine[b + 1] - o;
+            if (c < 2u) continue;
+            if (c > MAX_FINE) { s_flag = 1u; atomicMax(&p.hdr->pad0[1], c); continue; }
+            for (uint32_t a = 1; a < c; a++) {
+                const uint64_t v = s_out[o + a];
+                uint32_t j = a;
+                while (j > 0 && s_out[o + j - 1] > v) { s_out[o + j] = s_out[o + j - 1]; j--; }
+                s_out[o + j] = v;
+            }
+        }
+        __syncthreads();
+        if (s_flag) {
+            if (tid == 0) atomicAdd(&p.hdr->pad0[0], 1u);  // statistics: tiles that took the network
+#pragma unroll
+            for (int e = 0; e < KPT; e++)
+                if (tid + e * NT < n) s_out[tid + e * NT] = k[e];
+            __syncthreads();
+            bitonic_sort(s_out, n, tid, NT);
+        }
+        write_sorted(p, tile, start, s_out, n, tid, NT);
+    }
+}
+
+constexpr int SMALL_THREADS = 256, MED_THREADS = 1024;
+constexpr int SMALL_SMEM = SMALL_CAP * 8 + (SMALL_CAP + SMALL_CAP / SMALL_THREADS + 1) * 4;
+constexpr int MED_SMEM = MED_CAP * 8 + (MED_CAP + MED_CAP / MED_THREADS + 1) * 4;
+static int g_num_sms = 0, g_small_per_sm = 4, g_med_per_sm = 1;
 
 int tile_sort_setup()
 {
-    return (int)cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_CAP * sizeof(uint64_t)));
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_CAP * sizeof(uint64_t)));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_tile_sort_bucket<MED_CAP, MED_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MED_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_tile_sort_bucket<SMALL_CAP, SMALL_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_small_per_sm, k_tile_sort_bucket<SMALL_CAP, SMALL_THREADS>, SMALL_THREADS, SMALL_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_med_per_sm, k_tile_sort_bucket<MED_CAP, MED_THREADS>, MED_THREADS, MED_SMEM);
+    g_small_per_sm = g_small_per_sm > 0 ? g_small_per_sm : 1;
+    g_med_per_sm = g_med_per_sm > 0 ? g_med_per_sm : 1;
+    return (int)e;
 }
 
 void launch_tile_scan(const BinParams& p, cudaStream_t s) { k_tile_scan<<<1, SCAN_THREADS, 0, s>>>(p); }
 void launch_emit(const BinParams& p, cudaStream_t s) { k_emit<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
 void launch_tile_sort(const BinParams& p, cudaStream_t s)
 {
-    k_tile_sort<<<p.num_tiles, SORT_THREADS, SORT_CAP * sizeof(uint64_t), s>>>(p);
+    // persistent CTAs, one grid per list-length class, sized to the machine (148 SMs on B200), longest class first
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    k_tile_sort<<<min(p.num_tiles, sms), SORT_THREADS, SORT_CAP * sizeof(uint64_t), s>>>(p);
+    k_tile_sort_bucket<MED_CAP, MED_THREADS><<<min(p.num_tiles, g_med_per_sm * sms), MED_THREADS, MED_SMEM, s>>>(p, 1);
+    k_tile_sort_bucket<SMALL_CAP, SMALL_THREADS><<<min(p.num_tiles, g_small_per_sm * sms), SMALL_THREADS, SMALL_SMEM, s>>>(p, 2);
 }
 
 }  // namespace gstar

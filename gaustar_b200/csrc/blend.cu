@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
                     counted = true;
                 }
                 const int s = b % NSTAGE;
-                mbar_wait(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
+                // a finished warp only keeps the ring's arrival counts whole: it must not burn issue slots spinning
+                if (warp_done) mbar_wait_sleep(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
+                else mbar_wait(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
                 if (s_stop) break;
                 if (!warp_done) {
                     const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS;
@@ -538,9 +540,14 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
         const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
         const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
         const GHit* hrow = hitlog + __float_as_uint(q2.w);
+        const int area = f.w * f.h;
+        // The footprint's log slots are contiguous: pull all of its lines towards L2 now, for every lane at once, so
+        // that the dependent loads in the pixel loop below find them there (the loop itself exposes one miss at a time).
+        for (int off = 0; off < area * (int)sizeof(GHit); off += 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
+        prefetch_l2(hrow + (area - 1));  // the row need not start on a line boundary
+        if (i + GATHER_THREADS < total) prefetch_l2(tile_packed + (size_t)(i + GATHER_THREADS) * 3);
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f;
         bool any = false;
-        const int area = f.w * f.h;
         int xx = 0, pl = f.y0 * GSTAR_TILE + f.x0;
 #pragma unroll 1
         for (int s = 0; s < area; s++) {

@@ -40,17 +40,20 @@ struct GHeader {
     uint32_t num_rendered;   // R = sum of tiles_touched
     uint32_t capacity;       // instances the binning buffer can hold
     uint32_t overflow;       // 1 if R > capacity (binning/blend skipped, host retries)
-    uint32_t n_big;          // tiles whose list does not fit the small sort kernel
-    uint32_t big_cursor;     // work counter of the big-tile sort kernel
     uint32_t max_tile;       // longest tile list
     uint32_t log_overflow;   // 1: the hit log is disabled or too small for this view -> blend_bwd walks the lists instead
-    uint32_t pad0;
+    uint32_t pad0[3];
     unsigned long long log_cursor;      // hit-log slots handed out by tile_sort (= sum of clipped footprint areas)
     unsigned long long log_capacity;    // hit-log slots the binning buffer holds
     unsigned long long off_point_list;  // byte offsets inside the binning buffer
     unsigned long long off_log;
+    // tile_order lists the tiles longest first; class c = positions [cls_end[c-1], cls_end[c]) of it:
+    // 0: >= 8192 instances, 1: 2048..8191, 2: 1..2047 (cls_end[2] = number of non-empty tiles).  The sort kernels are
+    // persistent and pull tiles of their class through cls_cursor.
+    uint32_t cls_end[4];
+    uint32_t cls_cursor[4];
 };
-static_assert(sizeof(GHeader) == 64, "GHeader layout");
+static_assert(sizeof(GHeader) == 96, "GHeader layout");
 
 // One hit-log slot per (instance, pixel of its clipped footprint): what the forward blend knew when it blended the
 // pair -- transmittance in front of it and the colour accumulated up to and including it (blend.cu).
@@ -105,7 +108,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity)
 {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(256);
+        __nanosleep(512);
         if (spins > (1u << 22)) __trap();
     }
 }
@@ -138,6 +141,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p)
 {

@@ -524,23 +524,32 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
     const float* vm = s_vm;
     const float* proj = s_pm;
     const int radius = valid ? (p.radii ? p.radii[idx] : p.recs[idx].radius) : 0;
+    // blend_bwd accumulated the raw moments [S, Sx, Sy, Sxx, Sxy, Syy, cr, cg, cb] of every Gaussian (see blend.cu).
+    // A Gaussian no pixel blended (culled, hidden behind the saturated front layer, ...) still has the all-zero row the
+    // caller's memset left: all of its gradients are exactly zero, so nothing below needs its parameters or SH row --
+    // in accumulate mode it is not touched at all.  On a closed surface that is about half of the Gaussians.
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    float m8 = 0.f;
+    if (valid && radius > 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(p.gacc + i * GSTAR_GACC);
+        a0 = a4[0]; a1 = a4[1];
+        m8 = p.gacc[i * GSTAR_GACC + 8];
+    }
+    const bool vis = radius > 0 && (a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f || a1.x != 0.f || a1.y != 0.f || a1.z != 0.f ||
+                                    a1.w != 0.f || m8 != 0.f);
     // SH rows of the warp staged in shared memory: coalesced loads now, coalesced dL_dsh stores at the end
     const bool sh_staged = p.shs && p.dL_dsh && M > 0 && M <= SH_MAX_M;
     ShStage st;
     st.rows = nullptr; st.stride = 0; st.vec = false;
     if (sh_staged) {
         st = sh_stage_make(s_sh, p.shs, M);
-        const unsigned need = __ballot_sync(0xffffffffu, valid && radius > 0 && p.D > 0);
+        const unsigned need = __ballot_sync(0xffffffffu, valid && vis && p.D > 0);
         if (need) sh_stage_load(st, p.shs, M, (long long)idx - lane, p.P, need);
     }
     if (valid) {
-    // blend_bwd accumulated the raw moments [S, Sx, Sy, Sxx, Sxy, Syy, cr, cg, cb] of every Gaussian (see blend.cu);
-    // turn them into the reference's blend-stage gradients (backward.cu:523-554) with the per-Gaussian factors.
+    // turn the moments into the reference's blend-stage gradients (backward.cu:523-554) with the per-Gaussian factors
     float acc[9];
     {
-        const float4* a4 = reinterpret_cast<const float4*>(p.gacc + i * GSTAR_GACC);
-        const float4 a0 = a4[0], a1 = a4[1];
-        const float m8 = p.gacc[i * GSTAR_GACC + 8];
         const GRec* rc = p.recs + i;
         const float4 r0 = *reinterpret_cast<const float4*>(rc);       // x y A B
         const float2 r1 = *(reinterpret_cast<const float2*>(rc) + 2);  // C o
@@ -552,15 +561,14 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
         acc[3] = -0.5f * Sxy;                         // dL_dconic.y
         acc[4] = -0.5f * Syy;                         // dL_dconic.w
         acc[5] = a1.z; acc[6] = a1.w; acc[7] = m8;    // dL_dcolor
-        acc[8] = (radius > 0 && o != 0.f) ? S / o : 0.f;  // dL_dopacity = sum G*dL_dalpha = S / o
+        acc[8] = (vis && o != 0.f) ? S / o : 0.f;  // dL_dopacity = sum G*dL_dalpha = S / o
     }
     // blend-stage gradients in the reference's layouts (also outputs of the op / parity intermediates)
     p.dL_dmean2D[3 * i] = acc[0]; p.dL_dmean2D[3 * i + 1] = acc[1]; p.dL_dmean2D[3 * i + 2] = 0.f;
     if (p.dL_dconic) { p.dL_dconic[4 * i] = acc[2]; p.dL_dconic[4 * i + 1] = acc[3]; p.dL_dconic[4 * i + 2] = 0.f; p.dL_dconic[4 * i + 3] = acc[4]; }
     p.dL_dcolor[3 * i] = acc[5]; p.dL_dcolor[3 * i + 1] = acc[6]; p.dL_dcolor[3 * i + 2] = acc[7];
-    if (p.accumulate) { if (radius > 0) p.dL_dopacity[i] += acc[8]; } else p.dL_dopacity[i] = acc[8];
+    if (p.accumulate) { if (vis) p.dL_dopacity[i] += acc[8]; } else p.dL_dopacity[i] = acc[8];
     float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool vis = radius > 0;
     if (vis) {
         const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
         float c6[6];
@@ -682,7 +690,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
     for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
     }  // valid
     if (sh_staged) {
-        const unsigned rows = p.accumulate ? __ballot_sync(0xffffffffu, valid && radius > 0) : 0xffffffffu;
+        const unsigned rows = p.accumulate ? __ballot_sync(0xffffffffu, valid && vis) : 0xffffffffu;
         sh_stage_store(st, p.dL_dsh, M, (long long)idx - lane, p.P, rows, p.accumulate != 0);
     }
 }

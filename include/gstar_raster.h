@@ -165,6 +165,8 @@ GSTAR_API int gstar_binning_views(char* binning_buffer, char* image_buffer, uint
  * (default 8192).  gstar_set_hit_log(0|1) overrides the environment (returns the previous mode; other values only
  * query).  gstar_hit_log_state() is a synchronous test helper reading one forward call's header. */
 GSTAR_API int gstar_set_hit_log(int mode);
+/* Raw copy of one forward call's device header (24 32-bit words; private layout, gstar_common.cuh) -- diagnostics. */
+GSTAR_API int gstar_debug_header(char* image_buffer, uint32_t* words24);
 GSTAR_API int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, uint64_t* slots_capacity, int* in_use);
 
 /* ---- measurement hook: record `start`/`stop` (cudaEvent_t) around kernel stage `stage` of every
