@@ -249,7 +249,7 @@ def run_gpu(args, impl_name, rank, world, local):
     # every kernel of the library is launched on the caller's current stream).  Each stream accumulates into its own flat
     # gradient buffer; the two are summed once per step before the single allreduce.  The reference launches on the
     # legacy default stream and blocks on a D2H copy inside every forward, so it runs its views one after the other.
-    n_streams = 2 if impl.fused_accumulate else 1
+    n_streams = max(1, args.streams) if impl.fused_accumulate else 1
     side = [torch.cuda.Stream(device) for _ in range(n_streams)] if n_streams > 1 else []
     flats = [flat] + [gdist.FlatGrads(P, M, device) for _ in range(n_streams - 1)]
     fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in side]
@@ -337,7 +337,9 @@ def run_gpu(args, impl_name, rank, world, local):
     torch.cuda.synchronize()
     copy_stream = torch.cuda.Stream(device)
     slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), tgt_f=torch.empty(3, H, W, device=device), vm=torch.empty(4, 4, device=device),
-                  pm=torch.empty(4, 4, device=device), cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+                  pm=torch.empty(4, 4, device=device), cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event())
+             for _ in range(n_streams + 1)]
+    NSLOT = len(slots)
     h2d_per_view = H * W * 3 + (16 + 16 + 3) * 4
 
     def prefetch(slot, v, i):
@@ -369,9 +371,9 @@ def run_gpu(args, impl_name, rank, world, local):
                 st.wait_event(fork)
         ns = len(e2e_streams)
         for i, v in enumerate(views):
-            s = slots[i & 1]
+            s = slots[i % NSLOT]
             if i + 1 < len(views):
-                prefetch((i + 1) & 1, views[i + 1], i + 1)
+                prefetch((i + 1) % NSLOT, views[i + 1], i + 1)
             st, ls = e2e_streams[i % ns], leaf_sets[i % ns]
             with torch.cuda.stream(st):
                 st.wait_event(s["ev"])
@@ -441,13 +443,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (CUDA streams) in our arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = gdist.init_from_env()
     have_gpu = torch.cuda.is_available()
     config = {"workload": f"surface-1M-1080p-sh3 ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
               "gaussians": None, "resolution": [W, H], "sh_degree": SH_DEG, "views_per_step": VIEWS_PER_GPU * world,
-              "parallelism": f"view-sharded dp{world} + 1 allreduce/step; ours: 2 views in flight on 2 CUDA streams per GPU", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
+              "parallelism": f"view-sharded dp{world} + 1 allreduce/step; ours: {args.streams} views in flight on {args.streams} CUDA streams per GPU", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
 
     if args.impl == "reference":
         use_gpu_ref = have_gpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C.so"))

@@ -287,6 +287,7 @@ __device__ __forceinline__ uint32_t foot_area(uint32_t bbx, uint32_t bby, int tx
 // pixel of its alpha-bounds inside this tile (clip_foot).  Slots of a tile are contiguous (exclusive scan over the
 // CTA, any order), tiles take their block from a global cursor.  The cursor keeps counting when the log is too small
 // (or disabled) so that the host learns the size this view needs.
+template <int U>
 __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, uint32_t start, const uint64_t* keys, uint32_t n, uint32_t tid,
                                              uint32_t nt)
 {
@@ -296,11 +297,20 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
     float4* out = reinterpret_cast<float4*>(p.packed + (size_t)start * GSTAR_REC_SMEM);
     const int tx0 = (int)(tile % (uint32_t)p.gx) * GSTAR_TILE, ty0 = (int)(tile / (uint32_t)p.gx) * GSTAR_TILE;
     const int limx = min(GSTAR_TILE - 1, p.W - 1 - tx0), limy = min(GSTAR_TILE - 1, p.H - 1 - ty0);
+    // every gather below is issued for U instances at once: the loop is latency-bound (one L2 round trip per step)
+    const unsigned char* recb = reinterpret_cast<const unsigned char*>(p.recs);
     uint32_t mine = 0;
-    for (uint32_t i = tid; i < n; i += nt) {
-        const uint32_t id = (uint32_t)keys[i];
-        const uint2 bb = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(p.recs) + (size_t)id * GSTAR_REC_BYTES + 32);
-        mine += foot_area(bb.x, bb.y, tx0, ty0, limx, limy);
+    for (uint32_t i0 = tid; i0 < n; i0 += U * nt) {
+        uint2 bb[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * nt;
+            bb[u] = make_uint2(1u, 0u);  // empty box
+            if (i < n) bb[u] = *reinterpret_cast<const uint2*>(recb + (size_t)(uint32_t)keys[i] * GSTAR_REC_BYTES + 32);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (i0 + u * nt < n) mine += foot_area(bb[u].x, bb[u].y, tx0, ty0, limx, limy);
     }
     const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     uint32_t incl = mine;
@@ -328,14 +338,28 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
     }
     __syncthreads();
     uint32_t slot = (uint32_t)s_base + s_warp[warp] + (incl - mine);
-    for (uint32_t i = tid; i < n; i += nt) {
-        const uint32_t id = (uint32_t)keys[i];
-        p.point_list[start + i] = id;
-        const float4 a = recs[(size_t)id * 4], b = recs[(size_t)id * 4 + 1];
-        float4 c = recs[(size_t)id * 4 + 2];
-        c.w = __uint_as_float(slot);
-        slot += foot_area(__float_as_uint(c.x), __float_as_uint(c.y), tx0, ty0, limx, limy);
-        out[(size_t)i * 3] = a; out[(size_t)i * 3 + 1] = b; out[(size_t)i * 3 + 2] = c;
+    for (uint32_t i0 = tid; i0 < n; i0 += U * nt) {
+        uint32_t id[U];
+        float4 a[U], b[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * nt;
+            id[u] = i < n ? (uint32_t)keys[i] : 0u;
+            if (i < n) {
+                a[u] = recs[(size_t)id[u] * 4]; b[u] = recs[(size_t)id[u] * 4 + 1]; c[u] = recs[(size_t)id[u] * 4 + 2];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + u * nt;
+            if (i < n) {
+                p.point_list[start + i] = id[u];
+                const uint32_t area = foot_area(__float_as_uint(c[u].x), __float_as_uint(c[u].y), tx0, ty0, limx, limy);
+                c[u].w = __uint_as_float(slot);
+                slot += area;
+                out[(size_t)i * 3] = a[u]; out[(size_t)i * 3 + 1] = b[u]; out[(size_t)i * 3 + 2] = c[u];
+            }
+        }
     }
 }
 
@@ -373,7 +397,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
         for (uint32_t i = tid; i < n; i += nt) s_keys[i] = g[i];
         __syncthreads();
         bitonic_sort(s_keys, n, tid, nt);
-        write_sorted(p, tile, start, s_keys, n, tid, nt);
+        write_sorted<2>(p, tile, start, s_keys, n, tid, nt);
         continue;
     }
     uint32_t npad = CH;
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
             __syncthreads();
         }
     }
-    write_sorted(p, tile, start, g, n, tid, nt);
+    write_sorted<2>(p, tile, start, g, n, tid, nt);
     }
 }
 
@@ -455,7 +479,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_w)
 // 64-bit key, so the result is the reference's (tile, depth, index) order exactly.  A pathological fine bucket
 // (> MAX_FINE keys, e.g. thousands of identical depths) sends the tile through the bitonic network instead.
 template <uint32_t CAP, int NT>
-__global__ void __launch_bounds__(NT) k_tile_sort_bucket(BinParams p, int cls)
+__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 3)) k_tile_sort_bucket(BinParams p, int cls)
 {
     constexpr int KPT = CAP / NT;
     constexpr uint32_t MAX_FINE = 48;
@@ -491,15 +515,14 @@ __global__ void __launch_bounds__(NT) k_tile_sort_bucket(BinParams p, int cls)
         __syncthreads();
         dmin = s_dmin; dmax = s_dmax;
         const float scale = 256.0f / ((float)(dmax - dmin) + 1.0f);
-        uint32_t cb[KPT];
 #pragma unroll
         for (int e = 0; e < KPT; e++) {
             const uint32_t i = tid + e * NT;
             const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
-            cb[e] = min(255u, (uint32_t)x);
+            const uint32_t cb = min(255u, (uint32_t)x);
             // neighbouring keys of a surface fall into few coarse bins: one shared-memory atomic per distinct bin per warp
-            const unsigned peers = __match_any_sync(0xffffffffu, i < n ? cb[e] : 0xffffffffu);
-            if (i < n && (int)lane == __ffs(peers) - 1) atomicAdd(&s_coarse[cb[e]], (uint32_t)__popc(peers));
+            const unsigned peers = __match_any_sync(0xffffffffu, i < n ? cb : 0xffffffffu);
+            if (i < n && (int)lane == __ffs(peers) - 1) atomicAdd(&s_coarse[cb], (uint32_t)__popc(peers));
         }
         __syncthreads();
         {
@@ -508,17 +531,18 @@ __global__ void __launch_bounds__(NT) k_tile_sort_bucket(BinParams p, int cls)
             if (tid < 256) s_cbase[tid] = ex;
         }
         __syncthreads();
-        uint32_t fb[KPT], rk[KPT];
+        uint32_t fr[KPT];  // fine bucket | rank inside it << 16 (both < CAP <= 2^13)
 #pragma unroll
         for (int e = 0; e < KPT; e++) {
             const uint32_t i = tid + e * NT;
-            fb[e] = 0u; rk[e] = 0u;
+            fr[e] = 0u;
             if (i < n) {
                 const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
-                const uint32_t cnt = s_coarse[cb[e]];
-                const float frac = fminf(fmaxf(x - (float)cb[e], 0.0f), 1.0f);
-                fb[e] = s_cbase[cb[e]] + min(cnt - 1u, (uint32_t)(frac * (float)cnt));
-                rk[e] = atomicAdd(&s_fine[fb[e]], 1u);
+                const uint32_t cb = min(255u, (uint32_t)x);
+                const uint32_t cnt = s_coarse[cb];
+                const float frac = fminf(fmaxf(x - (float)cb, 0.0f), 1.0f);
+                const uint32_t fb = s_cbase[cb] + min(cnt - 1u, (uint32_t)(frac * (float)cnt));
+                fr[e] = fb | (atomicAdd(&s_fine[fb], 1u) << 16);
             }
         }
         __syncthreads();
@@ -534,7 +558,7 @@ __global__ void __launch_bounds__(NT) k_tile_sort_bucket(BinParams p, int cls)
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < KPT; e++)
-            if (tid + e * NT < n) s_out[s_fine[fb[e]] + rk[e]] = k[e];
+            if (tid + e * NT < n) s_out[s_fine[fr[e] & 0xffffu] + (fr[e] >> 16)] = k[e];
         __syncthreads();
         for (uint32_t b = tid; b < n; b += NT) {
             const uint32_t o = s_fine[b], c = s_fine[b + 1] - o;
@@ -556,7 +580,7 @@ __global__ void __launch_bounds__(NT) k_tile_sort_bucket(BinParams p, int cls)
             __syncthreads();
             bitonic_sort(s_out, n, tid, NT);
         }
-        write_sorted(p, tile, start, s_out, n, tid, NT);
+        write_sorted<(NT >= 1024 ? 2 : 4)>(p, tile, start, s_out, n, tid, NT);
     }
 }
 
