@@ -97,17 +97,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp is parked by the hardware for up to `ns` instead of re-issuing the poll
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 24)) __trap();
+    if (mbar_try_wait(bar, parity)) return;  // the common case: the stage is already there
+    for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 4000u); ++spins)
+        if (spins > (1u << 22)) __trap();
 }
 // Waiting side of a long-latency hand-off (the producer waiting for its consumers): back off with nanosleep so
 // that the spinning warp does not steal issue slots from the warps doing the work.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity)
 {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spins) {
         __nanosleep(512);
         if (spins > (1u << 22)) __trap();
     }

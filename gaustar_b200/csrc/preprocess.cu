@@ -231,28 +231,61 @@ __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restr
     }
 }
 
+// Floats [4*q0, 4*q1) of a coefficient row into v (static indices after unrolling: registers).  VEC: the row is a
+// 16-byte aligned shared-memory row of the staging area (stride 3M+4 floats): one conflict-free LDS.128 per four floats,
+// where scalar reads of the same element of 32 rows would be 4-way bank conflicted (rows are float4-aligned).
+template <bool VEC>
+__device__ __forceinline__ void sh_row_load(const float* c, int q0, int q1, float* v)
+{
+#pragma unroll
+    for (int q = q0; q < q1; q++) {
+        if (VEC) {
+            const float4 t = reinterpret_cast<const float4*>(c)[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[4 * q + i] = c[4 * q + i];
+        }
+    }
+}
+
 // forward.cu:20-71.  `c` = this Gaussian's coefficients [M][3] (shared-memory row or global memory).
+template <bool VEC>
 __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* c, float3 pos, float3 campos, uint32_t& clamp_bits)
 {
     float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
     const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
     dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
-#define SHK(k) make_float3(c[3 * (k)], c[3 * (k) + 1], c[3 * (k) + 2])
+    float v[48];
+#define SHK(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
 #define ACC(w, k) { const float w_ = (w); const float3 s_ = SHK(k); res.x += w_ * s_.x; res.y += w_ * s_.y; res.z += w_ * s_.z; }
-    float3 res = {c_SH_C0 * c[0], c_SH_C0 * c[1], c_SH_C0 * c[2]};
+    if (VEC || deg > 0) sh_row_load<VEC>(c, 0, 1, v);
+    else { v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; }  // a degree-0 row in global memory may be only three floats long
+    float3 res = {c_SH_C0 * v[0], c_SH_C0 * v[1], c_SH_C0 * v[2]};
     if (deg > 0) {
         const float x = dir.x, y = dir.y, z = dir.z;
+        sh_row_load<VEC>(c, 1, 3, v);  // coefficients 1-3 = floats 3..11
         ACC(-c_SH_C1 * y, 1);
         ACC(c_SH_C1 * z, 2);
         ACC(-c_SH_C1 * x, 3);
         if (deg > 1) {
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            if (VEC) sh_row_load<VEC>(c, 3, 7, v);  // coefficients 4-8 = floats 12..26 (+ one of coefficient 9)
+            else {
+#pragma unroll
+                for (int i = 12; i < 27; i++) v[i] = c[i];
+            }
             ACC(c_SH_C2[0] * xy, 4);
             ACC(c_SH_C2[1] * yz, 5);
             ACC(c_SH_C2[2] * (2.0f * zz - xx - yy), 6);
             ACC(c_SH_C2[3] * xz, 7);
             ACC(c_SH_C2[4] * (xx - yy), 8);
             if (deg > 2) {
+                if (VEC) sh_row_load<VEC>(c, 7, 12, v);  // coefficients 9-15 = floats 27..47
+                else {
+#pragma unroll
+                    for (int i = 27; i < 48; i++) v[i] = c[i];
+                }
                 ACC(c_SH_C3[0] * y * (3.0f * xx - yy), 9);
                 ACC(c_SH_C3[1] * xy * z, 10);
                 ACC(c_SH_C3[2] * y * (4.0f * zz - xx - yy), 11);
@@ -370,14 +403,18 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_fwd(PreFwdParams p)
             if (need) {
                 const ShStage st = sh_stage_make(s_sh, p.shs, p.M);
                 sh_stage_load(st, p.shs, p.M, (long long)idx - lane, p.P, need);
-                if (visible) col = sh_to_rgb(p.D, st.rows + lane * st.stride, make_float3(px, py, pz), campos, clamp_bits);
+                if (visible) {
+                    const float* row = st.rows + lane * st.stride;
+                    col = st.vec ? sh_to_rgb<true>(p.D, row, make_float3(px, py, pz), campos, clamp_bits)
+                                 : sh_to_rgb<false>(p.D, row, make_float3(px, py, pz), campos, clamp_bits);
+                }
             }
         } else if (visible) {
             float c[48];
             const float* sh = p.shs + (size_t)3 * p.M * idx;
             for (int i = 0; i < 48; i++)
                 if (i < nfl) c[i] = __ldg(sh + i);
-            col = sh_to_rgb(p.D, c, make_float3(px, py, pz), campos, clamp_bits);
+            col = sh_to_rgb<false>(p.D, c, make_float3(px, py, pz), campos, clamp_bits);
         }
         if (visible) { rec.r = col.x; rec.g = col.y; rec.b = col.z; rec.flags = clamp_bits; }
     }
@@ -442,6 +479,7 @@ __global__ void k_geom_unpack(const GRec* __restrict__ recs, int P, float* depth
 // ------------------------------------------------------------------------------------------------
 // `sh` and `dL_dsh` may alias (the staged shared-memory row is overwritten in place: every coefficient is
 // read before the first gradient is written)
+template <bool VEC>
 __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, float3 pos, float3 campos, uint32_t clamp_bits,
                                             float3 dL_dcolor, float3& dmean_add, float* dL_dsh, bool acc_out)
 {
@@ -454,10 +492,14 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
     if (clamp_bits & 4) g.z = 0;
     float3 dx = {0, 0, 0}, dy = {0, 0, 0}, dz = {0, 0, 0};
     float w[16];
-#define SHK(k) make_float3(sh[3 * (k)], sh[3 * (k) + 1], sh[3 * (k) + 2])
+    float v[48];  // the coefficient row (VEC: read with conflict-free LDS.128, see sh_row_load)
+#define SHK(k) make_float3(v[3 * (k)], v[3 * (k) + 1], v[3 * (k) + 2])
 #define AXPY(d, a, v) { const float a_ = (a); d.x += a_ * v.x; d.y += a_ * v.y; d.z += a_ * v.z; }
+#pragma unroll
+    for (int k = 1; k < 16; k++) w[k] = 0.f;
     w[0] = c_SH_C0;
     if (deg > 0) {
+        sh_row_load<VEC>(sh, 0, 3, v);
         w[1] = -c_SH_C1 * y; w[2] = c_SH_C1 * z; w[3] = -c_SH_C1 * x;
         const float3 s1 = SHK(1), s2 = SHK(2), s3 = SHK(3);
         AXPY(dx, -c_SH_C1, s3);
@@ -467,6 +509,11 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             w[4] = c_SH_C2[0] * xy; w[5] = c_SH_C2[1] * yz; w[6] = c_SH_C2[2] * (2.f * zz - xx - yy);
             w[7] = c_SH_C2[3] * xz; w[8] = c_SH_C2[4] * (xx - yy);
+            if (VEC) sh_row_load<VEC>(sh, 3, 7, v);
+            else {
+#pragma unroll
+                for (int i = 12; i < 27; i++) v[i] = sh[i];
+            }
             const float3 s4 = SHK(4), s5 = SHK(5), s6 = SHK(6), s7 = SHK(7), s8 = SHK(8);
             AXPY(dx, c_SH_C2[0] * y, s4); AXPY(dx, c_SH_C2[2] * 2.f * -x, s6); AXPY(dx, c_SH_C2[3] * z, s7); AXPY(dx, c_SH_C2[4] * 2.f * x, s8);
             AXPY(dy, c_SH_C2[0] * x, s4); AXPY(dy, c_SH_C2[1] * z, s5); AXPY(dy, c_SH_C2[2] * 2.f * -y, s6); AXPY(dy, c_SH_C2[4] * 2.f * -y, s8);
@@ -475,6 +522,11 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
                 w[9] = c_SH_C3[0] * y * (3.f * xx - yy); w[10] = c_SH_C3[1] * xy * z; w[11] = c_SH_C3[2] * y * (4.f * zz - xx - yy);
                 w[12] = c_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); w[13] = c_SH_C3[4] * x * (4.f * zz - xx - yy);
                 w[14] = c_SH_C3[5] * z * (xx - yy); w[15] = c_SH_C3[6] * x * (xx - 3.f * yy);
+                if (VEC) sh_row_load<VEC>(sh, 7, 12, v);
+                else {
+#pragma unroll
+                    for (int i = 27; i < 48; i++) v[i] = sh[i];
+                }
                 const float3 s9 = SHK(9), s10 = SHK(10), s11 = SHK(11), s12 = SHK(12), s13 = SHK(13), s14 = SHK(14), s15 = SHK(15);
                 AXPY(dx, c_SH_C3[0] * 3.f * 2.f * xy, s9); AXPY(dx, c_SH_C3[1] * yz, s10); AXPY(dx, c_SH_C3[2] * -2.f * xy, s11);
                 AXPY(dx, c_SH_C3[3] * -3.f * 2.f * xz, s12); AXPY(dx, c_SH_C3[4] * (-3.f * xx + 4.f * zz - yy), s13);
@@ -489,13 +541,31 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
     }
 #undef AXPY
 #undef SHK
-    const int ncoef = (deg + 1) * (deg + 1);
-    for (int k = 0; k < M; k++) {
-        const float wk = k < ncoef ? w[k] : 0.f;  // coefficients above the active degree get zero gradient
-        if (acc_out) {  // direct-to-global path in accumulate mode
-            dL_dsh[3 * k] += wk * g.x; dL_dsh[3 * k + 1] += wk * g.y; dL_dsh[3 * k + 2] += wk * g.z;
-        } else {
-            dL_dsh[3 * k] = wk * g.x; dL_dsh[3 * k + 1] = wk * g.y; dL_dsh[3 * k + 2] = wk * g.z;
+    // dL_dsh[k] = basis_k * dL_dRGB; coefficients above the active degree get zero gradient (w[k] == 0 there)
+    if (VEC) {  // staged row, M in {4, 8, 12, 16}: float4 stores (the row was read completely above)
+        const float gc[3] = {g.x, g.y, g.z};
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            if (4 * q < 3 * M) {
+                float4 t;
+                t.x = w[(4 * q) / 3] * gc[(4 * q) % 3];
+                t.y = w[(4 * q + 1) / 3] * gc[(4 * q + 1) % 3];
+                t.z = w[(4 * q + 2) / 3] * gc[(4 * q + 2) % 3];
+                t.w = w[(4 * q + 3) / 3] * gc[(4 * q + 3) % 3];
+                reinterpret_cast<float4*>(dL_dsh)[q] = t;
+            }
+        }
+    } else {
+        const int ncoef = (deg + 1) * (deg + 1);
+        for (int k = 0; k < M; k++) {
+            float wk = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) wk = (j == k && j < ncoef) ? w[j] : wk;
+            if (acc_out) {  // direct-to-global path in accumulate mode
+                dL_dsh[3 * k] += wk * g.x; dL_dsh[3 * k + 1] += wk * g.y; dL_dsh[3 * k + 2] += wk * g.z;
+            } else {
+                dL_dsh[3 * k] = wk * g.x; dL_dsh[3 * k + 1] = wk * g.y; dL_dsh[3 * k + 2] = wk * g.z;
+            }
         }
     }
     const float ddx = dx.x * g.x + dx.y * g.y + dx.z * g.z;
@@ -509,7 +579,7 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
     dmean_add.z = (-dorig.x * dorig.z * ddx - dorig.y * dorig.z * ddy + (sum2 - dorig.z * dorig.z) * ddz) * inv;
 }
 
-__global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
+__global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
 {
     extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_vm[16], s_pm[16];
@@ -634,8 +704,12 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(PreBwdParams p)
             float3 add;
             const float* sh_in = sh_staged ? st.rows + lane * st.stride : p.shs + (size_t)3 * M * i;
             float* sh_out = sh_staged ? st.rows + lane * st.stride : p.dL_dsh + (size_t)3 * M * i;
-            sh_backward(p.D, M, sh_in, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]), p.recs[idx].flags,
-                        make_float3(acc[5], acc[6], acc[7]), add, sh_out, !sh_staged && p.accumulate != 0);
+            if (sh_staged && st.vec)
+                sh_backward<true>(p.D, M, sh_in, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]), p.recs[idx].flags,
+                                  make_float3(acc[5], acc[6], acc[7]), add, sh_out, false);
+            else
+                sh_backward<false>(p.D, M, sh_in, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]), p.recs[idx].flags,
+                                   make_float3(acc[5], acc[6], acc[7]), add, sh_out, !sh_staged && p.accumulate != 0);
             dmean[0] += add.x; dmean[1] += add.y; dmean[2] += add.z;
         }
         if (p.scales) {
