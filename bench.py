@@ -49,6 +49,9 @@ UNIT = "views/s"
 P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
 VIEWS_PER_GPU = 20  # BASELINE.json config #3: 160 views / 8 GPUs per step
 CAM_POOL = 32
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+# (profiles/r1i_ncu_full_summary.txt); None where no capture is committed
+NCU_TRAFFIC = {"blend_fwd": 383398400, "blend_bwd": 561370112, "preprocess_bwd": 574310144, "preprocess_fwd": 257299200}
 
 
 def measured_peak():
@@ -132,7 +135,7 @@ def build_workload(device, rank, world):
 class OursCABI:
     """Device-resident arm: straight through the C ABI."""
     name = "gaustar_b200 (C ABI)"
-    launches_per_view = 8  # preprocess_fwd, tile_scan, emit, tile_sort, tile_sort_big, blend_fwd, blend_bwd, preprocess_bwd
+    launches_per_view = 10  # preprocess_fwd, tile_scan, emit, tile_sort x3 (length classes), blend_fwd, blend_bwd_gather, blend_bwd (no-op), preprocess_bwd
 
     def __init__(self):
         from gaustar_b200 import capi
@@ -257,8 +260,9 @@ def run_gpu(args, impl_name, rank, world, local):
     def one_view(step, i, v, timed, fl):
         nonlocal R_sum, V_count
         if prof is not None and timed:
-            a, b = prof[(step - args.warmup) * VIEWS_PER_GPU + i]
-            capi.profile_stage(capi.STAGES.index("blend_bwd"), a, b)
+            n = (step - args.warmup) * VIEWS_PER_GPU + i
+            a, b = prof[n]
+            capi.profile_stage(n % len(capi.STAGES), a, b)  # every view times one stage, round robin over the seven
         if impl.fused_accumulate:
             R, _, grads = impl.fwd_bwd(params, cam_dev[v], bg, l1_grad_fn(target_f[i & 1]), fl)
         else:
@@ -310,14 +314,30 @@ def run_gpu(args, impl_name, rank, world, local):
 
     roofline = None
     if prof is not None:
-        t_bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in prof]))
         R_avg = R_sum / max(V_count, 1)
-        alg_bytes = 40.0 * R_avg + 20.0 * W * H + 36.0 * P  # B7, V ~= P for this scene
+        T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        npix = W * H
+        # algorithmic bytes per launch (SURVEY 8d / BASELINE.md 2.4; V ~= P for this scene: nothing is frustum-culled)
+        alg = {"preprocess_fwd": P * (44 + 12 * M) + 8 * P + P * (52 + 12), "tile_scan": 8 * T_tiles, "emit": 20 * P + 12 * R_avg,
+               "tile_sort": 24 * R_avg + 8 * R_avg + 8 * T_tiles, "blend_fwd": 40 * R_avg + 20 * npix + 8 * T_tiles,
+               "blend_bwd": 40 * R_avg + 20 * npix + 36 * P, "preprocess_bwd": P * (108 + 12 * M) + P * (40 + 12 * M)}
+        kernel_of = {"preprocess_fwd": "k_preprocess_fwd", "tile_scan": "k_tile_scan", "emit": "k_emit", "tile_sort": "k_tile_sort_bucket (x2) + k_tile_sort",
+                     "blend_fwd": "k_blend_fwd", "blend_bwd": "k_blend_bwd_gather", "preprocess_bwd": "k_preprocess_bwd"}
         peak, how = measured_peak()
-        ach = alg_bytes / (t_bwd_ms * 1e-3) / 1e9
-        roofline = {"kernel": "k_blend_bwd", "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                    "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(t_bwd_ms, 4),
-                    "avg_num_rendered": int(R_avg)}
+        per = {}
+        for si, name in enumerate(capi.STAGES):
+            ts = [a.elapsed_time(b) for n, (a, b) in enumerate(prof) if n % len(capi.STAGES) == si]
+            if ts:
+                ms = float(np.mean(ts))
+                per[name] = {"ms": round(ms, 4), "algorithmic_bytes": int(alg[name]), "gbs": round(alg[name] / (ms * 1e-3) / 1e9, 1),
+                             "frac": round(alg[name] / (ms * 1e-3) / 1e9 / peak, 4), "samples": len(ts)}
+        dom = max(per, key=lambda k: per[k]["ms"])
+        roofline = {"kernel": kernel_of[dom], "stage": dom, "bound": "hbm", "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": per[dom]["frac"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": how, "algorithmic_bytes_per_launch": per[dom]["algorithmic_bytes"],
+                    "avg_launch_ms": per[dom]["ms"], "avg_num_rendered": int(R_avg),
+                    "note": "dominant (longest) kernel of the step, timed live with CUDA events on its launching stream while the other "
+                            "stream's view runs concurrently; blend kernels are SIMT-issue-bound by construction (DESIGN.md section 4)",
+                    "stages": per}
 
     # ---------------- public-API arm (e2e): host buffers, copies inside the timed region ----------------
     Settings, Rasterizer = make_autograd_rasterizer(impl_name)
