@@ -138,16 +138,32 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
     __syncwarp();
 }
 
-constexpr int FWD_DYN_SMEM = NSTAGE * GSTAR_BATCH * RS + NCONS * QCAP * 32;  // record ring + per-pixel hit queues
+// ---- K6: forward blend ---------------------------------------------------------------------------------------------
+// One CTA per tile, eight warps, one per 8x4 pixel block, and NO coupling between them: every warp streams the tile's
+// packed records through its OWN shared-memory ring (FWD_NST stages of FWD_SB records; lane 0 issues one TMA bulk copy per
+// stage, completion on the stage's mbarrier), so a warp whose pixels are finished simply leaves, a warp with few hits
+// runs ahead, and nobody polls a barrier for somebody else's progress.  (The first version shared one ring per CTA
+// behind a producer warp: ~15 % of its issued instructions were mbarrier polls of warps waiting for the tile's slowest
+// warp.)  The records come out of L2; fetching them once per warp costs L2->shared bandwidth, not HBM.
+// Per batch: every lane turns ONE record's alpha-bounds into a 32-bit mask of the block's pixels, a 32x32 bit transpose
+// hands every pixel the records that can touch it (one register word per 32 records = the pixel's hit queue), and the
+// set bits are walked four at a time in list order with the reference's arithmetic.
+constexpr int FWD_SB = 64;    // records per stage (two rounds of 32)
+constexpr int FWD_NST = 2;    // stages per warp
+constexpr int FWD_THREADS = NCONS * 32;
+constexpr int FWD_DYN_SMEM = NCONS * FWD_NST * FWD_SB * RS;  // 48 KB
 
-__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
+__device__ __forceinline__ void fwd_fetch(unsigned char* stage, uint64_t* bar, const unsigned char* tile_packed, int b, int n)
+{
+    const uint32_t bytes = (uint32_t)min(FWD_SB, n - b * FWD_SB) * RS;
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(stage, tile_packed + (size_t)b * FWD_SB * RS, bytes, bar);
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 4) k_blend_fwd(BlendParams p)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    unsigned char* s_rec = s_dyn;                                                   // [NSTAGE][GSTAR_BATCH * RS]
-    unsigned char (*s_q)[QCAP][32] = reinterpret_cast<unsigned char (*)[QCAP][32]>(s_dyn + NSTAGE * GSTAR_BATCH * RS);  // [warp][pos][lane]
-    __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
-    __shared__ int s_done_warps;
-    __shared__ volatile int s_stop;
+    __shared__ __align__(8) uint64_t s_full[NCONS][FWD_NST];
     if (p.hdr->overflow) return;
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
@@ -172,129 +188,93 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_fwd(BlendParams p)
     uint32_t last = 0;
     bool done = !g.inside;
 
-    if (n > 0) {
-        if (tid == 0) {
-            for (int s = 0; s < NSTAGE; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NCONS); }
-            s_done_warps = 0;
-            s_stop = 0;
+    if (n > 0 && __any_sync(FULL, !done)) {
+        unsigned char* const ring = s_dyn + (size_t)warp * FWD_NST * FWD_SB * RS;
+        uint64_t* const full = s_full[warp];
+        const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
+        const int nb = (n + FWD_SB - 1) / FWD_SB;
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < FWD_NST; s++) mbar_init(&full[s], 1);
             fence_mbar_init();
+#pragma unroll
+            for (int s = 0; s < FWD_NST; s++)
+                if (s < nb) fwd_fetch(ring + s * FWD_SB * RS, &full[s], tile_packed, s, n);
         }
-        __syncthreads();
-        const int nb = (n + GSTAR_BATCH - 1) / GSTAR_BATCH;
-        Ring ring{s_rec, s_full, s_empty};
-        if (warp == NCONS) {
-            // ===== producer warp =====
-            const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
+        __syncwarp();
+        int b = 0;
 #pragma unroll 1
-            for (int b = 0; b < nb; b++) {
-                if (*(volatile int*)&s_done_warps == NCONS) {
-                    // every pixel of the tile is finished: stop streaming and release anyone waiting for batch b
-                    s_stop = 1;
-                    __threadfence_block();
-                    if (lane == 0) mbar_arrive_expect_tx(&s_full[b % NSTAGE], 0);
-                    break;
-                }
-                produce_batch(ring, b, b * GSTAR_BATCH, min(GSTAR_BATCH, n - b * GSTAR_BATCH), tile_packed, lane);
+        for (; b < nb; b++) {
+            const int s = b % FWD_NST;
+            const unsigned char* buf = ring + s * FWD_SB * RS;
+            mbar_wait(&full[s], (uint32_t)(b / FWD_NST) & 1u);
+            const unsigned live = __ballot_sync(FULL, !done);
+            if (live == 0) break;  // every pixel of the block is finished: this warp is done with the tile
+            const int cnt = min(FWD_SB, n - b * FWD_SB);
+            unsigned w0 = 0u, w1 = 0u;  // bit k of w0 / w1: record k / 32 + k of the batch may touch my pixel
+            {
+                const unsigned pm = (lane < cnt) ? (block_pixel_mask(buf + lane * RS, g) & live) : 0u;
+                if (__any_sync(FULL, pm != 0u)) w0 = transpose32(pm, lane);
             }
-        } else {
-            // ===== consumer warps =====
-            bool warp_done = __all_sync(FULL, done);
-            bool counted = false;
+            if (cnt > 32) {
+                const unsigned pm = (32 + lane < cnt) ? (block_pixel_mask(buf + (32 + lane) * RS, g) & live) : 0u;
+                if (__any_sync(FULL, pm != 0u)) w1 = transpose32(pm, lane);
+            }
 #pragma unroll 1
-            for (int b = 0; b < nb; b++) {
-                if (warp_done && !counted) {
-                    if (lane == 0) atomicAdd(&s_done_warps, 1);
-                    counted = true;
+            while (__any_sync(FULL, (w0 | w1) != 0u)) {
+                int sl[4];
+                bool ok[4];
+                float al[4], cr[4], cg[4], cbv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    bool have = true;
+                    if (w0) { sl[u] = __ffs(w0) - 1; w0 &= w0 - 1u; }
+                    else if (w1) { sl[u] = 32 + __ffs(w1) - 1; w1 &= w1 - 1u; }
+                    else { sl[u] = 0; have = false; }
+                    const unsigned char* rp = buf + sl[u] * RS;
+                    const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
+                    const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
+                    cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
+                    cr[u] = q1.z; cg[u] = q1.w;
+                    float dx, dy;
+                    const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
+                    al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
+                    ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
                 }
-                const int s = b % NSTAGE;
-                // a finished warp only keeps the ring's arrival counts whole: it must not burn issue slots spinning
-                if (warp_done) mbar_wait_sleep(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
-                else mbar_wait(&s_full[s], (uint32_t)(b / NSTAGE) & 1u);
-                if (s_stop) break;
-                if (!warp_done) {
-                    const unsigned char* buf = s_rec + (size_t)s * GSTAR_BATCH * RS;
-                    const int cnt = min(GSTAR_BATCH, n - b * GSTAR_BATCH);
-                    // Per-pixel hit queues.  Per round of 32 records every lane turns ITS record's alpha-bounds into a
-                    // 32-bit mask of the block's pixels; a 32x32 bit-matrix transpose hands every pixel the mask of the
-                    // records that can touch it, and the set bits are appended (in list order) to that pixel's queue.
-                    // The queues are then drained with every lane working on its own next hit: no lane evaluates a
-                    // record whose bounds exclude its pixel.  Order per pixel == list order, arithmetic unchanged.
-                    int qn = 0;
-                    unsigned char* qrow = &s_q[warp][0][lane];
-                    auto drain = [&]() {
-                        const int maxn = __reduce_max_sync(FULL, qn);
-#pragma unroll 1
-                        for (int i0 = 0; i0 < maxn; i0 += 4) {
-                            int sl[4];
-                            bool ok[4];
-                            float al[4], cr[4], cg[4], cbv[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const bool have = i0 + u < qn;
-                                sl[u] = have ? (int)qrow[(i0 + u) * 32] : 0;
-                                const unsigned char* rp = buf + sl[u] * RS;
-                                const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
-                                const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
-                                cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
-                                cr[u] = q1.z; cg[u] = q1.w;
-                                float dx, dy;
-                                const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
-                                al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
-                                ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+                for (int u = 0; u < 4; u++) {
+                    if (ok[u] && !done) {
+                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
+                            C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
+                            C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
+                            if (log_on) {
+                                const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // bbox_x bbox_y b slot
+                                const Foot f = clip_foot(tail.x, tail.y, tile_x0, tile_y0, lim_x, lim_y);
+                                GHit h;
+                                h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
+                                hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
                             }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                if (ok[u] && !done) {
-                                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
-                                    if (test_T < 0.0001f) {
-                                        done = true;
-                                    } else {
-                                        C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
-                                        C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
-                                        C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
-                                        if (log_on) {
-                                            const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // bbox_x bbox_y b slot
-                                            const Foot f = clip_foot(tail.x, tail.y, tile_x0, tile_y0, lim_x, lim_y);
-                                            GHit h;
-                                            h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
-                                            hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
-                                        }
-                                        T = test_T;
-                                        last = (uint32_t)(b * GSTAR_BATCH + sl[u] + 1);
-                                    }
-                                }
-                            }
+                            T = test_T;
+                            last = (uint32_t)(b * FWD_SB + sl[u] + 1);
                         }
-                        qn = 0;
-                    };
-#pragma unroll 1
-                    for (int r0 = 0; r0 < cnt; r0 += 32) {
-                        const unsigned live = __ballot_sync(FULL, !done);
-                        if (live == 0) {
-                            warp_done = true;
-                            break;
-                        }
-                        const int j = r0 + lane;
-                        const unsigned pm = (j < cnt) ? (block_pixel_mask(buf + j * RS, g) & live) : 0u;
-                        if (!__any_sync(FULL, pm != 0u)) continue;
-                        unsigned word = transpose32(pm, lane);  // bit k: record r0+k may touch my pixel
-                        while (word) {
-                            const int k = __ffs(word) - 1;
-                            word &= word - 1;
-                            qrow[qn * 32] = (unsigned char)(r0 + k);
-                            qn++;
-                        }
-                        if (__any_sync(FULL, qn > QCAP - 32)) drain();
                     }
-                    if (!warp_done) drain();
-                    if (!warp_done && __all_sync(FULL, done)) warp_done = true;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[s]);
+                if (done) { w0 = 0u; w1 = 0u; }  // a finished pixel drops the rest of its queue
+            }
+            __syncwarp();
+            if (lane == 0 && b + FWD_NST < nb) {
+                fence_proxy_async();  // the warp's reads of this stage are ordered before the copy that overwrites it
+                fwd_fetch(ring + s * FWD_SB * RS, &full[s], tile_packed, b + FWD_NST, n);
             }
         }
+        // leaving early: the copies already issued for the next stages must have landed before the CTA can retire
+        for (int pb = b + 1; pb < min(nb, b + FWD_NST); pb++) mbar_wait(&full[pb % FWD_NST], (uint32_t)(pb / FWD_NST) & 1u);
     }
-    if (g.inside && warp < NCONS) {
+    if (g.inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pid = (size_t)g.py * p.W + g.px;
         p.final_T[pid] = T;
@@ -583,7 +563,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
 }
 
 int blend_setup() { return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM); }
-void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, BLEND_THREADS, FWD_DYN_SMEM, s>>>(p); }
+void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, FWD_THREADS, FWD_DYN_SMEM, s>>>(p); }
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
 void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s) { k_blend_bwd_gather<<<p.gx * p.gy, GATHER_THREADS, 0, s>>>(p); }
 

@@ -22,6 +22,12 @@ import helpers as Hh
 pytestmark = pytest.mark.gpu
 
 GRAD_TOL = 1e-3
+# The reference sums its blend gradients with order-nondeterministic fp32 atomics, and dL_dcov3D / dL_dscales /
+# dL_drotations amplify that noise through 1/det^2 (backward.cu:201-212): two runs of the UNMODIFIED reference on the same
+# inputs differ by up to 1.4e-3 / 5.6e-4 / 2.8e-4 of the tensor's max on the close-up scene (tools/grad_noise.py).  Against
+# the live reference those three tensors therefore get a bound above the reference's own run-to-run spread; against the
+# deterministic fp64-accumulating oracle and the golden files every tensor keeps GRAD_TOL.
+LIVE_REF_TOL = {"dL_dcov3D": 5e-3, "dL_dscales": 3e-3, "dL_drotations": 3e-3}
 
 
 def bits(a):
@@ -80,14 +86,15 @@ def check_forward_against(fwd, kw, ref, exact_image, n_contrib_slack=0):
     return g, st
 
 
-def check_grads(mine, ref, tol=GRAD_TOL):
+def check_grads(mine, ref, tol=GRAD_TOL, per_key=None):
     for k in Hh.GRAD_KEYS:
         r = np.asarray(ref[k])
         if r.size == 0:
             continue
         m = mine[k].cpu().numpy().reshape(r.shape)
         assert np.isfinite(m).all(), k
-        assert Hh.rel_err(m, r) < tol, (k, Hh.rel_err(m, r))
+        bound = max(tol, (per_key or {}).get(k, 0.0))
+        assert Hh.rel_err(m, r) < bound, (k, Hh.rel_err(m, r), bound)
 
 
 SCENES = {
@@ -149,7 +156,7 @@ def test_against_live_reference(name):
     dpix = torch.randn(3, d["H"], d["W"], device="cuda", generator=torch.Generator("cuda").manual_seed(2))
     mine = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
     rg = refgpu.backward(ref, dpix, **Hh.bwd_kwargs(kw))
-    check_grads(mine, {k: v.cpu().numpy() for k, v in rg.items()})
+    check_grads(mine, {k: v.cpu().numpy() for k, v in rg.items()}, per_key=LIVE_REF_TOL)
 
 
 def test_operator_api_autograd_matches_cabi():
