@@ -341,6 +341,11 @@ def run_gpu(args, impl_name, rank, world, local):
 
     # ---------------- public-API arm (e2e): host buffers, copies inside the timed region ----------------
     Settings, Rasterizer = make_autograd_rasterizer(impl_name)
+    if impl_name == "ours":
+        # gradient-accumulation fusion: the leaves' .grad (views of the flat all-reduce buffer) are updated inside the
+        # backward kernel instead of by autograd's AccumulateGrad (gaustar_b200/rasterizer.py)
+        import gaustar_b200
+        gaustar_b200.set_grad_accumulation_fusion(True)
     name_of = {"means3D": "dL_dmeans3D", "scales": "dL_dscales", "rotations": "dL_drotations", "opacities": "dL_dopacity", "shs": "dL_dsh"}
     base_leaves = {k: params[k].clone() for k in name_of}
     # one set of autograd leaves per compute stream (same storage, separate .grad buffers = the per-stream flat buffers),
@@ -429,7 +434,8 @@ def run_gpu(args, impl_name, rank, world, local):
     e2e_val = VIEWS_PER_GPU * world * e2e_steps / (ms_e2e / 1e3)
     e2e = {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_per_view * VIEWS_PER_GPU, "d2h_bytes_per_step": 4,
            "api": "diff_gaussian_rasterization.GaussianRasterizer + autograd; target image (uint8) and camera copied from pinned host memory per view "
-                  "(prefetched on a copy stream), loss scalar read back per step; compute streams: " + str(len(e2e_streams))}
+                  "(prefetched on a copy stream), loss scalar read back per step; compute streams: " + str(len(e2e_streams))
+                  + ("; gradient-accumulation fusion into the leaves' .grad (set_grad_accumulation_fusion)" if impl_name == "ours" else "")}
     return dict(value=value, ms_per_step=ms_value / args.steps, roofline=roofline, e2e=e2e, clocks=clk, P=P, M=M, device_name=torch.cuda.get_device_name(device),
                 launches=impl.launches_per_view * VIEWS_PER_GPU * args.steps, impl_desc=impl.name, allreduce_bytes=flat.nbytes)
 

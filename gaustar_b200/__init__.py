@@ -14,6 +14,7 @@ from .rasterizer import (  # noqa: F401
     rasterize_gaussians,
     _RasterizeGaussians,
     _C,
+    set_grad_accumulation_fusion,
 )
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_grad_accumulation_fusion"]

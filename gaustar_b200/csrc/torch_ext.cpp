@@ -94,6 +94,17 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torc
     return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);
 }
 
+struct FusedTargets {
+    torch::Tensor means3D, sh, opacity, scales, rotations;
+};
+using BwdTuple = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
+static BwdTuple backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+                              const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+                              const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+                              const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& sh,
+                              const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                              const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const FusedTargets* fused);
+
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
 RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
                                const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
@@ -102,6 +113,45 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
                                const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
                                const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
                                const torch::Tensor& imageBuffer, const bool debug)
+{
+    return backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                         tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, nullptr);
+}
+
+// Gradient-accumulation fusion (multi-view steps): the five parameter gradients are ADDED into the given tensors
+// (typically the leaves' .grad = views of the flat all-reduce buffer) inside the per-Gaussian backward kernel instead of
+// being written to fresh tensors and summed by autograd's AccumulateGrad afterwards (which re-reads and re-writes
+// 236 MB per view at 1 M Gaussians / SH degree 3).  Returns the same 8-tuple; the five fused entries are the targets.
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardFusedCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                                    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                                    const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                                    const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
+                                    const torch::Tensor& imageBuffer, const bool debug, torch::Tensor acc_means3D, torch::Tensor acc_sh,
+                                    torch::Tensor acc_opacity, torch::Tensor acc_scales, torch::Tensor acc_rotations)
+{
+    const int P = means3D.size(0);
+    const int M = sh.size(0) != 0 ? (int)sh.size(1) : 0;
+    auto ok = [&](const torch::Tensor& t, int64_t n) {
+        return t.is_cuda() && t.device() == means3D.device() && t.scalar_type() == torch::kFloat32 && t.is_contiguous() && t.numel() == n;
+    };
+    TORCH_CHECK(ok(acc_means3D, (int64_t)P * 3) && ok(acc_opacity, P) && ok(acc_scales, (int64_t)P * 3) && ok(acc_rotations, (int64_t)P * 4) &&
+                    (M == 0 || ok(acc_sh, (int64_t)P * M * 3)),
+                "gaustar_b200: fused accumulation targets must be contiguous float32 CUDA tensors of the parameters' sizes");
+    FusedTargets ft{acc_means3D, acc_sh, acc_opacity, acc_scales, acc_rotations};
+    return backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                         tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, &ft);
+}
+
+static std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+              const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+              const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+              const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+              const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+              const bool debug, const FusedTargets* fused)
 {
     TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
     const torch::Device dev = means3D.device();
@@ -115,15 +165,15 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
     auto opts = means3D.options().dtype(torch::kFloat32);
     // every output is fully written by the fused per-Gaussian backward kernel: no zero-fills
     // (the reference zero-fills nine tensors per call, rasterize_points.cu:150-158)
-    torch::Tensor dL_dmeans3D = torch::empty({P, 3}, opts);
+    torch::Tensor dL_dmeans3D = fused ? fused->means3D : torch::empty({P, 3}, opts);
     torch::Tensor dL_dmeans2D = torch::empty({P, 3}, opts);
     torch::Tensor dL_dcolors = torch::empty({P, 3}, opts);
     torch::Tensor dL_dconic = torch::empty({P, 2, 2}, opts);
-    torch::Tensor dL_dopacity = torch::empty({P, 1}, opts);
+    torch::Tensor dL_dopacity = fused ? fused->opacity : torch::empty({P, 1}, opts);
     torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
-    torch::Tensor dL_dsh = torch::empty({P, M, 3}, opts);
-    torch::Tensor dL_dscales = torch::empty({P, 3}, opts);
-    torch::Tensor dL_drotations = torch::empty({P, 4}, opts);
+    torch::Tensor dL_dsh = (fused && M) ? fused->sh : torch::empty({P, M, 3}, opts);
+    torch::Tensor dL_dscales = fused ? fused->scales : torch::empty({P, 3}, opts);
+    torch::Tensor dL_drotations = fused ? fused->rotations : torch::empty({P, 4}, opts);
     if (P != 0) {
         torch::Tensor scratch = torch::zeros({P, GSTAR_GRAD_SCRATCH_FLOATS}, opts);
         const torch::Tensor bg = prep(background, dev), m3 = prep(means3D, dev), col = prep(colors, dev), sc = prep(scales, dev),
@@ -149,7 +199,7 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
         a.dL_dscale = dL_dscales.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
         a.blend_grad_scratch = scratch.data_ptr<float>();
         a.debug = debug ? 1 : 0;
-        a.accumulate_param_grads = 0;
+        a.accumulate_param_grads = fused ? 1 : 0;
         check(gstar_raster_backward(&a, stream));
     }
     return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
@@ -174,5 +224,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+    m.def("rasterize_gaussians_backward_fused", &RasterizeGaussiansBackwardFusedCUDA);
     m.def("mark_visible", &markVisible);
 }

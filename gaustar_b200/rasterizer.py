@@ -21,6 +21,35 @@ except ImportError as e:  # fail loudly: there is no fallback implementation
     ) from e
 
 
+_GRAD_FUSION = False
+
+
+def set_grad_accumulation_fusion(enabled: bool) -> bool:
+    """Gradient-accumulation fusion for multi-view steps (off by default; returns the previous setting).
+
+    When on, and every differentiable parameter input of a call (means3D, opacities, scales, rotations, shs) is a LEAF
+    whose ``.grad`` is already allocated (contiguous float32, the parameter's shape), the backward kernel adds the
+    view's gradients straight into those ``.grad`` tensors and the autograd function returns ``None`` for them --
+    instead of writing five fresh tensors that AccumulateGrad then re-reads and sums (236 MB per view at 1 M Gaussians /
+    SH degree 3).  Point the ``.grad`` tensors at views of one flat buffer (``gaustar_b200.dist.FlatGrads``) and a
+    multi-view step needs a single all-reduce.  Any call that does not qualify takes the ordinary path, so results are
+    the same either way; tensor hooks on those leaves are not run for fused calls."""
+    global _GRAD_FUSION
+    old, _GRAD_FUSION = _GRAD_FUSION, bool(enabled)
+    return old
+
+
+def _fusable(t, needs):
+    """t: an input of the autograd function.  Empty (absent) inputs are trivially fine."""
+    if t.numel() == 0:
+        return True
+    if not (needs and t.is_leaf):
+        return False
+    g = t.grad
+    return (g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()
+            and g.shape == t.shape and g.device == t.device)
+
+
 def _cpu_snapshot(args):
     # DGR/__init__.py:17-19: inputs are copied before the call so a crash can be replayed
     return tuple(a.cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
@@ -55,6 +84,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer)
+        # the caller's own tensor objects (their .grad is the accumulation target of a fused backward)
+        ctx.param_inputs = (means3D, sh, opacities, scales, rotations) if _GRAD_FUSION else None
         ctx.mark_non_differentiable(radii)
         return color, radii
 
@@ -65,6 +96,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix,
                 rs.tanfovx, rs.tanfovy, grad_out_color, sh, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer,
                 imgBuffer, rs.debug)
+        pin = ctx.param_inputs
+        if (_GRAD_FUSION and pin is not None and not rs.debug and cov3Ds_precomp.numel() == 0
+                and all(_fusable(t, ctx.needs_input_grad[i]) for t, i in zip(pin, (0, 2, 4, 5, 6)))):
+            m3, shp, op, sc, rot = pin
+            e = torch.Tensor([])
+            out = _C.rasterize_gaussians_backward_fused(*args, m3.grad, shp.grad if shp.numel() else e, op.grad, sc.grad, rot.grad)
+            grad_means2D, grad_colors_precomp, _go, _gm, grad_cov3Ds_precomp, _gs, _gsc, _gr = out
+            return (None, grad_means2D, None, grad_colors_precomp, None, None, None, None, None)
         if rs.debug:
             snapshot = _cpu_snapshot(args)
             try:

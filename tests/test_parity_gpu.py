@@ -377,3 +377,46 @@ def test_two_streams_autograd_equals_single_stream():
         torch.cuda.synchronize()
         total = flats[0].flat + flats[1].flat
         assert Hh.rel_err(total.cpu(), ref.flat.cpu()) < 1e-4, rep
+
+
+def test_grad_accumulation_fusion_matches_autograd():
+    """set_grad_accumulation_fusion(True): leaves with preallocated .grad receive the views' gradients inside the kernel
+    (the function returns None for them); the result equals ordinary autograd accumulation, and a call that does not
+    qualify (non-leaf input) silently takes the ordinary path."""
+    import diff_gaussian_rasterization as dgr
+    import gaustar_b200
+    g = scene.surface_gaussians(9000, 3, seed=11)
+    cams = scene.dome_cameras(5, 256, 160)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    base = {"means3D": t(g.means3D), "scales": t(g.scales), "rotations": t(g.rotations), "opacities": t(g.opacities), "shs": t(g.shs)}
+    bg = torch.tensor([0.0, 1.0, 0.0], device="cuda")
+    tg = [torch.rand(3, 160, 256, device="cuda", generator=torch.Generator("cuda").manual_seed(i)) for i in range(3)]
+
+    def run(fused, scale_inputs=False):
+        old = gaustar_b200.set_grad_accumulation_fusion(fused)
+        try:
+            ls = {k: v.detach().clone().requires_grad_(True) for k, v in base.items()}
+            for p_ in ls.values():
+                p_.grad = torch.zeros_like(p_)
+            m2d = torch.zeros(g.P, 3, device="cuda", requires_grad=True)
+            for i in range(3):
+                cam = cams[i + 1]
+                rs = dgr.GaussianRasterizationSettings(160, 256, cam.tanfovx, cam.tanfovy, bg, 1.0, t(cam.viewmatrix), t(cam.projmatrix), 3, t(cam.campos),
+                                                       False, False)
+                m3 = ls["means3D"] * 1.0 if scale_inputs else ls["means3D"]  # non-leaf input: must fall back
+                img, _ = dgr.GaussianRasterizer(rs)(means3D=m3, means2D=m2d, opacities=ls["opacities"], shs=ls["shs"], scales=ls["scales"],
+                                                    rotations=ls["rotations"])
+                torch.nn.functional.l1_loss(img, tg[i]).backward()
+            torch.cuda.synchronize()
+            return {k: v.grad.clone() for k, v in ls.items()}, m2d.grad.clone()
+        finally:
+            gaustar_b200.set_grad_accumulation_fusion(old)
+
+    ref, ref2d = run(False)
+    fus, fus2d = run(True)
+    mixed, _ = run(True, scale_inputs=True)
+    for k in ref:
+        assert float(ref[k].abs().max()) > 0
+        assert Hh.rel_err(fus[k].cpu(), ref[k].cpu()) < 1e-4, k
+        assert Hh.rel_err(mixed[k].cpu(), ref[k].cpu()) < 1e-4, k
+    assert Hh.rel_err(fus2d.cpu(), ref2d.cpu()) < 1e-4
