@@ -135,7 +135,7 @@ def build_workload(device, rank, world):
 class OursCABI:
     """Device-resident arm: straight through the C ABI."""
     name = "gaustar_b200 (C ABI)"
-    launches_per_view = 10  # preprocess_fwd, tile_scan, emit, tile_sort x3 (length classes), blend_fwd, blend_bwd_gather, blend_bwd (no-op), preprocess_bwd
+    launches_per_view = 8  # preprocess_fwd, tile_scan, emit, tile_sort, blend_fwd, blend_bwd_gather, blend_bwd (no-op), preprocess_bwd
 
     def __init__(self):
         from gaustar_b200 import capi
@@ -321,7 +321,7 @@ def run_gpu(args, impl_name, rank, world, local):
         alg = {"preprocess_fwd": P * (44 + 12 * M) + 8 * P + P * (52 + 12), "tile_scan": 8 * T_tiles, "emit": 20 * P + 12 * R_avg,
                "tile_sort": 24 * R_avg + 8 * R_avg + 8 * T_tiles, "blend_fwd": 40 * R_avg + 20 * npix + 8 * T_tiles,
                "blend_bwd": 40 * R_avg + 20 * npix + 36 * P, "preprocess_bwd": P * (108 + 12 * M) + P * (40 + 12 * M)}
-        kernel_of = {"preprocess_fwd": "k_preprocess_fwd", "tile_scan": "k_tile_scan", "emit": "k_emit", "tile_sort": "k_tile_sort_bucket (x2) + k_tile_sort",
+        kernel_of = {"preprocess_fwd": "k_preprocess_fwd", "tile_scan": "k_tile_scan", "emit": "k_emit", "tile_sort": "k_tile_sort",
                      "blend_fwd": "k_blend_fwd", "blend_bwd": "k_blend_bwd_gather", "preprocess_bwd": "k_preprocess_bwd"}
         peak, how = measured_peak()
         per = {}

@@ -19,9 +19,7 @@ namespace gstar {
 
 constexpr int SCAN_THREADS = 1024;
 constexpr uint32_t SORT_CAP = 8192;                // keys (64 KB, a power of two) one CTA sorts in shared memory
-constexpr int SORT_THREADS = 512;
 constexpr int LPT_BUCKETS = 132;                   // quarter-octave size classes for the longest-first tile order
-constexpr uint32_t SMALL_CAP = 2048, MED_CAP = 8192;  // list-length classes of the sort kernels (powers of two = LPT bucket edges)
 constexpr int LPT_SMALL_END = 1 + 11 * 4;          // first LPT bucket with >= 2048 instances
 constexpr int LPT_MED_END = 1 + 13 * 4;            // first LPT bucket with >= 8192 instances
 
@@ -219,19 +217,37 @@ __device__ __forceinline__ void sort8(uint64_t v[8])
     cx(v[0], v[1]); cx(v[2], v[3]); cx(v[4], v[5]); cx(v[6], v[7]);                      //     j=1
 }
 
+// A "group" is the set of threads that sorts one tile: the whole CTA, or a 256-thread quarter of it (named barrier).
+struct Grp {
+    uint32_t tid, nt;  // thread index inside the group, group size (a multiple of 32)
+    int bar;           // 0: __syncthreads(); 1..15: bar.sync <bar>, nt
+};
+__device__ __forceinline__ void gsync(const Grp& g)
+{
+    if (g.bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.nt) : "memory");
+}
+// per-group scratch in shared memory
+struct GrpSmem {
+    uint32_t coarse[256], cbase[256];
+    uint32_t w[33];            // warp partials of the group scans
+    uint32_t item, dmin, dmax, flag;
+    unsigned long long base;   // hit-log base of the tile
+};
+
 // disperse stages j = jstart .. 8 on the array, then the register tail (4,2,1); npad = padded length (multiple of 8)
-__device__ __forceinline__ void disperse_and_tail(uint64_t* a, uint32_t n, uint32_t npad, uint32_t jstart, uint32_t tid, uint32_t nt)
+__device__ __forceinline__ void disperse_and_tail(uint64_t* a, uint32_t n, uint32_t npad, uint32_t jstart, const Grp& g)
 {
     const uint32_t pairs = npad >> 1;
     for (uint32_t j = jstart; j >= 8; j >>= 1) {
         const uint32_t jshift = 31 - __clz(j);
-        for (uint32_t t = tid; t < pairs; t += nt) {
+        for (uint32_t t = g.tid; t < pairs; t += g.nt) {
             const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
             if (l < n) cmpxchg(a, i, l);
         }
-        __syncthreads();
+        gsync(g);
     }
-    for (uint32_t gidx = tid; gidx < (npad >> 3); gidx += nt) {
+    for (uint32_t gidx = g.tid; gidx < (npad >> 3); gidx += g.nt) {
         const uint32_t base = gidx << 3;
         if (base + 1 < n) {
             uint64_t v[8];
@@ -240,15 +256,15 @@ __device__ __forceinline__ void disperse_and_tail(uint64_t* a, uint32_t n, uint3
             store8(a, base, n, v);
         }
     }
-    __syncthreads();
+    gsync(g);
 }
 
-__device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, uint32_t tid, uint32_t nt)
+__device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, const Grp& g)
 {
     if (n < 2) return;
     uint32_t npad = 8;
     while (npad < n) npad <<= 1;
-    for (uint32_t gidx = tid; gidx < (npad >> 3); gidx += nt) {  // levels 2,4,8 in registers
+    for (uint32_t gidx = g.tid; gidx < (npad >> 3); gidx += g.nt) {  // levels 2,4,8 in registers
         const uint32_t base = gidx << 3;
         if (base + 1 < n) {
             uint64_t v[8];
@@ -257,48 +273,73 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* a, uint32_t n, uint32_t t
             store8(a, base, n, v);
         }
     }
-    __syncthreads();
+    gsync(g);
     const uint32_t pairs = npad >> 1;
     for (uint32_t k = 16; k <= npad; k <<= 1) {
         const uint32_t half = k >> 1, hshift = 31 - __clz(half);
-        for (uint32_t t = tid; t < pairs; t += nt) {  // flip stage
+        for (uint32_t t = g.tid; t < pairs; t += g.nt) {  // flip stage
             const uint32_t blk = t >> hshift, off = t & (half - 1);
             const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
             if (l < n) cmpxchg(a, i, l);
         }
-        __syncthreads();
-        disperse_and_tail(a, n, npad, k >> 2, tid, nt);
+        gsync(g);
+        disperse_and_tail(a, n, npad, k >> 2, g);
     }
 }
 
-// One CTA per tile, tiles taken longest-first.  Lists up to SORT_CAP keys are sorted entirely in shared memory;
-// longer ones chunk-wise in shared memory and finished with the hybrid schedule: only the few network stages whose
-// partners lie in different chunks run on global memory (L2-resident), every other stage on a staged chunk.
-// Write the sorted list of one tile: point_list (the reference's sorted value list) and the tile-contiguous packed
-// record stream the blend kernels read with one TMA bulk copy per 256 entries: the first 44 bytes of the Gaussian's
-// GRec followed by its index.  Random 48-byte reads hit the L2-resident GRec array; writes are contiguous.
 __device__ __forceinline__ uint32_t foot_area(uint32_t bbx, uint32_t bby, int tx0, int ty0, int limx, int limy)
 {
     const Foot f = clip_foot(bbx, bby, tx0, ty0, limx, limy);
     return (f.w > 0 && f.h > 0) ? (uint32_t)(f.w * f.h) : 0u;
 }
 
-// The last word of a packed record is the instance's first HIT-LOG slot: every instance owns one 16-byte slot per
-// pixel of its alpha-bounds inside this tile (clip_foot).  Slots of a tile are contiguous (exclusive scan over the
-// CTA, any order), tiles take their block from a global cursor.  The cursor keeps counting when the log is too small
-// (or disabled) so that the host learns the size this view needs.
-template <int U>
-__device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, uint32_t start, const uint64_t* keys, uint32_t n, uint32_t tid,
-                                             uint32_t nt)
+// Exclusive scan of one value per thread over the group.
+__device__ __forceinline__ uint32_t group_excl_scan(uint32_t v, const Grp& g, uint32_t* s_w, uint32_t* total = nullptr)
 {
-    __shared__ uint32_t s_warp[32];
-    __shared__ unsigned long long s_base;
+    const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nt >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += u;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    gsync(g);
+    if (warp == 0) {
+        const uint32_t w = lane < nwarps ? s_w[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += u;
+        }
+        if (lane < nwarps) s_w[lane] = wi - w;
+        if (lane == 31) s_w[32] = wi;
+    }
+    gsync(g);
+    const uint32_t r = s_w[warp] + incl - v;
+    if (total) *total = s_w[32];
+    gsync(g);  // s_w may be reused right away
+    return r;
+}
+
+// Write the sorted list of one tile: point_list (the reference's sorted value list) and the tile-contiguous packed
+// record stream the blend kernels read with one TMA bulk copy per batch: the first 44 bytes of the Gaussian's GRec
+// followed by the instance's first HIT-LOG slot.  Every instance owns one 16-byte slot per pixel of its alpha-bounds
+// inside this tile (clip_foot); slots of a tile are contiguous (exclusive scan over the group, any order), tiles take
+// their block from a global cursor.  The cursor keeps counting when the log is too small (or disabled) so that the host
+// learns the size this view needs.  Random 48-byte reads hit the L2-resident GRec array; writes are contiguous.
+// Every gather is issued for U instances at once: the loops are latency-bound (one L2 round trip per step).
+template <int U>
+__device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, uint32_t start, const uint64_t* keys, uint32_t n, const Grp& g,
+                                             GrpSmem* sm)
+{
     const float4* recs = reinterpret_cast<const float4*>(p.recs);
     float4* out = reinterpret_cast<float4*>(p.packed + (size_t)start * GSTAR_REC_SMEM);
     const int tx0 = (int)(tile % (uint32_t)p.gx) * GSTAR_TILE, ty0 = (int)(tile / (uint32_t)p.gx) * GSTAR_TILE;
     const int limx = min(GSTAR_TILE - 1, p.W - 1 - tx0), limy = min(GSTAR_TILE - 1, p.H - 1 - ty0);
-    // every gather below is issued for U instances at once: the loop is latency-bound (one L2 round trip per step)
     const unsigned char* recb = reinterpret_cast<const unsigned char*>(p.recs);
+    const uint32_t tid = g.tid, nt = g.nt;
     uint32_t mine = 0;
     for (uint32_t i0 = tid; i0 < n; i0 += U * nt) {
         uint2 bb[U];
@@ -312,32 +353,15 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
         for (int u = 0; u < U; u++)
             if (i0 + u * nt < n) mine += foot_area(bb[u].x, bb[u].y, tx0, ty0, limx, limy);
     }
-    const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += v;
+    uint32_t tile_total;
+    const uint32_t excl = group_excl_scan(mine, g, sm->w, &tile_total);
+    if (tid == 0) {
+        const unsigned long long base = atomicAdd(&p.hdr->log_cursor, (unsigned long long)tile_total);
+        if (base + tile_total > p.log_capacity) p.hdr->log_overflow = 1u;
+        sm->base = base;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = lane < nwarps ? s_warp[lane] : 0u;
-        uint32_t wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-            if ((int)lane >= d) wi += v;
-        }
-        s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
-        if (lane == 31) {
-            const unsigned long long base = atomicAdd(&p.hdr->log_cursor, (unsigned long long)wi);
-            if (base + wi > p.log_capacity) p.hdr->log_overflow = 1u;
-            s_base = base;
-        }
-    }
-    __syncthreads();
-    uint32_t slot = (uint32_t)s_base + s_warp[warp] + (incl - mine);
+    gsync(g);
+    uint32_t slot = (uint32_t)sm->base + excl;
     for (uint32_t i0 = tid; i0 < n; i0 += U * nt) {
         uint32_t id[U];
         float4 a[U], b[U], c[U];
@@ -363,16 +387,16 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
     }
 }
 
-// Next tile of list-length class `cls` (persistent CTAs; tiles were ordered longest first by tile_scan).
-__device__ __forceinline__ bool next_tile(const BinParams& p, int cls, uint32_t* s_item, uint32_t& tile, uint32_t& start, uint32_t& n)
+// Next tile of list-length class `cls` for this group (tiles were ordered longest first by tile_scan).
+__device__ __forceinline__ bool next_tile(const BinParams& p, int cls, const Grp& g, GrpSmem* sm, uint32_t& tile, uint32_t& start, uint32_t& n)
 {
-    __syncthreads();  // everyone is done with the previous tile (shared memory, *s_item)
-    if (threadIdx.x == 0) {
+    gsync(g);  // everyone is done with the previous tile (shared memory, sm->item)
+    if (g.tid == 0) {
         const uint32_t lo = cls ? p.hdr->cls_end[cls - 1] : 0u;
-        *s_item = lo + atomicAdd(&p.hdr->cls_cursor[cls], 1u);
+        sm->item = lo + atomicAdd(&p.hdr->cls_cursor[cls], 1u);
     }
-    __syncthreads();
-    const uint32_t item = *s_item;
+    gsync(g);
+    const uint32_t item = sm->item;
     if (item >= p.hdr->cls_end[cls]) return false;
     tile = p.tile_order[item];
     start = p.ranges[2 * tile];
@@ -381,92 +405,57 @@ __device__ __forceinline__ bool next_tile(const BinParams& p, int cls, uint32_t*
 }
 
 // Class 0 (lists of >= 8192 instances; rare): bitonic network, chunk-wise in shared memory with the chunk-crossing stages
-// on the L2-resident keys.  Also the network the bucket kernels fall back to.
-__global__ void __launch_bounds__(SORT_THREADS) k_tile_sort(BinParams p)
+// on the L2-resident keys.  Also the network the bucket sort falls back to.
+__device__ __forceinline__ void network_sort_tile(const BinParams& p, const Grp& g, GrpSmem* sm, uint64_t* s_keys, uint32_t tile, uint32_t start,
+                                                  uint32_t n)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ uint32_t s_item;
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);
-    if (p.hdr->overflow) return;
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    uint32_t tile, start, n;
-    while (next_tile(p, 0, &s_item, tile, start, n)) {
-    uint64_t* g = reinterpret_cast<uint64_t*>(p.entries) + start;
+    const uint32_t tid = g.tid, nt = g.nt;
+    uint64_t* gk = reinterpret_cast<uint64_t*>(p.entries) + start;
     constexpr uint32_t CH = SORT_CAP;
     if (n <= CH) {
-        for (uint32_t i = tid; i < n; i += nt) s_keys[i] = g[i];
-        __syncthreads();
-        bitonic_sort(s_keys, n, tid, nt);
-        write_sorted<2>(p, tile, start, s_keys, n, tid, nt);
-        continue;
+        for (uint32_t i = tid; i < n; i += nt) s_keys[i] = gk[i];
+        gsync(g);
+        bitonic_sort(s_keys, n, g);
+        write_sorted<2>(p, tile, start, s_keys, n, g, sm);
+        return;
     }
     uint32_t npad = CH;
     while (npad < n) npad <<= 1;
     const uint32_t nchunks = (n + CH - 1) / CH;
     for (uint32_t c = 0; c < nchunks; c++) {  // phase 0: every chunk fully sorted in shared memory
         const uint32_t base = c * CH, m = min(CH, n - base);
-        for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
-        __syncthreads();
-        bitonic_sort(s_keys, m, tid, nt);
-        for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
-        __syncthreads();
+        for (uint32_t i = tid; i < m; i += nt) s_keys[i] = gk[base + i];
+        gsync(g);
+        bitonic_sort(s_keys, m, g);
+        for (uint32_t i = tid; i < m; i += nt) gk[base + i] = s_keys[i];
+        gsync(g);
     }
     for (uint32_t k = 2 * CH; k <= npad; k <<= 1) {  // merge levels
         const uint32_t half = k >> 1, hshift = 31 - __clz(half);
         for (uint32_t t = tid; t < (npad >> 1); t += nt) {  // flip stage (global)
             const uint32_t blk = t >> hshift, off = t & (half - 1);
             const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
-            if (l < n) cmpxchg(g, i, l);
+            if (l < n) cmpxchg(gk, i, l);
         }
-        __syncthreads();
+        gsync(g);
         for (uint32_t j = k >> 2; j >= CH; j >>= 1) {  // disperse stages that still cross chunks (global)
             const uint32_t jshift = 31 - __clz(j);
             for (uint32_t t = tid; t < (npad >> 1); t += nt) {
                 const uint32_t i = ((t >> jshift) << (jshift + 1)) + (t & (j - 1)), l = i + j;
-                if (l < n) cmpxchg(g, i, l);
+                if (l < n) cmpxchg(gk, i, l);
             }
-            __syncthreads();
+            gsync(g);
         }
         for (uint32_t c = 0; c < nchunks; c++) {  // stages j = CH/2 .. 1 are chunk-local (shared memory)
             const uint32_t base = c * CH, m = min(CH, n - base);
-            for (uint32_t i = tid; i < m; i += nt) s_keys[i] = g[base + i];
-            __syncthreads();
-            disperse_and_tail(s_keys, m, CH, CH >> 1, tid, nt);
-            for (uint32_t i = tid; i < m; i += nt) g[base + i] = s_keys[i];
-            __syncthreads();
+            for (uint32_t i = tid; i < m; i += nt) s_keys[i] = gk[base + i];
+            gsync(g);
+            disperse_and_tail(s_keys, m, CH, CH >> 1, g);
+            for (uint32_t i = tid; i < m; i += nt) gk[base + i] = s_keys[i];
+            gsync(g);
         }
     }
-    write_sorted<2>(p, tile, start, g, n, tid, nt);
-    }
-}
-
-// Exclusive scan of one value per thread over the CTA (NT threads, a multiple of 32).  s_w: NT/32 + 1 words.
-template <int NT>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_w)
-{
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += u;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = lane < NT / 32 ? s_w[lane] : 0u;
-        uint32_t wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, d);
-            if ((int)lane >= d) wi += u;
-        }
-        if (lane < NT / 32) s_w[lane] = wi - w;
-    }
-    __syncthreads();
-    const uint32_t r = s_w[warp] + incl - v;
-    __syncthreads();  // s_w may be reused right away
-    return r;
+    write_sorted<2>(p, tile, start, gk, n, g, sm);
 }
 
 // Classes 1 and 2 (lists shorter than CAP): two-level adaptive bucket sort, O(n) and ~a dozen barriers instead of the
@@ -479,115 +468,142 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_w)
 // 64-bit key, so the result is the reference's (tile, depth, index) order exactly.  A pathological fine bucket
 // (> MAX_FINE keys, e.g. thousands of identical depths) sends the tile through the bitonic network instead.
 template <uint32_t CAP, int NT>
-__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 3)) k_tile_sort_bucket(BinParams p, int cls)
+__device__ __forceinline__ void bucket_sort_tile(const BinParams& p, const Grp& g, GrpSmem* sm, uint64_t* s_out, uint32_t* s_fine, uint32_t tile,
+                                                 uint32_t start, uint32_t n)
 {
     constexpr int KPT = CAP / NT;
     constexpr uint32_t MAX_FINE = 48;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    uint64_t* s_out = reinterpret_cast<uint64_t*>(s_raw);              // [CAP]
-    uint32_t* s_fine = reinterpret_cast<uint32_t*>(s_raw + CAP * 8);   // [CAP + KPT] fine-bucket counts, then offsets
-    __shared__ uint32_t s_coarse[256], s_cbase[256], s_w[NT / 32 + 1];
-    __shared__ uint32_t s_item, s_dmin, s_dmax, s_flag;
-    if (p.hdr->overflow) return;
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    uint32_t tile, start, n;
-    while (next_tile(p, cls, &s_item, tile, start, n)) {
-        const uint64_t* g = reinterpret_cast<const uint64_t*>(p.entries) + start;
-        uint64_t k[KPT];
-        uint32_t dmin = 0xffffffffu, dmax = 0u;
+    const uint32_t tid = g.tid, lane = tid & 31;
+    const uint64_t* gk = reinterpret_cast<const uint64_t*>(p.entries) + start;
+    uint64_t k[KPT];
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
-        for (int e = 0; e < KPT; e++) {
-            const uint32_t i = tid + e * NT;
-            k[e] = i < n ? g[i] : ~0ull;
-            if (i < n) { dmin = min(dmin, (uint32_t)(k[e] >> 32)); dmax = max(dmax, (uint32_t)(k[e] >> 32)); }
-        }
-        if (tid == 0) { s_dmin = 0xffffffffu; s_dmax = 0u; s_flag = 0u; }
-        if (tid < 256) s_coarse[tid] = 0u;
+    for (int e = 0; e < KPT; e++) {
+        const uint32_t i = tid + e * NT;
+        k[e] = i < n ? gk[i] : ~0ull;
+        if (i < n) { dmin = min(dmin, (uint32_t)(k[e] >> 32)); dmax = max(dmax, (uint32_t)(k[e] >> 32)); }
+    }
+    if (tid == 0) { sm->dmin = 0xffffffffu; sm->dmax = 0u; sm->flag = 0u; }
+    if (tid < 256) sm->coarse[tid] = 0u;
 #pragma unroll
-        for (int e = 0; e <= KPT; e++) {
-            const uint32_t i = tid + e * NT;
-            if (i < CAP + KPT) s_fine[i] = 0u;
-        }
-        __syncthreads();
-        dmin = __reduce_min_sync(0xffffffffu, dmin);
-        dmax = __reduce_max_sync(0xffffffffu, dmax);
-        if (lane == 0) { atomicMin(&s_dmin, dmin); atomicMax(&s_dmax, dmax); }
-        __syncthreads();
-        dmin = s_dmin; dmax = s_dmax;
-        const float scale = 256.0f / ((float)(dmax - dmin) + 1.0f);
+    for (int e = 0; e <= KPT; e++) {
+        const uint32_t i = tid + e * NT;
+        if (i < CAP + KPT) s_fine[i] = 0u;
+    }
+    gsync(g);
+    dmin = __reduce_min_sync(0xffffffffu, dmin);
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    if (lane == 0) { atomicMin(&sm->dmin, dmin); atomicMax(&sm->dmax, dmax); }
+    gsync(g);
+    dmin = sm->dmin; dmax = sm->dmax;
+    const float scale = 256.0f / ((float)(dmax - dmin) + 1.0f);
 #pragma unroll
-        for (int e = 0; e < KPT; e++) {
-            const uint32_t i = tid + e * NT;
+    for (int e = 0; e < KPT; e++) {
+        const uint32_t i = tid + e * NT;
+        const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
+        const uint32_t cb = min(255u, (uint32_t)x);
+        // neighbouring keys of a surface fall into few coarse bins: one shared-memory atomic per distinct bin per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, i < n ? cb : 0xffffffffu);
+        if (i < n && (int)lane == __ffs(peers) - 1) atomicAdd(&sm->coarse[cb], (uint32_t)__popc(peers));
+    }
+    gsync(g);
+    {
+        const uint32_t c = tid < 256 ? sm->coarse[tid] : 0u;
+        const uint32_t ex = group_excl_scan(c, g, sm->w);
+        if (tid < 256) sm->cbase[tid] = ex;
+    }
+    gsync(g);
+    uint32_t fr[KPT];  // fine bucket | rank inside it << 16 (both < CAP <= 2^13)
+#pragma unroll
+    for (int e = 0; e < KPT; e++) {
+        const uint32_t i = tid + e * NT;
+        fr[e] = 0u;
+        if (i < n) {
             const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
             const uint32_t cb = min(255u, (uint32_t)x);
-            // neighbouring keys of a surface fall into few coarse bins: one shared-memory atomic per distinct bin per warp
-            const unsigned peers = __match_any_sync(0xffffffffu, i < n ? cb : 0xffffffffu);
-            if (i < n && (int)lane == __ffs(peers) - 1) atomicAdd(&s_coarse[cb], (uint32_t)__popc(peers));
+            const uint32_t cnt = sm->coarse[cb];
+            const float frac = fminf(fmaxf(x - (float)cb, 0.0f), 1.0f);
+            const uint32_t fb = sm->cbase[cb] + min(cnt - 1u, (uint32_t)(frac * (float)cnt));
+            fr[e] = fb | (atomicAdd(&s_fine[fb], 1u) << 16);
         }
-        __syncthreads();
-        {
-            const uint32_t c = tid < 256 ? s_coarse[tid] : 0u;
-            const uint32_t ex = block_excl_scan<NT>(c, s_w);
-            if (tid < 256) s_cbase[tid] = ex;
-        }
-        __syncthreads();
-        uint32_t fr[KPT];  // fine bucket | rank inside it << 16 (both < CAP <= 2^13)
+    }
+    gsync(g);
+    {   // counts -> exclusive offsets, KPT consecutive fine buckets per thread (the n fine buckets fit: n < CAP)
+        uint32_t c[KPT], sum = 0u;
 #pragma unroll
-        for (int e = 0; e < KPT; e++) {
-            const uint32_t i = tid + e * NT;
-            fr[e] = 0u;
-            if (i < n) {
-                const float x = (float)((uint32_t)(k[e] >> 32) - dmin) * scale;
-                const uint32_t cb = min(255u, (uint32_t)x);
-                const uint32_t cnt = s_coarse[cb];
-                const float frac = fminf(fmaxf(x - (float)cb, 0.0f), 1.0f);
-                const uint32_t fb = s_cbase[cb] + min(cnt - 1u, (uint32_t)(frac * (float)cnt));
-                fr[e] = fb | (atomicAdd(&s_fine[fb], 1u) << 16);
-            }
-        }
-        __syncthreads();
-        {   // counts -> exclusive offsets, KPT consecutive fine buckets per thread (the n fine buckets fit: n < CAP)
-            uint32_t c[KPT], sum = 0u;
+        for (int e = 0; e < KPT; e++) { c[e] = s_fine[tid * KPT + e]; sum += c[e]; }
+        uint32_t run = group_excl_scan(sum, g, sm->w);
 #pragma unroll
-            for (int e = 0; e < KPT; e++) { c[e] = s_fine[tid * KPT + e]; sum += c[e]; }
-            uint32_t run = block_excl_scan<NT>(sum, s_w);
+        for (int e = 0; e < KPT; e++) { s_fine[tid * KPT + e] = run; run += c[e]; }
+        if (tid == NT - 1) s_fine[CAP] = run;
+    }
+    gsync(g);
 #pragma unroll
-            for (int e = 0; e < KPT; e++) { s_fine[tid * KPT + e] = run; run += c[e]; }
-            if (tid == NT - 1) s_fine[CAP] = run;
+    for (int e = 0; e < KPT; e++)
+        if (tid + e * NT < n) s_out[s_fine[fr[e] & 0xffffu] + (fr[e] >> 16)] = k[e];
+    gsync(g);
+    for (uint32_t b = tid; b < n; b += NT) {
+        const uint32_t o = s_fine[b], c = s_fine[b + 1] - o;
+        if (c < 2u) continue;
+        if (c > MAX_FINE) { sm->flag = 1u; atomicMax(&p.hdr->pad0[1], c); continue; }
+        for (uint32_t a = 1; a < c; a++) {
+            const uint64_t v = s_out[o + a];
+            uint32_t j = a;
+            while (j > 0 && s_out[o + j - 1] > v) { s_out[o + j] = s_out[o + j - 1]; j--; }
+            s_out[o + j] = v;
         }
-        __syncthreads();
+    }
+    gsync(g);
+    if (sm->flag) {
+        if (tid == 0) atomicAdd(&p.hdr->pad0[0], 1u);  // statistics: tiles that took the network
 #pragma unroll
         for (int e = 0; e < KPT; e++)
-            if (tid + e * NT < n) s_out[s_fine[fr[e] & 0xffffu] + (fr[e] >> 16)] = k[e];
+            if (tid + e * NT < n) s_out[tid + e * NT] = k[e];
+        gsync(g);
+        bitonic_sort(s_out, n, g);
+    }
+    write_sorted<2>(p, tile, start, s_out, n, g, sm);
+}
+
+// ---- K4: ONE persistent kernel sorts every tile list -------------------------------------------------------------
+// CTAs of 1024 threads, one per SM.  A CTA first pulls tiles of class 0 (>= 8192 instances, network) and class 1
+// (2048..8191, bucket sort with all 1024 threads), longest first; when those run out it splits into four 256-thread
+// groups (named barriers 1..4) that pull class-2 tiles (< 2048 instances) independently.  One launch, no tail between
+// the classes, and the short lists -- the bulk of a surface view -- are sorted four at a time per SM.
+constexpr int SORT_CTA = 1024;
+constexpr uint32_t SMALL_CAP = 2048, MED_CAP = 8192;
+constexpr int SMALL_NT = 256, SMALL_GROUPS = SORT_CTA / SMALL_NT;
+constexpr int SMALL_BYTES = SMALL_CAP * 8 + (SMALL_CAP + SMALL_CAP / SMALL_NT + 1) * 4;   // keys out + fine buckets
+constexpr int SMALL_STRIDE = (SMALL_BYTES + 127) / 128 * 128;
+constexpr int MED_BYTES = MED_CAP * 8 + (MED_CAP + MED_CAP / SORT_CTA + 1) * 4;
+constexpr int SORT_DYN_SMEM = (MED_BYTES > SMALL_GROUPS * SMALL_STRIDE ? MED_BYTES : SMALL_GROUPS * SMALL_STRIDE);
+
+__global__ void __launch_bounds__(SORT_CTA, 1) k_tile_sort(BinParams p)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ GrpSmem s_grp[SMALL_GROUPS];
+    if (p.hdr->overflow) return;
+    uint32_t tile, start, n;
+    {
+        Grp g{threadIdx.x, SORT_CTA, 0};
+        GrpSmem* sm = &s_grp[0];
+        uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);
+        while (next_tile(p, 0, g, sm, tile, start, n)) network_sort_tile(p, g, sm, s_keys, tile, start, n);
+        uint32_t* s_fine = reinterpret_cast<uint32_t*>(s_raw + MED_CAP * 8);
+        while (next_tile(p, 1, g, sm, tile, start, n)) bucket_sort_tile<MED_CAP, SORT_CTA>(p, g, sm, s_keys, s_fine, tile, start, n);
         __syncthreads();
-        for (uint32_t b = tid; b < n; b += NT) {
-            const uint32_t o = s_fine[b], c = s_fine[b + 1] - o;
-            if (c < 2u) continue;
-            if (c > MAX_FINE) { s_flag = 1u; atomicMax(&p.hdr->pad0[1], c); continue; }
-            for (uint32_t a = 1; a < c; a++) {
-                const uint64_t v = s_out[o + a];
-                uint32_t j = a;
-                while (j > 0 && s_out[o + j - 1] > v) { s_out[o + j] = s_out[o + j - 1]; j--; }
-                s_out[o + j] = v;
-            }
-        }
-        __syncthreads();
-        if (s_flag) {
-            if (tid == 0) atomicAdd(&p.hdr->pad0[0], 1u);  // statistics: tiles that took the network
-#pragma unroll
-            for (int e = 0; e < KPT; e++)
-                if (tid + e * NT < n) s_out[tid + e * NT] = k[e];
-            __syncthreads();
-            bitonic_sort(s_out, n, tid, NT);
-        }
-        write_sorted<(NT >= 1024 ? 2 : 4)>(p, tile, start, s_out, n, tid, NT);
+    }
+    {
+        const int grp = threadIdx.x / SMALL_NT;
+        Grp g{threadIdx.x % SMALL_NT, SMALL_NT, 1 + grp};
+        GrpSmem* sm = &s_grp[grp];
+        uint64_t* s_out = reinterpret_cast<uint64_t*>(s_raw + (size_t)grp * SMALL_STRIDE);
+        uint32_t* s_fine = reinterpret_cast<uint32_t*>(s_raw + (size_t)grp * SMALL_STRIDE + SMALL_CAP * 8);
+        while (next_tile(p, 2, g, sm, tile, start, n)) bucket_sort_tile<SMALL_CAP, SMALL_NT>(p, g, sm, s_out, s_fine, tile, start, n);
     }
 }
 
-constexpr int SMALL_THREADS = 256, MED_THREADS = 1024;
-constexpr int SMALL_SMEM = SMALL_CAP * 8 + (SMALL_CAP + SMALL_CAP / SMALL_THREADS + 1) * 4;
-constexpr int MED_SMEM = MED_CAP * 8 + (MED_CAP + MED_CAP / MED_THREADS + 1) * 4;
-static int g_num_sms = 0, g_small_per_sm = 4, g_med_per_sm = 1;
+static int g_num_sms = 0;
 
 int tile_sort_setup()
 {
@@ -596,29 +612,15 @@ int tile_sort_setup()
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_CAP * sizeof(uint64_t)));
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_tile_sort_bucket<MED_CAP, MED_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MED_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_tile_sort_bucket<SMALL_CAP, SMALL_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_small_per_sm, k_tile_sort_bucket<SMALL_CAP, SMALL_THREADS>, SMALL_THREADS, SMALL_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_med_per_sm, k_tile_sort_bucket<MED_CAP, MED_THREADS>, MED_THREADS, MED_SMEM);
-    g_small_per_sm = g_small_per_sm > 0 ? g_small_per_sm : 1;
-    g_med_per_sm = g_med_per_sm > 0 ? g_med_per_sm : 1;
-    return (int)e;
+    return (int)cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_DYN_SMEM);
 }
 
 void launch_tile_scan(const BinParams& p, cudaStream_t s) { k_tile_scan<<<1, SCAN_THREADS, 0, s>>>(p); }
 void launch_emit(const BinParams& p, cudaStream_t s) { k_emit<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
 void launch_tile_sort(const BinParams& p, cudaStream_t s)
 {
-    // persistent CTAs, one grid per list-length class, sized to the machine (148 SMs on B200), longest class first
-    const int sms = g_num_sms > 0 ? g_num_sms : 148;
-    k_tile_sort<<<min(p.num_tiles, sms), SORT_THREADS, SORT_CAP * sizeof(uint64_t), s>>>(p);
-    k_tile_sort_bucket<MED_CAP, MED_THREADS><<<min(p.num_tiles, g_med_per_sm * sms), MED_THREADS, MED_SMEM, s>>>(p, 1);
-    k_tile_sort_bucket<SMALL_CAP, SMALL_THREADS><<<min(p.num_tiles, g_small_per_sm * sms), SMALL_THREADS, SMALL_SMEM, s>>>(p, 2);
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;  // persistent: one CTA per SM (148 on B200)
+    k_tile_sort<<<min(p.num_tiles, sms), SORT_CTA, SORT_DYN_SMEM, s>>>(p);
 }
 
 }  // namespace gstar
