@@ -45,67 +45,99 @@ __device__ __forceinline__ uint32_t warp_aggregated_add(uint32_t* counters, uint
 }
 
 // ---- K2: exclusive scan over the per-tile histogram; one CTA --------------------------------------
+// Thread t owns tiles [t*per, (t+1)*per).  Warp-shuffle scans (two barriers, not a 20-barrier Hillis-Steele), and the
+// size-class histogram / ranking for the longest-first order use ONE shared-memory atomic per distinct class per warp
+// (__match_any_sync): the non-empty tiles of a view fall into a handful of classes, plain atomics serialise on them.
+__device__ __forceinline__ uint32_t class_rank_add(uint32_t* hist, int bucket, bool active)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, active ? bucket : -1);
+    uint32_t base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (active && (int)lane == leader) base = atomicAdd(hist + bucket, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
 {
-    __shared__ uint32_t s_part[SCAN_THREADS];
-    __shared__ uint32_t s_max, s_cls[3];
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_max, s_total, s_cls[3];
     __shared__ uint32_t s_hist[LPT_BUCKETS];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = p.num_tiles;
     const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
     const int t0 = tid * per, t1 = min(T, t0 + per);
     if (tid == 0) s_max = 0;
     for (int b = tid; b < LPT_BUCKETS; b += SCAN_THREADS) s_hist[b] = 0;
     __syncthreads();
-    uint32_t sum = 0, mx = 0, n_empty = 0;
-    for (int t = t0; t < t1; t++) {
-        const uint32_t c = p.tile_count[t];
-        sum += c;
-        mx = max(mx, c);
-        if (c == 0) n_empty++;  // most tiles are empty: count them locally instead of hammering one shared counter
-        else atomicAdd(&s_hist[lpt_bucket(c)], 1u);
+    uint32_t sum = 0, mx = 0;
+    for (int k0 = 0; k0 < per; k0 += 8) {  // uniform trip count (warp-wide matches); eight independent loads in flight
+        uint32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = (k0 + u < per && t0 + k0 + u < t1) ? p.tile_count[t0 + k0 + u] : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (k0 + u >= per) break;
+            sum += c[u];
+            mx = max(mx, c[u]);
+            class_rank_add(s_hist, lpt_bucket(c[u]), t0 + k0 + u < t1);
+        }
     }
-    if (n_empty) atomicAdd(&s_hist[0], n_empty);
-    s_part[tid] = sum;
+    // exclusive scan of the per-thread sums
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) atomicMax(&s_max, mx);
     __syncthreads();
-    // Hillis-Steele inclusive scan of 1024 partials
-    for (int off = 1; off < SCAN_THREADS; off <<= 1) {
-        uint32_t v = 0;
-        if (tid >= off) v = s_part[tid - off];
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
-    }
-    uint32_t run = s_part[tid] - sum;  // exclusive prefix of this thread's chunk
-    atomicMax(&s_max, mx);
-    for (int t = t0; t < t1; t++) {
-        const uint32_t c = p.tile_count[t];
-        p.tile_cursor[t] = run;
-        // identifyTileRanges leaves untouched tiles at the memset value (0,0): rasterizer_impl.cu:310
-        p.ranges[2 * t] = c ? run : 0u;
-        p.ranges[2 * t + 1] = c ? run + c : 0u;
-        run += c;
-    }
-    __syncthreads();
-    // longest-processing-time-first order of the tiles for the blend kernels: counting sort on the size class,
-    // largest class first; empty tiles last (the forward still has to paint them with the background)
-    if (tid == 0) {
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];  // SCAN_THREADS / 32 == 32 warps
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_total = wi;
+        // longest-processing-time-first order of the tiles: counting sort on the size class, largest class first; empty
+        // tiles (class 0) last -- the forward still has to paint them with the background
         uint32_t acc = 0;
-        for (int b = LPT_BUCKETS - 1; b >= 0; b--) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }
-        // s_hist[b] = tiles in buckets > b = first position of bucket b: the class boundaries of the sort kernels
-        s_cls[0] = s_hist[LPT_MED_END - 1]; s_cls[1] = s_hist[LPT_SMALL_END - 1]; s_cls[2] = s_hist[0];
+        if (lane == 0) {
+            for (int b = LPT_BUCKETS - 1; b >= 0; b--) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }
+            // s_hist[b] = tiles in classes > b = first position of class b: the list-length classes of the sort kernel
+            s_cls[0] = s_hist[LPT_MED_END - 1]; s_cls[1] = s_hist[LPT_SMALL_END - 1]; s_cls[2] = s_hist[0];
+        }
     }
     __syncthreads();
-    {
-        uint32_t empty_base = n_empty ? atomicAdd(&s_hist[0], n_empty) : 0u;
-        for (int t = t0; t < t1; t++) {
-            const uint32_t c = p.tile_count[t];
-            const uint32_t pos = c ? atomicAdd(&s_hist[lpt_bucket(c)], 1u) : empty_base++;
-            p.tile_order[pos] = (uint32_t)t;
+    uint32_t run = s_warp[warp] + incl - sum;  // exclusive prefix of this thread's chunk
+    for (int k0 = 0; k0 < per; k0 += 8) {
+        uint32_t cc[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) cc[u] = (k0 + u < per && t0 + k0 + u < t1) ? p.tile_count[t0 + k0 + u] : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (k0 + u >= per) break;
+            const int t = t0 + k0 + u;
+            const bool act = t < t1;
+            const uint32_t c = cc[u];
+            const uint32_t pos = class_rank_add(s_hist, lpt_bucket(c), act);
+            if (act) {
+                p.tile_cursor[t] = run;
+                // identifyTileRanges leaves untouched tiles at the memset value (0,0): rasterizer_impl.cu:310
+                *reinterpret_cast<uint2*>(p.ranges + 2 * t) = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+                p.tile_order[pos] = (uint32_t)t;
+                run += c;
+            }
         }
     }
     if (tid == 0) {
-        const uint32_t total = s_part[SCAN_THREADS - 1];
+        const uint32_t total = s_total;
         const uint32_t ovf = total > p.capacity ? 1u : 0u;
         p.hdr->num_rendered = total;
         p.hdr->capacity = p.capacity;
