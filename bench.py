@@ -50,8 +50,8 @@ P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
 VIEWS_PER_GPU = 20  # BASELINE.json config #3: 160 views / 8 GPUs per step
 CAM_POOL = 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-# (profiles/r1i_ncu_full_summary.txt); None where no capture is committed
-NCU_TRAFFIC = {"blend_fwd": 383398400, "blend_bwd": 561370112, "preprocess_bwd": 574310144, "preprocess_fwd": 257299200}
+# (profiles/r1k_ncu_full_summary.txt); None where no capture is committed
+NCU_TRAFFIC = {"blend_fwd": 388571648, "blend_bwd": 561560832, "preprocess_bwd": 573778688, "preprocess_fwd": 255691008, "tile_sort": 130042112}
 
 
 def measured_peak():
