@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgstar_raster.so")
+LIB_PATH = os.environ.get("GSTAR_LIB_PATH") or os.path.join(_HERE, "lib", "libgstar_raster.so")  # override: kernel-variant experiments
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -22,7 +22,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 EXPORTED = [
     "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
     "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
-    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state", "gstar_debug_header",
+    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state", "gstar_debug_header", "gstar_knn3_mean_dist2",
 ]
 STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
@@ -81,6 +81,8 @@ def lib():
         L.gstar_binning_views.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.gstar_profile_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.gstar_set_hit_log.argtypes = [C.c_int]
+        L.gstar_knn3_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_void_p, C.c_void_p]
         L.gstar_debug_header.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.gstar_hit_log_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         _lib = L

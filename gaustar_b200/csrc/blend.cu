@@ -148,8 +148,15 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
 // Per batch: every lane turns ONE record's alpha-bounds into a 32-bit mask of the block's pixels, a 32x32 bit transpose
 // hands every pixel the records that can touch it (one register word per 32 records = the pixel's hit queue), and the
 // set bits are walked four at a time in list order with the reference's arithmetic.
-constexpr int FWD_SB = 64;    // records per stage (two rounds of 32)
-constexpr int FWD_NST = 2;    // stages per warp
+#ifndef GSTAR_FWD_SB
+#define GSTAR_FWD_SB 64
+#define GSTAR_FWD_NST 2
+#define GSTAR_FWD_CTAS 4
+#endif
+constexpr int FWD_SB = GSTAR_FWD_SB;   // records per stage
+constexpr int FWD_NW = FWD_SB / 32;
+constexpr int FWD_NST = GSTAR_FWD_NST;    // stages per warp
+constexpr int FWD_CTAS_PER_SM = GSTAR_FWD_CTAS;
 constexpr int FWD_THREADS = NCONS * 32;
 constexpr int FWD_DYN_SMEM = NCONS * FWD_NST * FWD_SB * RS;  // 48 KB
 
@@ -160,7 +167,7 @@ __device__ __forceinline__ void fwd_fetch(unsigned char* stage, uint64_t* bar, c
     bulk_g2s(stage, tile_packed + (size_t)b * FWD_SB * RS, bytes, bar);
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 4) k_blend_fwd(BlendParams p)
+__global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(BlendParams p)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) uint64_t s_full[NCONS][FWD_NST];
@@ -211,31 +218,47 @@ __global__ void __launch_bounds__(FWD_THREADS, 4) k_blend_fwd(BlendParams p)
             const unsigned live = __ballot_sync(FULL, !done);
             if (live == 0) break;  // every pixel of the block is finished: this warp is done with the tile
             const int cnt = min(FWD_SB, n - b * FWD_SB);
-            unsigned w0 = 0u, w1 = 0u;  // bit k of w0 / w1: record k / 32 + k of the batch may touch my pixel
-            {
-                const unsigned pm = (lane < cnt) ? (block_pixel_mask(buf + lane * RS, g) & live) : 0u;
-                if (__any_sync(FULL, pm != 0u)) w0 = transpose32(pm, lane);
+            // per-pixel hit queue of the batch: bit k of word r = record 32 r + k may touch my pixel
+            unsigned w[FWD_NW];
+            int left = 0;
+#pragma unroll
+            for (int r = 0; r < FWD_NW; r++) {
+                w[r] = 0u;
+                if (r * 32 < cnt) {
+                    const unsigned pm = (r * 32 + lane < cnt) ? (block_pixel_mask(buf + (r * 32 + lane) * RS, g) & live) : 0u;
+                    if (__any_sync(FULL, pm != 0u)) w[r] = transpose32(pm, lane);
+                }
+                left += __popc(w[r]);
             }
-            if (cnt > 32) {
-                const unsigned pm = (32 + lane < cnt) ? (block_pixel_mask(buf + (32 + lane) * RS, g) & live) : 0u;
-                if (__any_sync(FULL, pm != 0u)) w1 = transpose32(pm, lane);
-            }
+            unsigned cw = w[0];  // word being walked, and its index
+            int cr = 0;
 #pragma unroll 1
-            while (__any_sync(FULL, (w0 | w1) != 0u)) {
+            while (__any_sync(FULL, left > 0)) {
                 int sl[4];
                 bool ok[4];
-                float al[4], cr[4], cg[4], cbv[4];
+                float al[4], cr_[4], cg[4], cbv[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    bool have = true;
-                    if (w0) { sl[u] = __ffs(w0) - 1; w0 &= w0 - 1u; }
-                    else if (w1) { sl[u] = 32 + __ffs(w1) - 1; w1 &= w1 - 1u; }
-                    else { sl[u] = 0; have = false; }
+                    const bool have = left > 0;
+                    if (have) {
+                        while (cw == 0u) {  // next non-empty word (left > 0 guarantees there is one)
+                            cr++;
+                            unsigned nx = 0u;
+#pragma unroll
+                            for (int r = 1; r < FWD_NW; r++) nx = (cr == r) ? w[r] : nx;
+                            cw = nx;
+                        }
+                        sl[u] = cr * 32 + __ffs(cw) - 1;
+                        cw &= cw - 1u;
+                        left--;
+                    } else {
+                        sl[u] = 0;
+                    }
                     const unsigned char* rp = buf + sl[u] * RS;
                     const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
                     const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
                     cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
-                    cr[u] = q1.z; cg[u] = q1.w;
+                    cr_[u] = q1.z; cg[u] = q1.w;
                     float dx, dy;
                     const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
                     al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
@@ -248,7 +271,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 4) k_blend_fwd(BlendParams p)
                         if (test_T < 0.0001f) {
                             done = true;
                         } else {
-                            C0 = __fmaf_rn(T, __fmul_rn(al[u], cr[u]), C0);
+                            C0 = __fmaf_rn(T, __fmul_rn(al[u], cr_[u]), C0);
                             C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
                             C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
                             if (log_on) {
@@ -263,7 +286,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 4) k_blend_fwd(BlendParams p)
                         }
                     }
                 }
-                if (done) { w0 = 0u; w1 = 0u; }  // a finished pixel drops the rest of its queue
+                if (done) left = 0;  // a finished pixel drops the rest of its queue
             }
             __syncwarp();
             if (lane == 0 && b + FWD_NST < nb) {

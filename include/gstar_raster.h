@@ -169,6 +169,13 @@ GSTAR_API int gstar_set_hit_log(int mode);
 GSTAR_API int gstar_debug_header(char* image_buffer, uint32_t* words24);
 GSTAR_API int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, uint64_t* slots_capacity, int* in_use);
 
+/* ---- co-requisite of the drop-in: simple_knn._C.distCUDA2 (SimpleKNN::knn, simple-knn/simple_knn.cu:188-220) ----
+ * out[i] = mean squared distance of point i to its three nearest OTHER points.  The caller bins the points into a
+ * uniform grid (nx*ny*nz cells of edge `cell` starting at (ox,oy,oz)): `order` lists the point indices cell by cell,
+ * cell_start[c] .. cell_start[c+1] is cell c's range in it (cell index = (z*ny + y)*nx + x).  See simple_knn/_C.py. */
+GSTAR_API int gstar_knn3_mean_dist2(int P, const float* points, const int* order, const int* cell_start, int nx, int ny, int nz,
+                                    float ox, float oy, float oz, float cell, float* out, void* stream);
+
 /* ---- measurement hook: record `start`/`stop` (cudaEvent_t) around kernel stage `stage` of every
  * subsequent call on this thread (stage < 0 disables).  Stages: see gstar_stage_name(). ---- */
 GSTAR_API int gstar_profile_stage(int stage, void* start_event, void* stop_event);
