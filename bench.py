@@ -149,7 +149,7 @@ class OursCABI:
                   tan_fovx=cam["tanfovx"], tan_fovy=cam["tanfovy"], shs=params["shs"], scales=params["scales"], rotations=params["rotations"],
                   sh_degree=SH_DEG)
         f = self.capi.forward(opacities=params["opacities"], W=W, H=H, **kw)
-        g = self.capi.backward(f, grad_fn(f["out_color"]), accumulate_into=flat.views if flat is not None else None, **kw)
+        g = self.capi.backward(f, grad_fn(f["out_color"]), accumulate_into=flat.views if flat is not None else None, lean=True, **kw)
         return f["num_rendered"], int(0), g
 
 
@@ -376,8 +376,7 @@ def run_gpu(args, impl_name, rank, world, local):
             s["vm"].copy_(cam_host[v]["viewmatrix"], non_blocking=True)
             s["pm"].copy_(cam_host[v]["projmatrix"], non_blocking=True)
             s["cp"].copy_(cam_host[v]["campos"], non_blocking=True)
-            s["tgt_f"].copy_(s["tgt"].permute(2, 0, 1))
-            s["tgt_f"].mul_(1.0 / 255.0)
+            torch.mul(s["tgt"].permute(2, 0, 1), 1.0 / 255.0, out=s["tgt_f"])  # uint8 HWC -> float CHW in one kernel
             s["ev"].record(copy_stream)
 
     loss_acc = [torch.zeros((), device=device) for _ in e2e_streams]

@@ -149,8 +149,10 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,
-             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None):
+             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None, lean=False):
     """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts).
+    lean: do not materialise the intermediates dL_dconic and -- for inputs that were not given -- dL_dcolors / dL_dcov3D
+    (NULL in the C ABI; the dict then holds empty tensors for them).
     accumulate_into: optional dict with dL_dmeans3D/dL_dscales/dL_drotations/dL_dopacity/dL_dsh tensors; the
     parameter gradients are then ADDED to them inside the kernel (accumulate_param_grads=1)."""
     L = lib()
@@ -163,6 +165,12 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     g = dict(dL_dmeans2D=e(P, 3), dL_dconic=e(P, 4), dL_dopacity=e(P, 1), dL_dcolors=e(P, 3), dL_dmeans3D=e(P, 3), dL_dcov3D=e(P, 6),
              dL_dsh=e(P, M, 3), dL_dscales=e(P, 3), dL_drotations=e(P, 4))
+    if lean:
+        g["dL_dconic"] = e(0, 4)
+        if col is None:
+            g["dL_dcolors"] = e(0, 3)
+        if cov is None:
+            g["dL_dcov3D"] = e(0, 6)
     if accumulate_into is not None:
         for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh"):
             t = accumulate_into[k]

@@ -420,8 +420,9 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
     pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = (a->M > 0) ? a->dL_dsh : nullptr;
     pb.dL_dscale = a->dL_dscale; pb.dL_drot = a->dL_drot;
     pb.accumulate = a->accumulate_param_grads;
-    if (!pb.dL_dmean2D || !pb.dL_dopacity || !pb.dL_dcolor || !pb.dL_dmean3D || !pb.dL_dcov3D)
-        return fail(GSTAR_ERR_INVALID, "missing gradient output");
+    if (!pb.dL_dmean2D || !pb.dL_dopacity || !pb.dL_dmean3D) return fail(GSTAR_ERR_INVALID, "missing gradient output");
+    if (a->colors_precomp && !pb.dL_dcolor) return fail(GSTAR_ERR_INVALID, "missing dL_dcolor (colors_precomp was given)");
+    if (a->cov3D_precomp && !pb.dL_dcov3D) return fail(GSTAR_ERR_INVALID, "missing dL_dcov3D (cov3D_precomp was given)");
     if (a->shs && a->M > 0 && !a->dL_dsh) return fail(GSTAR_ERR_INVALID, "missing dL_dsh");
     {
         StageScope sc(GSTAR_STAGE_PREPROCESS_BWD, stream);

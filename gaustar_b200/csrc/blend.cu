@@ -4,20 +4,17 @@
 // (DGR/cuda_rasterizer/backward.cu:399-557).  Same per-pixel arithmetic and thresholds
 // (power>0 skip, alpha=min(0.99,o*exp(power)), alpha<1/255 skip, T<1e-4 stop), re-mapped for B200:
 //
-//  * one CTA per 16x16 tile: 8 consumer warps, each owning an 8x4 pixel block, plus one producer warp;
-//  * the tile's depth-sorted Gaussian list is streamed through a 3-stage shared-memory ring in batches of
-//    256 48-byte records, each fetched by its own TMA bulk copy (cp.async.bulk -> UBLKCP) issued by the
-//    producer warp and completing on the stage's `full` mbarrier; consumers release a stage through its
-//    `empty` mbarrier.  There is no __syncthreads in the loop: warps whose pixels need few records (or are
-//    done) run ahead instead of waiting for the slowest warp of the tile at every batch;
-//  * every record carries exact-conservative pixel bounds of {alpha >= 1/255}; a warp first tests 32
-//    records against its 8x4 block (one record per lane + ballot) and only walks the survivors.
-//    Surface Gaussians cover ~5x5 pixels, so ~3/4 of the (record, warp) pairs of a tile are skipped
-//    without evaluating a single exponential, and the result is bit-identical because a culled pair
-//    can never pass the reference's own alpha test;
-//  * backward: the nine per-(Gaussian,pixel) atomics of the reference become one multi-value
-//    butterfly warp reduction and one vector of 9 RED ops per (Gaussian, warp) into a packed
-//    [P][12] accumulator; tiles start their back-to-front walk at the tile's max n_contrib.
+//  * forward: one CTA per 16x16 tile, eight warps each owning an 8x4 pixel block and streaming the tile's packed
+//    records through its own shared-memory ring (TMA bulk copies, cp.async.bulk -> UBLKCP, completing on mbarriers);
+//  * every record carries exact-conservative pixel bounds of {alpha >= 1/255}; per round every lane turns one record's
+//    bounds into a mask of the block's pixels and a 32x32 bit transpose gives every pixel its own hit queue, so no lane
+//    evaluates a record whose bounds exclude its pixel -- bit-identical, because such a pair can never pass the
+//    reference's own alpha test;
+//  * the forward leaves (T_i, C_i) of every blended pair in a hit log; the backward (k_blend_bwd_gather) is then
+//    instance-parallel with no pixel-serial walk, no cross-lane reduction and three reductions per instance;
+//  * without a hit log (switched off, or too small for the view) the backward walks the lists back to front
+//    (k_blend_bwd): warp-specialised producer/consumer ring, ballot culling against the live pixels' bounding box,
+//    one multi-value butterfly warp reduction and 9 RED ops per (Gaussian, warp) instead of 9 atomics per pair.
 #include "gstar_common.cuh"
 #include "gstar_kernels.h"
 
@@ -28,7 +25,6 @@ constexpr int RS = GSTAR_REC_SMEM;
 constexpr int NSTAGE = 3;                 // ring depth (3 x 12 KB stays within static shared memory)
 constexpr int NCONS = 8;                  // consumer warps (8x4 pixel blocks of a 16x16 tile)
 constexpr int BLEND_THREADS = (NCONS + 1) * 32;  // + one producer warp
-constexpr int QCAP = 64;                   // per-pixel hit-queue capacity (entries) between two flushes
 
 struct WarpGeom {
     int rx0, ry0, rx1, ry1, px, py;
@@ -48,14 +44,6 @@ __device__ __forceinline__ WarpGeom warp_geom(int tile, int gx, int W, int H)
     g.py = g.ry0 + (lane >> 3);
     g.inside = g.px < W && g.py < H;
     return g;
-}
-
-__device__ __forceinline__ bool bbox_overlaps(const unsigned char* rec, const WarpGeom& g)
-{
-    const uint2 bb = *reinterpret_cast<const uint2*>(rec + 32);
-    const int bx0 = (int)(short)(bb.x & 0xffffu), bx1 = (int)(short)(bb.x >> 16);
-    const int by0 = (int)(short)(bb.y & 0xffffu), by1 = (int)(short)(bb.y >> 16);
-    return bx0 <= g.rx1 && bx1 >= g.rx0 && by0 <= g.ry1 && by1 >= g.ry0;
 }
 
 // Bounding box (absolute pixel coordinates) of the lanes set in `live` (lane = 8*row + col of the warp's 8x4 block).

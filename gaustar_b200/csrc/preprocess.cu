@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
     // blend-stage gradients in the reference's layouts (also outputs of the op / parity intermediates)
     p.dL_dmean2D[3 * i] = acc[0]; p.dL_dmean2D[3 * i + 1] = acc[1]; p.dL_dmean2D[3 * i + 2] = 0.f;
     if (p.dL_dconic) { p.dL_dconic[4 * i] = acc[2]; p.dL_dconic[4 * i + 1] = acc[3]; p.dL_dconic[4 * i + 2] = 0.f; p.dL_dconic[4 * i + 3] = acc[4]; }
-    p.dL_dcolor[3 * i] = acc[5]; p.dL_dcolor[3 * i + 1] = acc[6]; p.dL_dcolor[3 * i + 2] = acc[7];
+    if (p.dL_dcolor) { p.dL_dcolor[3 * i] = acc[5]; p.dL_dcolor[3 * i + 1] = acc[6]; p.dL_dcolor[3 * i + 2] = acc[7]; }
     if (p.accumulate) { if (vis) p.dL_dopacity[i] += acc[8]; } else p.dL_dopacity[i] = acc[8];
     float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     if (vis) {
@@ -761,7 +761,8 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
         }
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
+    for (int k = 0; k < 6; k++)
+        if (p.dL_dcov3D) p.dL_dcov3D[6 * i + k] = dcov[k];
     }  // valid
     if (sh_staged) {
         const unsigned rows = p.accumulate ? __ballot_sync(0xffffffffu, valid && vis) : 0xffffffffu;

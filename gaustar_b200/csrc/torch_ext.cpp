@@ -167,10 +167,12 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
     // (the reference zero-fills nine tensors per call, rasterize_points.cu:150-158)
     torch::Tensor dL_dmeans3D = fused ? fused->means3D : torch::empty({P, 3}, opts);
     torch::Tensor dL_dmeans2D = torch::empty({P, 3}, opts);
-    torch::Tensor dL_dcolors = torch::empty({P, 3}, opts);
-    torch::Tensor dL_dconic = torch::empty({P, 2, 2}, opts);
+    // gradients of inputs that were not given are intermediates of the fused kernel: they are not materialised
+    // (the reference returns them too, rasterize_points.cu:190-195, but autograd drops gradients of absent inputs)
+    const bool has_colors = colors.numel() != 0, has_cov = cov3D_precomp.numel() != 0;
+    torch::Tensor dL_dcolors = torch::empty({has_colors ? P : 0, 3}, opts);
     torch::Tensor dL_dopacity = fused ? fused->opacity : torch::empty({P, 1}, opts);
-    torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
+    torch::Tensor dL_dcov3D = torch::empty({has_cov ? P : 0, 6}, opts);
     torch::Tensor dL_dsh = (fused && M) ? fused->sh : torch::empty({P, M, 3}, opts);
     torch::Tensor dL_dscales = fused ? fused->scales : torch::empty({P, 3}, opts);
     torch::Tensor dL_drotations = fused ? fused->rotations : torch::empty({P, 4}, opts);
@@ -192,9 +194,9 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
         a.binning_buffer = bb.numel() ? reinterpret_cast<char*>(bb.data_ptr()) : nullptr;
         a.image_buffer = reinterpret_cast<char*>(ib.data_ptr());
         a.dL_dpix = fptr(dpix);
-        a.dL_dmean2D = dL_dmeans2D.data_ptr<float>(); a.dL_dconic = dL_dconic.data_ptr<float>();
-        a.dL_dopacity = dL_dopacity.data_ptr<float>(); a.dL_dcolor = dL_dcolors.data_ptr<float>();
-        a.dL_dmean3D = dL_dmeans3D.data_ptr<float>(); a.dL_dcov3D = dL_dcov3D.data_ptr<float>();
+        a.dL_dmean2D = dL_dmeans2D.data_ptr<float>(); a.dL_dconic = nullptr;
+        a.dL_dopacity = dL_dopacity.data_ptr<float>(); a.dL_dcolor = has_colors ? dL_dcolors.data_ptr<float>() : nullptr;
+        a.dL_dmean3D = dL_dmeans3D.data_ptr<float>(); a.dL_dcov3D = has_cov ? dL_dcov3D.data_ptr<float>() : nullptr;
         a.dL_dsh = M ? dL_dsh.data_ptr<float>() : nullptr;
         a.dL_dscale = dL_dscales.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
         a.blend_grad_scratch = scratch.data_ptr<float>();

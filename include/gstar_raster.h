@@ -106,11 +106,11 @@ typedef struct gstar_bwd_args {
     /* Outputs.  Unlike the reference (which accumulates with atomics into caller-zeroed arrays,
      * rasterize_points.cu:150-158) every output below is FULLY OVERWRITTEN; no zero-fill needed. */
     float* dL_dmean2D;           /* [P,3] (x,y in NDC-scaled pixels, z = 0) backward.cu:545-546 */
-    float* dL_dconic;            /* [P,4] (.x,.y,.w used)                    backward.cu:549-551 */
+    float* dL_dconic;            /* [P,4] (.x,.y,.w used)                    backward.cu:549-551; may be NULL (intermediate) */
     float* dL_dopacity;          /* [P]                                      backward.cu:554 */
-    float* dL_dcolor;            /* [P,3]                                    backward.cu:523 */
+    float* dL_dcolor;            /* [P,3]                                    backward.cu:523; may be NULL unless colors_precomp */
     float* dL_dmean3D;           /* [P,3] */
-    float* dL_dcov3D;            /* [P,6] */
+    float* dL_dcov3D;            /* [P,6]; may be NULL unless cov3D_precomp (an intermediate otherwise) */
     float* dL_dsh;               /* [P,M,3] (NULL if M == 0) */
     float* dL_dscale;            /* [P,3] */
     float* dL_drot;              /* [P,4] */
