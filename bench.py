@@ -471,6 +471,7 @@ def main():
     ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (CUDA streams) in our arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     rank, world, local = gdist.init_from_env()
     have_gpu = torch.cuda.is_available()
     config = {"workload": f"surface-1M-1080p-sh3 ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
