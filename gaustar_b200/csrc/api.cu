@@ -113,7 +113,7 @@ int get_ctx(DevCtx** out)
 
 // ---- private layouts of the three opaque buffers ----
 struct ImgLayout {
-    size_t hdr, final_T, n_contrib, pixstate, ranges, tile_count, tile_cursor, big_tiles, tile_order, total;
+    size_t hdr, final_T, n_contrib, pixstate, ranges, tile_count, tile_cursor, tile_order, total;
 };
 ImgLayout img_layout(int W, int H)
 {
@@ -128,7 +128,6 @@ ImgLayout img_layout(int W, int H)
     L.ranges = o; o = align_up(o + T * 8, 128);
     L.tile_count = o; o = align_up(o + T * 4, 128);
     L.tile_cursor = o; o = align_up(o + T * 4, 128);
-    L.big_tiles = o; o = align_up(o + T * 4, 128);
     L.tile_order = o; o = align_up(o + T * 4, 128);
     L.total = o;
     return L;
@@ -250,7 +249,6 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bp.recs = (const GRec*)geom; bp.hdr = hdr; bp.tile_count = tile_count;
     bp.tile_cursor = (uint32_t*)(img + IL.tile_cursor);
     bp.ranges = (uint32_t*)(img + IL.ranges);
-    bp.big_tiles = (uint32_t*)(img + IL.big_tiles);
     bp.tile_order = (uint32_t*)(img + IL.tile_order);
     bp.host_counts = ctx->host_counts_dev;
 

@@ -66,32 +66,39 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
     __shared__ uint32_t s_hist[LPT_BUCKETS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = p.num_tiles;
+    // warp w owns the contiguous tiles [w*per*32, (w+1)*per*32); in row k lane l handles tile w*per*32 + 32k + l, so
+    // that every load and store of a row is one coalesced 128-byte (256-byte for ranges) access -- a thread-contiguous
+    // split made every warp access touch 32 sectors and the kernel LSU-bound on its single SM
     const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int t0 = tid * per, t1 = min(T, t0 + per);
+    const int w0 = warp * per * 32;
     if (tid == 0) s_max = 0;
     for (int b = tid; b < LPT_BUCKETS; b += SCAN_THREADS) s_hist[b] = 0;
     __syncthreads();
-    uint32_t sum = 0, mx = 0;
+    uint32_t sum = 0, mx = 0, n_empty = 0;
     for (int k0 = 0; k0 < per; k0 += 8) {  // uniform trip count (warp-wide matches); eight independent loads in flight
         uint32_t c[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) c[u] = (k0 + u < per && t0 + k0 + u < t1) ? p.tile_count[t0 + k0 + u] : 0u;
+        for (int u = 0; u < 8; u++) {
+            const int t = w0 + (k0 + u) * 32 + lane;
+            c[u] = (k0 + u < per && t < T) ? p.tile_count[t] : 0u;
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             if (k0 + u >= per) break;
+            const bool in = w0 + (k0 + u) * 32 + lane < T;
             sum += c[u];
             mx = max(mx, c[u]);
-            class_rank_add(s_hist, lpt_bucket(c[u]), t0 + k0 + u < t1);
+            // most tiles of a view are empty: counted per thread, one atomic per warp below
+            if (in && c[u] == 0u) n_empty++;
+            class_rank_add(s_hist, lpt_bucket(c[u]), in && c[u] != 0u);
         }
     }
-    // exclusive scan of the per-thread sums
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+    const uint32_t warp_empty = __reduce_add_sync(0xffffffffu, n_empty);
+    const uint32_t warp_sum = __reduce_add_sync(0xffffffffu, sum);
+    if (lane == 0) {
+        if (warp_empty) atomicAdd(&s_hist[0], warp_empty);
+        s_warp[warp] = warp_sum;
     }
-    if (lane == 31) s_warp[warp] = incl;
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) atomicMax(&s_max, mx);
     __syncthreads();
@@ -115,24 +122,49 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         }
     }
     __syncthreads();
-    uint32_t run = s_warp[warp] + incl - sum;  // exclusive prefix of this thread's chunk
+    uint32_t carry = s_warp[warp];  // exclusive prefix of this warp's tiles
+    uint32_t empty_pos;  // this thread's first position among the empty tiles (class 0, the tail of tile_order)
+    {
+        uint32_t ei = n_empty;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, ei, d);
+            if (lane >= d) ei += v;
+        }
+        uint32_t wbase = 0;
+        if (lane == 31 && ei) wbase = atomicAdd(&s_hist[0], ei);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        empty_pos = wbase + ei - n_empty;
+    }
     for (int k0 = 0; k0 < per; k0 += 8) {
         uint32_t cc[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) cc[u] = (k0 + u < per && t0 + k0 + u < t1) ? p.tile_count[t0 + k0 + u] : 0u;
+        for (int u = 0; u < 8; u++) {
+            const int t = w0 + (k0 + u) * 32 + lane;
+            cc[u] = (k0 + u < per && t < T) ? p.tile_count[t] : 0u;
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             if (k0 + u >= per) break;
-            const int t = t0 + k0 + u;
-            const bool act = t < t1;
+            const int t = w0 + (k0 + u) * 32 + lane;
+            const bool act = t < T;
             const uint32_t c = cc[u];
-            const uint32_t pos = class_rank_add(s_hist, lpt_bucket(c), act);
+            uint32_t incl = c;  // inclusive scan of the row
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t run = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t rk = class_rank_add(s_hist, lpt_bucket(c), act && c != 0u);
+            const uint32_t pos = c ? rk : empty_pos;
+            if (act && c == 0u) empty_pos++;
             if (act) {
                 p.tile_cursor[t] = run;
                 // identifyTileRanges leaves untouched tiles at the memset value (0,0): rasterizer_impl.cu:310
                 *reinterpret_cast<uint2*>(p.ranges + 2 * t) = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
                 p.tile_order[pos] = (uint32_t)t;
-                run += c;
             }
         }
     }

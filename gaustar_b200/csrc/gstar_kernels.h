@@ -62,7 +62,6 @@ struct BinParams {
     uint32_t* tile_count;  // [T] histogram from preprocess
     uint32_t* tile_cursor; // [T] running write position per tile
     uint32_t* ranges;      // [T][2]
-    uint32_t* big_tiles;   // [T] worklist of tiles too long for the small sort kernel
     uint32_t* tile_order;  // [T] all tiles, longest list first (work order of the blend kernels)
     uint2* entries;        // [capacity] (depth bits, idx), tile-segmented
     uint32_t* point_list;  // [capacity] sorted gaussian ids
