@@ -170,7 +170,8 @@ extern "C" {
 const char* gstar_last_error(void) { return t_err.c_str(); }
 int gstar_abi_version(void) { return GSTAR_ABI_VERSION; }
 
-size_t gstar_geom_bytes(int P) { return align_up((size_t)std::max(P, 0) * sizeof(GRec), 128) + 128; }
+static size_t geom_aux_offset(int P) { return align_up((size_t)std::max(P, 0) * sizeof(GRec), 128); }
+size_t gstar_geom_bytes(int P) { return geom_aux_offset(P) + align_up((size_t)std::max(P, 0) * sizeof(GAux), 128) + 128; }
 size_t gstar_image_bytes(int width, int height) { return img_layout(width, height).total + 128; }
 size_t gstar_binning_bytes(size_t cap) { return bin_layout(cap, 0).total + 128; }
 
@@ -237,7 +238,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     pp.focal_y = H / (2.0f * a->tan_fovy);  // rasterizer_impl.cu:222-223
     pp.focal_x = W / (2.0f * a->tan_fovx);
     pp.prefiltered = a->prefiltered;
-    pp.recs = (GRec*)geom; pp.radii = a->radii; pp.tile_count = tile_count;
+    pp.recs = (GRec*)geom; pp.aux = (GAux*)(geom + geom_aux_offset(a->P)); pp.radii = a->radii; pp.tile_count = tile_count;
     {
         StageScope sc(GSTAR_STAGE_PREPROCESS_FWD, stream);
         launch_preprocess_fwd(pp, stream);
@@ -246,7 +247,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
 
     BinParams bp;
     bp.P = a->P; bp.gx = gx; bp.gy = gy; bp.num_tiles = T; bp.W = W; bp.H = H;
-    bp.recs = (const GRec*)geom; bp.hdr = hdr; bp.tile_count = tile_count;
+    bp.recs = (const GRec*)geom; bp.aux = (const GAux*)(geom + geom_aux_offset(a->P)); bp.hdr = hdr; bp.tile_count = tile_count;
     bp.tile_cursor = (uint32_t*)(img + IL.tile_cursor);
     bp.ranges = (uint32_t*)(img + IL.ranges);
     bp.tile_order = (uint32_t*)(img + IL.tile_order);
@@ -413,7 +414,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
     pb.campos = a->campos; pb.tan_fovx = a->tan_fovx; pb.tan_fovy = a->tan_fovy;
     pb.focal_y = H / (2.0f * a->tan_fovy);
     pb.focal_x = W / (2.0f * a->tan_fovx);
-    pb.radii = a->radii; pb.recs = (const GRec*)geom; pb.gacc = a->blend_grad_scratch;
+    pb.radii = a->radii; pb.recs = (const GRec*)geom; pb.aux = (const GAux*)(geom + geom_aux_offset(a->P)); pb.gacc = a->blend_grad_scratch;
     pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;
     pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = (a->M > 0) ? a->dL_dsh : nullptr;
     pb.dL_dscale = a->dL_dscale; pb.dL_drot = a->dL_drot;
@@ -446,7 +447,8 @@ int gstar_geom_unpack(const char* geom_buffer, int P, float* depths, float* mean
 {
     if (P <= 0) return 0;
     if (!geom_buffer) return fail(GSTAR_ERR_INVALID, "null geometry buffer");
-    gstar::launch_geom_unpack((const GRec*)aligned128((char*)geom_buffer), P, depths, means2D, conic_opacity, rgb, tiles_touched, clamped,
+    const char* gb = aligned128((char*)geom_buffer);
+    gstar::launch_geom_unpack((const GRec*)gb, (const GAux*)(gb + geom_aux_offset(P)), P, depths, means2D, conic_opacity, rgb, tiles_touched, clamped,
                               (cudaStream_t)stream);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));

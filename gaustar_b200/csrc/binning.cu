@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256) k_emit(BinParams p)
     bool vis = false;
     uint32_t minx = 0, miny = 0, w = 0, h = 0, dbits = 0;
     if (idx < p.P) {
-        // last 16 bytes of the record: depth, rect_min, rect_max, radius
-        const uint4 q = *(reinterpret_cast<const uint4*>(p.recs + idx) + 3);
+        // depth, rect_min, rect_max, radius
+        const uint4 q = *reinterpret_cast<const uint4*>(p.aux + idx);
         vis = (int)q.w > 0;
         dbits = q.x;
         minx = q.y & 0xffffu; miny = q.y >> 16;
@@ -434,7 +434,7 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
             const uint32_t i = i0 + u * nt;
             id[u] = i < n ? (uint32_t)keys[i] : 0u;
             if (i < n) {
-                a[u] = recs[(size_t)id[u] * 4]; b[u] = recs[(size_t)id[u] * 4 + 1]; c[u] = recs[(size_t)id[u] * 4 + 2];
+                a[u] = recs[(size_t)id[u] * 3]; b[u] = recs[(size_t)id[u] * 3 + 1]; c[u] = recs[(size_t)id[u] * 3 + 2];
             }
         }
 #pragma unroll

@@ -1,8 +1,8 @@
 // gstar_common.cuh -- shared device-side definitions for the sm_100a surface-Gaussian rasterizer.
 //
 // Data layout in HBM:
-//   GRec[P]       64-byte packed per-Gaussian record written by preprocess_fwd and gathered
-//                 (first 48 bytes, one cp.async.bulk each) by the blend kernels.
+//   GRec[P]       48-byte packed per-Gaussian record written by preprocess_fwd (what blending needs of a Gaussian);
+//   GAux[P]       16 bytes per Gaussian for binning (depth, tile rect, radius).
 //   entries[R]    unsorted per-tile segments of (depth bits, gaussian idx) pairs.
 //   point_list[R] per-tile depth-sorted gaussian indices == the reference's sorted value list
 //                 (DGR/cuda_rasterizer/rasterizer_impl.cu:303-308).
@@ -15,7 +15,7 @@
 
 #define GSTAR_TILE 16          // DGR/cuda_rasterizer/config.h:16-17 (BLOCK_X, BLOCK_Y)
 #define GSTAR_BATCH 256        // records staged in shared memory per pipeline stage
-#define GSTAR_REC_BYTES 64     // stride of GRec in HBM
+#define GSTAR_REC_BYTES 48     // stride of GRec in HBM
 #define GSTAR_REC_SMEM 48      // bytes of a record the blend kernels need (bulk-copied)
 #define GSTAR_GACC 12          // floats per Gaussian in the blend-gradient accumulator
 
@@ -28,12 +28,15 @@ struct __align__(16) GRec {
     uint32_t bbox_y;   // int16 ymin | int16 ymax << 16
     float b;           // colour, third channel
     uint32_t flags;    // bit0..2: SH clamp mask (forward.cu:67-69)
+};
+// What binning needs of a Gaussian, in its own array: emit streams 16 bytes per Gaussian instead of whole records.
+struct __align__(16) GAux {
     float depth;       // view-space z                      forward.cu:250
     uint32_t rect_min; // tile rect min x | y << 16         auxiliary.h:46-56
     uint32_t rect_max; // tile rect max x | y << 16 (exclusive)
     int32_t radius;    // forward.cu:251 (0 = culled)
 };
-static_assert(sizeof(GRec) == GSTAR_REC_BYTES, "GRec must be 64 bytes");
+static_assert(sizeof(GRec) == GSTAR_REC_BYTES && sizeof(GAux) == 16, "GRec / GAux layout");
 
 // Small header kept at the start of the image buffer (device) -- counters of one forward call.
 struct GHeader {

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 struct GRec;
+struct GAux;
 struct GHeader;
 
 namespace gstar {
@@ -24,6 +25,7 @@ struct PreFwdParams {
     float tan_fovx, tan_fovy, focal_x, focal_y;
     int prefiltered;
     GRec* recs;
+    GAux* aux;
     int* radii;
     uint32_t* tile_count;
 };
@@ -42,6 +44,7 @@ struct PreBwdParams {
     float tan_fovx, tan_fovy, focal_x, focal_y;
     const int* radii;
     const GRec* recs;
+    const GAux* aux;
     const float* gacc;  // [P][12] blend-stage gradient accumulator
     float* dL_dmean2D;
     float* dL_dconic;
@@ -58,6 +61,7 @@ struct PreBwdParams {
 struct BinParams {
     int P, gx, gy, num_tiles, W, H;
     const GRec* recs;
+    const GAux* aux;
     GHeader* hdr;          // device header (image buffer)
     uint32_t* tile_count;  // [T] histogram from preprocess
     uint32_t* tile_cursor; // [T] running write position per tile
@@ -95,7 +99,7 @@ struct BlendParams {
 void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s);
 void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* vm, unsigned char* present, cudaStream_t s);
-void launch_geom_unpack(const GRec* recs, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
+void launch_geom_unpack(const GRec* recs, const GAux* aux, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
                         unsigned char* clamped, cudaStream_t s);
 
 void launch_tile_scan(const BinParams& p, cudaStream_t s);

@@ -314,10 +314,12 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_fwd(PreFwdParams p)
     const unsigned lane = threadIdx.x & 31;
     const bool valid = idx < p.P;
     GRec rec;
+    GAux aux;
     {
         float4 z = {0.f, 0.f, 0.f, 0.f};
         float4* r4 = reinterpret_cast<float4*>(&rec);
-        r4[0] = z; r4[1] = z; r4[2] = z; r4[3] = z;
+        r4[0] = z; r4[1] = z; r4[2] = z;
+        *reinterpret_cast<float4*>(&aux) = z;
     }
     uint32_t minx = 0, miny = 0, maxx = 0, maxy = 0;
     bool visible = false;
@@ -381,10 +383,10 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_fwd(PreFwdParams p)
             rec.x = pix; rec.y = piy; rec.A = conx; rec.B = cony; rec.C = conz; rec.o = opac;
             rec.bbox_x = ((uint32_t)bx0 & 0xffffu) | ((uint32_t)bx1 << 16);
             rec.bbox_y = ((uint32_t)by0 & 0xffffu) | ((uint32_t)by1 << 16);
-            rec.depth = pvz;
-            rec.rect_min = minx | (miny << 16);
-            rec.rect_max = maxx | (maxy << 16);
-            rec.radius = radius;
+            aux.depth = pvz;
+            aux.rect_min = minx | (miny << 16);
+            aux.rect_max = maxx | (maxy << 16);
+            aux.radius = radius;
         } while (0);
     }
     // colour: colors_precomp, or SH -> RGB with the warp's SH rows staged through shared memory
@@ -421,8 +423,9 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_fwd(PreFwdParams p)
     if (valid) {
         float4* dst = reinterpret_cast<float4*>(p.recs + idx);
         const float4* src = reinterpret_cast<const float4*>(&rec);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-        p.radii[idx] = rec.radius;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        *reinterpret_cast<float4*>(p.aux + idx) = *reinterpret_cast<const float4*>(&aux);
+        p.radii[idx] = aux.radius;
     }
     // per-tile histogram (first digit of the MSD tile|depth sort): one atomic per distinct tile per warp
     uint32_t* cnt = p.tile_count;
@@ -457,19 +460,20 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means3D, const f
     present[idx] = xform_row(m, 2, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]) > 0.2f;
 }
 
-__global__ void k_geom_unpack(const GRec* __restrict__ recs, int P, float* depths, float* means2D, float* conic_opacity, float* rgb,
+__global__ void k_geom_unpack(const GRec* __restrict__ recs, const GAux* __restrict__ auxs, int P, float* depths, float* means2D, float* conic_opacity, float* rgb,
                               uint32_t* tiles_touched, unsigned char* clamped)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const GRec r = recs[idx];
-    if (depths) depths[idx] = r.depth;
+    const GAux a = auxs[idx];
+    if (depths) depths[idx] = a.depth;
     if (means2D) { means2D[2 * idx] = r.x; means2D[2 * idx + 1] = r.y; }
     if (conic_opacity) { conic_opacity[4 * idx] = r.A; conic_opacity[4 * idx + 1] = r.B; conic_opacity[4 * idx + 2] = r.C; conic_opacity[4 * idx + 3] = r.o; }
     if (rgb) { rgb[3 * idx] = r.r; rgb[3 * idx + 1] = r.g; rgb[3 * idx + 2] = r.b; }
     if (tiles_touched) {
-        const uint32_t w = (r.rect_max & 0xffff) - (r.rect_min & 0xffff), h = (r.rect_max >> 16) - (r.rect_min >> 16);
-        tiles_touched[idx] = r.radius > 0 ? w * h : 0;
+        const uint32_t w = (a.rect_max & 0xffff) - (a.rect_min & 0xffff), h = (a.rect_max >> 16) - (a.rect_min >> 16);
+        tiles_touched[idx] = a.radius > 0 ? w * h : 0;
     }
     if (clamped) { clamped[3 * idx] = r.flags & 1; clamped[3 * idx + 1] = (r.flags >> 1) & 1; clamped[3 * idx + 2] = (r.flags >> 2) & 1; }
 }
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
     const int M = p.M;
     const float* vm = s_vm;
     const float* proj = s_pm;
-    const int radius = valid ? (p.radii ? p.radii[idx] : p.recs[idx].radius) : 0;
+    const int radius = valid ? (p.radii ? p.radii[idx] : p.aux[idx].radius) : 0;
     // blend_bwd accumulated the raw moments [S, Sx, Sy, Sxx, Sxy, Syy, cr, cg, cb] of every Gaussian (see blend.cu).
     // A Gaussian no pixel blended (culled, hidden behind the saturated front layer, ...) still has the all-zero row the
     // caller's memset left: all of its gradients are exactly zero, so nothing below needs its parameters or SH row --
@@ -790,10 +794,10 @@ void launch_mark_visible(int P, const float* means3D, const float* vm, unsigned 
 {
     k_mark_visible<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vm, present);
 }
-void launch_geom_unpack(const GRec* recs, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
+void launch_geom_unpack(const GRec* recs, const GAux* aux, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
                         unsigned char* clamped, cudaStream_t s)
 {
-    k_geom_unpack<<<(P + 255) / 256, 256, 0, s>>>(recs, P, depths, means2D, conic_opacity, rgb, tiles_touched, clamped);
+    k_geom_unpack<<<(P + 255) / 256, 256, 0, s>>>(recs, aux, P, depths, means2D, conic_opacity, rgb, tiles_touched, clamped);
 }
 
 }  // namespace gstar
