@@ -215,9 +215,11 @@ __global__ void __launch_bounds__(256) k_emit(BinParams p)
     const bool small = vis && w * h <= 4;
     const uint32_t nsmall = small ? w * h : 0u;
     const uint32_t rounds = __reduce_max_sync(0xffffffffu, nsmall);
+    uint32_t tx = minx, ty = miny;  // walks the rect row by row (no integer division in the loop)
     for (uint32_t t = 0; t < rounds; t++) {
         const bool act = t < nsmall;
-        const uint32_t tile = act ? (miny + t / w) * gx + (minx + t % w) : 0u;
+        const uint32_t tile = act ? ty * gx + tx : 0u;
+        if (++tx == minx + w) { tx = minx; ty++; }
         const uint32_t slot = warp_aggregated_add(cur, tile, act);
         if (act) ent[slot] = make_uint2((uint32_t)idx, dbits);
     }

@@ -433,9 +433,11 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_fwd(PreFwdParams p)
     const uint32_t w = maxx - minx, h = maxy - miny;
     const uint32_t nsmall = (visible && w * h <= 4) ? w * h : 0u;
     const uint32_t rounds = __reduce_max_sync(0xffffffffu, nsmall);
+    uint32_t tx = minx, ty = miny;  // walks the rect row by row (no integer division in the loop)
     for (uint32_t t = 0; t < rounds; t++) {
         const bool act = t < nsmall;
-        const uint32_t tile = act ? (miny + t / w) * gx + (minx + t % w) : 0xffffffffu;
+        const uint32_t tile = act ? ty * gx + tx : 0xffffffffu;
+        if (++tx == maxx) { tx = minx; ty++; }
         const unsigned peers = __match_any_sync(0xffffffffu, tile);
         if (act && (int)lane == __ffs(peers) - 1) atomicAdd(cnt + tile, (uint32_t)__popc(peers));
     }
