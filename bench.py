@@ -50,8 +50,9 @@ P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
 VIEWS_PER_GPU = 20  # BASELINE.json config #3: 160 views / 8 GPUs per step
 CAM_POOL = 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-# (profiles/r1k_ncu_full_summary.txt); None where no capture is committed
-NCU_TRAFFIC = {"blend_fwd": 388571648, "blend_bwd": 561560832, "preprocess_bwd": 573778688, "preprocess_fwd": 255691008, "tile_sort": 130042112}
+# (profiles/r1n_ncu_full_summary.txt); None where no capture is committed
+NCU_TRAFFIC = {"blend_fwd": 388952832, "blend_bwd": 564004352, "preprocess_bwd": 555864576, "preprocess_fwd": 260868352, "tile_sort": 109561856,
+               "emit": 16019712, "tile_scan": 61696}
 
 
 def measured_peak():
@@ -483,7 +484,7 @@ def main():
         if not use_gpu_ref:
             if rank != 0:
                 return
-            v, dt, sample = cpu_oracle_views_per_sec(1)
+            v, dt, sample = cpu_oracle_views_per_sec(3)
             line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
                     "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                     "config": config, "device": "cpu",
@@ -512,7 +513,7 @@ def main():
     else:
         line["roofline"] = res["roofline"]
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, sample = cpu_oracle_views_per_sec(1)
+            v, dt, sample = cpu_oracle_views_per_sec(3)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
                                     "seconds": round(dt, 1)}
     print(json.dumps(line), flush=True)
