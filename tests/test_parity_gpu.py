@@ -420,3 +420,35 @@ def test_grad_accumulation_fusion_matches_autograd():
         assert Hh.rel_err(fus[k].cpu(), ref[k].cpu()) < 1e-4, k
         assert Hh.rel_err(mixed[k].cpu(), ref[k].cpu()) < 1e-4, k
     assert Hh.rel_err(fus2d.cpu(), ref2d.cpu()) < 1e-4
+
+
+def test_hit_log_too_small_falls_back_on_device():
+    """A view whose hit log does not fit the provision made from the previous (smaller) view must take the walk-back
+    backward by itself -- decided on the device, no host round trip -- and still be exact; the next call has a log again."""
+    old = capi.set_hit_log(1)
+    try:
+        small = SCENES["sh_deg1_of_3"]()
+        big = SCENES["random_big_sh2"]()
+        for _ in range(40):  # the provision shrinks only after 32 consecutive small views
+            fs = capi.forward(**Hh.to_torch_kwargs(small))
+        torch.cuda.synchronize()
+        assert capi.hit_log_state(fs)[2]
+        kw = Hh.to_torch_kwargs(big)
+        fwd = capi.forward(**kw)
+        torch.cuda.synchronize()
+        need, cap, used = capi.hit_log_state(fwd)
+        assert need > cap and not used, (need, cap, used)
+        inp = Hh.oracle_inputs_from_dict(big)
+        of = O.forward(inp)
+        g, st = check_forward_against(fwd, kw, dict(of.__dict__), exact_image=False, n_contrib_slack=4)
+        dpix = np.random.default_rng(5).normal(0, 1, (3, big["H"], big["W"])).astype(np.float32)
+        mine = capi.backward(fwd, torch.from_numpy(dpix).cuda(), **Hh.bwd_kwargs(kw))
+        torch.cuda.synchronize()
+        of.n_contrib = st["n_contrib"].astype(np.uint32)
+        of.final_T = st["final_T"].copy()
+        check_grads(mine, O.backward(inp, of, dpix).__dict__)
+        fwd2 = capi.forward(**kw)
+        torch.cuda.synchronize()
+        assert capi.hit_log_state(fwd2)[2]  # re-provisioned from the need the first call published
+    finally:
+        capi.set_hit_log(old)
