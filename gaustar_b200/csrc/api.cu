@@ -113,7 +113,7 @@ int get_ctx(DevCtx** out)
 
 // ---- private layouts of the three opaque buffers ----
 struct ImgLayout {
-    size_t hdr, final_T, n_contrib, pixstate, ranges, tile_count, tile_cursor, tile_order, total;
+    size_t hdr, final_T, n_contrib, pixstate, ranges, tile_count, tile_cursor, tile_order, tile_lanes, total;
 };
 ImgLayout img_layout(int W, int H)
 {
@@ -129,6 +129,7 @@ ImgLayout img_layout(int W, int H)
     L.tile_count = o; o = align_up(o + T * 4, 128);
     L.tile_cursor = o; o = align_up(o + T * 4, 128);
     L.tile_order = o; o = align_up(o + T * 4, 128);
+    L.tile_lanes = o; o = align_up(o + T, 128);
     L.total = o;
     return L;
 }
@@ -251,13 +252,14 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bp.tile_cursor = (uint32_t*)(img + IL.tile_cursor);
     bp.ranges = (uint32_t*)(img + IL.ranges);
     bp.tile_order = (uint32_t*)(img + IL.tile_order);
+    bp.tile_lanes = (unsigned char*)(img + IL.tile_lanes);
     bp.host_counts = ctx->host_counts_dev;
 
     BlendParams bl;
     bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
     bl.recs = (const GRec*)geom; bl.hdr = hdr; bl.ranges = bp.ranges; bl.tile_order = bp.tile_order; bl.bg = a->background;
     bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
-    bl.dL_dpix = nullptr; bl.gacc = nullptr;
+    bl.dL_dpix = nullptr; bl.gacc = nullptr; bl.tile_lanes = bp.tile_lanes;
     bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = ctx->host_counts_dev;
 
     // Hit-log provision: the slots the previous view needed (published by its blend_fwd; a hint, it may lag) with the
@@ -394,6 +396,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         bl.recs = (const GRec*)geom; bl.hdr = (const GHeader*)(img + IL.hdr);
         bl.ranges = (const uint32_t*)(img + IL.ranges);
         bl.tile_order = (const uint32_t*)(img + IL.tile_order);
+        bl.tile_lanes = (const unsigned char*)(img + IL.tile_lanes);
         bl.packed = (const unsigned char*)aligned128(a->binning_buffer);
         bl.bg = a->background;
         bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);

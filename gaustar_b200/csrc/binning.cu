@@ -425,6 +425,12 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
         const unsigned long long base = atomicAdd(&p.hdr->log_cursor, (unsigned long long)tile_total);
         if (base + tile_total > p.log_capacity) p.hdr->log_overflow = 1u;
         sm->base = base;
+        // lanes per instance for the gather backward: about a dozen footprint pixels per lane, and more lanes when the
+        // tile has fewer instances than the gather CTA has threads
+        const uint32_t mean = tile_total / max(n, 1u);
+        uint32_t lanes = mean <= 14u ? 1u : mean <= 28u ? 2u : mean <= 64u ? 4u : 8u;
+        while (lanes < 8u && n * lanes < 256u && mean > 3u * lanes) lanes <<= 1;
+        p.tile_lanes[tile] = (unsigned char)lanes;
     }
     gsync(g);
     uint32_t slot = (uint32_t)sm->base + excl;

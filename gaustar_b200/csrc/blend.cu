@@ -523,6 +523,11 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
     const uint32_t* const point_list = reinterpret_cast<const uint32_t*>(p.packed + p.hdr->off_point_list);
     const float4* const tile_packed = reinterpret_cast<const float4*>(p.packed + (size_t)rs * RS);
     const float tx0f = (float)tile_x0, ty0f = (float)tile_y0;
+    // Lanes per instance, chosen per tile by the sort kernel from the mean footprint area and the list length: one for
+    // the tiny splats of a dense surface, 2/4/8 when footprints are large or the tile has fewer instances than threads
+    // (a single lane would walk a 50-pixel footprint through 50 dependent hit-log loads).
+    const int L = p.tile_lanes ? (int)p.tile_lanes[tile] : 1;
+    if (L <= 1) {
 #pragma unroll 1
     for (uint32_t i = tid; i < total; i += GATHER_THREADS) {
         const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // bbox_x bbox_y b slot
@@ -569,6 +574,73 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
             red_add_v4(dst, m0, m1, m2, m3);
             red_add_v4(dst + 4, m4, m5, m6, m7);
             atomicAdd(dst + 8, m8);
+        }
+    }
+    return;
+    }
+    // ---- L = 2, 4 or 8 lanes per instance: lane q of the group takes footprint slots q, q+L, ...; the group's partial
+    // moments meet in log2(L) shuffle steps.  Uniform trip counts (the shuffles need whole warps).
+    const int lshift = L == 2 ? 1 : L == 4 ? 2 : 3;
+    const int q = tid & (L - 1);
+    const uint32_t stride = GATHER_THREADS >> lshift;
+    const uint32_t rounds = (total + stride - 1) / stride;
+#pragma unroll 1
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t i = r * stride + ((uint32_t)tid >> lshift);
+        float m[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) m[c] = 0.f;
+        bool any = false;
+        if (i < total) {
+            const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // bbox_x bbox_y b slot
+            const Foot f = clip_foot(__float_as_uint(q2.x), __float_as_uint(q2.y), tile_x0, tile_y0, lim_x, lim_y);
+            if (f.w > 0 && f.h > 0) {
+                const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
+                const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
+                const GHit* hrow = hitlog + __float_as_uint(q2.w);
+                const int area = f.w * f.h;
+                for (int off = q * 128; off < area * (int)sizeof(GHit); off += L * 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
+                int xx = q, yy = 0;
+                while (xx >= f.w) { xx -= f.w; yy++; }
+#pragma unroll 1
+                for (int s = q; s < area; s += L) {
+                    const int pl = (f.y0 + yy) * GSTAR_TILE + f.x0 + xx;
+                    xx += L;
+                    while (xx >= f.w) { xx -= f.w; yy++; }
+                    if (i >= s_nc[pl]) continue;  // behind this pixel's last contributor
+                    float dx, dy;
+                    const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, tx0f + (float)(pl & 15), ty0f + (float)(pl >> 4), dx, dy);
+                    if (power > 0.0f) continue;
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const GHit h = hrow[s];
+                    const float4 pv = s_pix[pl];
+                    const float w = alpha * h.T;
+                    const float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
+                    const float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
+                    const float dL_dalpha = h.T * cdot - behind * __frcp_rn(1.0f - alpha);
+                    const float sG = (q1.y * dL_dalpha) * G;
+                    const float sx = sG * dx, sy = sG * dy;
+                    m[0] += sG; m[1] += sx; m[2] += sy;
+                    m[3] = fmaf(sx, dx, m[3]); m[4] = fmaf(sx, dy, m[4]); m[5] = fmaf(sy, dy, m[5]);
+                    m[6] = fmaf(w, pv.x, m[6]); m[7] = fmaf(w, pv.y, m[7]); m[8] = fmaf(w, pv.z, m[8]);
+                    any = true;
+                }
+            }
+        }
+        const unsigned anyb = __ballot_sync(FULL, any);
+        if (anyb == 0u) continue;
+        for (int d = 1; d < L; d <<= 1) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) m[c] += __shfl_xor_sync(FULL, m[c], d);
+        }
+        const unsigned grp = (anyb >> ((tid & 31) & ~(L - 1))) & ((1u << L) - 1u);
+        if (grp != 0u && q == 0) {
+            float* dst = p.gacc + (size_t)point_list[rs + i] * GSTAR_GACC;
+            red_add_v4(dst, m[0], m[1], m[2], m[3]);
+            red_add_v4(dst + 4, m[4], m[5], m[6], m[7]);
+            atomicAdd(dst + 8, m[8]);
         }
     }
 }

@@ -67,6 +67,7 @@ struct BinParams {
     uint32_t* tile_cursor; // [T] running write position per tile
     uint32_t* ranges;      // [T][2]
     uint32_t* tile_order;  // [T] all tiles, longest list first (work order of the blend kernels)
+    unsigned char* tile_lanes;  // [T] lanes per instance of the gather backward (1, 2, 4 or 8), chosen by tile_sort
     uint2* entries;        // [capacity] (depth bits, idx), tile-segmented
     uint32_t* point_list;  // [capacity] sorted gaussian ids
     unsigned char* packed; // [capacity][48] tile-contiguous packed records (GRec[0:44] + gaussian id), sorted order
@@ -84,6 +85,7 @@ struct BlendParams {
     const uint32_t* ranges;
     const unsigned char* packed;  // [R][48] tile-contiguous packed records in blend order (= start of the binning buffer)
     const uint32_t* tile_order;
+    const unsigned char* tile_lanes;  // [T] lanes per instance for k_blend_bwd_gather (NULL: 1)
     float4* pixstate;             // [H*W] (C_r, C_g, C_b, T) per pixel as the forward left it (colour without background)
     volatile uint32_t* host_counts;
     const float* bg;
