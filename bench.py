@@ -50,9 +50,9 @@ P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
 VIEWS_PER_GPU = 20  # BASELINE.json config #3: 160 views / 8 GPUs per step
 CAM_POOL = 32
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-# (profiles/r1n_ncu_full_summary.txt); None where no capture is committed
-NCU_TRAFFIC = {"blend_fwd": 388952832, "blend_bwd": 564004352, "preprocess_bwd": 555864576, "preprocess_fwd": 260868352, "tile_sort": 109561856,
-               "emit": 16019712, "tile_scan": 61696}
+# (profiles/r1p_ncu_full_summary.txt); None where no capture is committed
+NCU_TRAFFIC = {"blend_fwd": 388686592, "blend_bwd": 548568832, "preprocess_bwd": 556546816, "preprocess_fwd": 258706176, "tile_sort": 112042240,
+               "emit": 16018176, "tile_scan": 61696}
 
 
 def measured_peak():
