@@ -1,4 +1,4 @@
-// binning.cu -- tile binning: K2 tile_scan, K3 emit, K4 tile_sort (+ big-tile variant).
+// binning.cu -- tile binning: K2 tile_scan, K3 emit, K4 tile_sort (one persistent kernel).
 //
 // Replaces, with an MSD formulation of the same 64-bit tile|depth key sort,
 //   cub::DeviceScan::InclusiveSum      rasterizer_impl.cu:277
@@ -10,8 +10,8 @@
 // high digit (tile id) is resolved first by a counting sort over tiles -- the histogram comes out of
 // preprocess_fwd, this file scans it (ranges[] falls out of the scan for free) and scatters
 // (depth, idx) pairs into per-tile segments -- and each segment is then sorted on the remaining
-// (depth_bits, idx) 64-bit key inside shared memory by one CTA.  The concatenation of the sorted
-// segments is bit-identical to the reference's sorted list.
+// (depth_bits, idx) 64-bit key inside shared memory by one CTA (or a 256-thread quarter of one).  The
+// concatenation of the sorted segments is bit-identical to the reference's sorted list.
 #include "gstar_common.cuh"
 #include "gstar_kernels.h"
 

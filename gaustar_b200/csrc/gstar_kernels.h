@@ -70,7 +70,7 @@ struct BinParams {
     unsigned char* tile_lanes;  // [T] lanes per instance of the gather backward (1, 2, 4 or 8), chosen by tile_sort
     uint2* entries;        // [capacity] (depth bits, idx), tile-segmented
     uint32_t* point_list;  // [capacity] sorted gaussian ids
-    unsigned char* packed; // [capacity][48] tile-contiguous packed records (GRec[0:44] + gaussian id), sorted order
+    unsigned char* packed; // [capacity][48] tile-contiguous packed records (GRec[0:44] + first hit-log slot), sorted order
     uint32_t capacity;
     unsigned long long log_capacity;    // hit-log slots available behind `entries` (0: log disabled)
     unsigned long long off_point_list;  // byte offsets inside the binning buffer, recorded in the header
