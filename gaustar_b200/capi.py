@@ -35,7 +35,7 @@ class FwdArgs(C.Structure):
         ("scales", C.c_void_p), ("scale_modifier", C.c_float), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("cam_pos", C.c_void_p),
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int),
-        ("out_color", C.c_void_p), ("radii", C.c_void_p), ("debug", C.c_int),
+        ("out_color", C.c_void_p), ("radii", C.c_void_p), ("debug", C.c_int), ("forward_only", C.c_int),
     ]
 
 
@@ -127,8 +127,10 @@ def _resizable(dev):
 
 
 def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, W, H, shs=None, colors_precomp=None,
-            scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, prefiltered=False, debug=False):
-    """gstar_raster_forward.  Returns dict(num_rendered, out_color, radii, geom, binning, image)."""
+            scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, prefiltered=False, debug=False,
+            forward_only=False):
+    """gstar_raster_forward.  Returns dict(num_rendered, out_color, radii, geom, binning, image).
+    forward_only: no backward will follow (the forward then skips the hit log)."""
     L = lib()
     dev = means3D.device
     assert dev.type == "cuda", "gaustar_b200 has no CPU path"
@@ -140,7 +142,7 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
     radii = torch.empty(P, dtype=torch.int32, device=dev)
     (geom, geom_cb), (binning, binning_cb), (image, image_cb) = _resizable(dev), _resizable(dev), _resizable(dev)
     a = FwdArgs(P, sh_degree, M, _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(op), _ptr(sc), scale_modifier, _ptr(rot), _ptr(cov),
-                _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, int(prefiltered), _ptr(out_color), _ptr(radii), int(debug))
+                _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, int(prefiltered), _ptr(out_color), _ptr(radii), int(debug), int(forward_only))
     with torch.cuda.device(dev):
         R = _check(L.gstar_raster_forward(C.byref(a), geom_cb, None, binning_cb, None, image_cb, None, _stream(dev)))
     if P == 0:

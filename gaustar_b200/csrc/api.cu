@@ -265,7 +265,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     // Hit-log provision: the slots the previous view needed (published by its blend_fwd; a hint, it may lag) with the
     // same grow-at-once / shrink-slowly / quantised policy as the instance count.  A view whose log does not fit simply
     // takes the walk-back backward (device-side flag), so a wrong guess costs speed, never correctness.
-    const bool use_log = hit_log_enabled();
+    const bool use_log = hit_log_enabled() && !a->forward_only;
     if (use_log) {
         const double need = (double)(((unsigned long long)ctx->host_counts[5] << 32) | ctx->host_counts[4]);
         if (need > 0.0) {

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         const size_t pid = (size_t)g.py * p.W + g.px;
         p.final_T[pid] = T;
         p.n_contrib[pid] = last;
-        if (n > 0) p.pixstate[pid] = make_float4(C0, C1, C2, T);  // only read back for tiles that have instances
+        if (n > 0 && log_on) p.pixstate[pid] = make_float4(C0, C1, C2, T);  // read back by the hit-log backward only
         p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), T, C0);  // forward.cu:372
         p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), T, C1);
         p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), T, C2);

@@ -45,6 +45,11 @@ void check(int rc)
 
 }  // namespace
 
+// Set by the Python wrapper around a call none of whose inputs requires grad (inference): the forward then skips the hit
+// log.  Thread-local, reset by the wrapper right after the call; the reference's 19-argument signature stays as it is.
+static thread_local bool t_forward_only = false;
+void set_forward_only(bool flag) { t_forward_only = flag; }
+
 std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> RasterizeGaussiansCUDA(
     const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors, const torch::Tensor& opacity,
     const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
@@ -86,6 +91,7 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torc
         a.viewmatrix = fptr(vm); a.projmatrix = fptr(pm); a.cam_pos = fptr(cp);
         a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered ? 1 : 0;
         a.out_color = out_color.data_ptr<float>(); a.radii = radii.data_ptr<int>(); a.debug = debug ? 1 : 0;
+        a.forward_only = t_forward_only ? 1 : 0;
         rendered = gstar_raster_forward(&a, resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer, stream);
         check(rendered);
     } else {
@@ -228,4 +234,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("rasterize_gaussians_backward_fused", &RasterizeGaussiansBackwardFusedCUDA);
     m.def("mark_visible", &markVisible);
+    m.def("set_forward_only", &set_forward_only);
 }

@@ -80,7 +80,15 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise
         else:
-            num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+            # inference (no input requires grad, e.g. the renders of refined_mesh.py): tell the forward that no backward follows
+            fwd_only = not any(ctx.needs_input_grad)
+            if fwd_only:
+                _C.set_forward_only(True)
+            try:
+                num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+            finally:
+                if fwd_only:
+                    _C.set_forward_only(False)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer)

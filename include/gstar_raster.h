@@ -73,6 +73,8 @@ typedef struct gstar_fwd_args {
     float* out_color;            /* [3,H,W] fully written */
     int* radii;                  /* [P] fully written (0 = culled) */
     int debug;                   /* !=0: synchronize + check after every stage (auxiliary.h:166-173) */
+    int forward_only;            /* !=0: no backward will follow (inference): the forward skips the hit log; a backward on
+                                  * these buffers is still correct (it takes the walk-back kernel) */
 } gstar_fwd_args;
 
 /* Forward pass.  Returns num_rendered (sum of tiles touched), exactly like Rasterizer::forward. */

@@ -452,3 +452,29 @@ def test_hit_log_too_small_falls_back_on_device():
         assert capi.hit_log_state(fwd2)[2]  # re-provisioned from the need the first call published
     finally:
         capi.set_hit_log(old)
+
+
+def test_forward_only_skips_hit_log_and_stays_exact():
+    """forward_only (set automatically by the operator when no input requires grad): same image bit for bit, no hit log;
+    a backward on those buffers still works (walk-back kernel)."""
+    import diff_gaussian_rasterization as dgr
+    old = capi.set_hit_log(1)
+    try:
+        d = SCENES["surface_sh3"]()
+        kw = Hh.to_torch_kwargs(d)
+        a = capi.forward(**kw)
+        b = capi.forward(forward_only=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(a["out_color"], b["out_color"]) and not capi.hit_log_state(b)[2]
+        dpix = torch.randn(3, d["H"], d["W"], device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+        ga, gb = capi.backward(a, dpix, **Hh.bwd_kwargs(kw)), capi.backward(b, dpix, **Hh.bwd_kwargs(kw))
+        for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity"):
+            assert Hh.rel_err(gb[k].cpu(), ga[k].cpu()) < GRAD_TOL, k
+        rs = dgr.GaussianRasterizationSettings(d["H"], d["W"], kw["tan_fovx"], kw["tan_fovy"], kw["bg"], 1.0, kw["viewmatrix"].view(4, 4),
+                                               kw["projmatrix"].view(4, 4), 3, kw["campos"], False, False)
+        with torch.no_grad():
+            img, _ = dgr.GaussianRasterizer(rs)(means3D=kw["means3D"], means2D=torch.zeros_like(kw["means3D"]), opacities=kw["opacities"],
+                                                shs=kw["shs"], scales=kw["scales"], rotations=kw["rotations"])
+        assert torch.equal(img, a["out_color"])
+    finally:
+        capi.set_hit_log(old)
