@@ -223,6 +223,22 @@ def make_autograd_rasterizer(impl):
 
 
 # ------------------------------------------------------------------------------------------------
+class _L1Mean(torch.autograd.Function):
+    """mean |img - target| with four elementwise/reduction kernels instead of the seven of
+    torch.nn.functional.l1_loss + autograd (same value and gradient); used by BOTH arms of the e2e measurement."""
+
+    @staticmethod
+    def forward(ctx, img, target):
+        d = img - target
+        ctx.save_for_backward(d)
+        return torch.linalg.vector_norm(d, ord=1) / d.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return torch.sign(d, out=d).mul_(g / d.numel()), None
+
+
 def l1_grad_fn(target_f):
     """dL/dcolor of L = mean |render - target| (SURVEY 8d upstream gradient)."""
     inv = 1.0 / (3 * H * W)
@@ -406,7 +422,7 @@ def run_gpu(args, impl_name, rank, world, local):
                               viewmatrix=s["vm"], projmatrix=s["pm"], sh_degree=SH_DEG, campos=s["cp"], prefiltered=False, debug=False)
                 img, _radii = Rasterizer(rs)(means3D=ls["means3D"], means2D=m2d_sets[i % ns], opacities=ls["opacities"], shs=ls["shs"],
                                              scales=ls["scales"], rotations=ls["rotations"])
-                loss = torch.nn.functional.l1_loss(img, s["tgt_f"])
+                loss = _L1Mean.apply(img, s["tgt_f"])
                 loss.backward()
                 loss_acc[i % ns] += loss.detach()
                 s["free"].record(st)
