@@ -450,9 +450,11 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
             const uint32_t i = i0 + u * nt;
             if (i < n) {
                 p.point_list[start + i] = id[u];
-                const uint32_t area = foot_area(__float_as_uint(c[u].x), __float_as_uint(c[u].y), tx0, ty0, limx, limy);
+                const Foot ft = clip_foot(__float_as_uint(c[u].x), __float_as_uint(c[u].y), tx0, ty0, limx, limy);
+                c[u].x = __uint_as_float(pack_foot(ft));  // the blend kernels get the clipped footprint ready-made
+                c[u].y = __uint_as_float(id[u]);
                 c[u].w = __uint_as_float(slot);
-                slot += area;
+                slot += (ft.w > 0 && ft.h > 0) ? (uint32_t)(ft.w * ft.h) : 0u;
                 out[(size_t)i * 3] = a[u]; out[(size_t)i * 3 + 1] = b[u]; out[(size_t)i * 3 + 2] = c[u];
             }
         }

@@ -28,6 +28,7 @@ constexpr int BLEND_THREADS = (NCONS + 1) * 32;  // + one producer warp
 
 struct WarpGeom {
     int rx0, ry0, rx1, ry1, px, py;
+    int bx, by;  // the block's origin inside the tile
     bool inside;
 };
 
@@ -36,8 +37,10 @@ __device__ __forceinline__ WarpGeom warp_geom(int tile, int gx, int W, int H)
     WarpGeom g;
     const int tx = tile % gx, ty = tile / gx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    g.rx0 = tx * GSTAR_TILE + (warp & 1) * 8;
-    g.ry0 = ty * GSTAR_TILE + (warp >> 1) * 4;
+    g.bx = (warp & 1) * 8;
+    g.by = ((warp >> 1) & 3) * 4;
+    g.rx0 = tx * GSTAR_TILE + g.bx;
+    g.ry0 = ty * GSTAR_TILE + g.by;
     g.rx1 = g.rx0 + 7;
     g.ry1 = g.ry0 + 3;
     g.px = g.rx0 + (lane & 7);
@@ -46,7 +49,7 @@ __device__ __forceinline__ WarpGeom warp_geom(int tile, int gx, int W, int H)
     return g;
 }
 
-// Bounding box (absolute pixel coordinates) of the lanes set in `live` (lane = 8*row + col of the warp's 8x4 block).
+// Bounding box (tile-local pixel coordinates) of the lanes set in `live` (lane = 8*row + col of the warp's 8x4 block).
 // Culling against the box of the pixels that can still change -- instead of the whole block -- is what keeps
 // silhouette tiles cheap: there a handful of never-saturating background pixels would otherwise drag the whole
 // warp through tens of thousands of records that only touch finished pixels.
@@ -57,27 +60,25 @@ __device__ __forceinline__ LiveBox live_box(unsigned live, const WarpGeom& g)
 {
     const unsigned cols = (live | (live >> 8) | (live >> 16) | (live >> 24)) & 0xffu;
     LiveBox b;
-    b.x0 = g.rx0 + __ffs(cols) - 1;
-    b.x1 = g.rx0 + 31 - __clz(cols);
-    b.y0 = g.ry0 + ((__ffs(live) - 1) >> 3);
-    b.y1 = g.ry0 + ((31 - __clz(live)) >> 3);
+    b.x0 = g.bx + __ffs(cols) - 1;
+    b.x1 = g.bx + 31 - __clz(cols);
+    b.y0 = g.by + ((__ffs(live) - 1) >> 3);
+    b.y1 = g.by + ((31 - __clz(live)) >> 3);
     return b;
 }
 __device__ __forceinline__ bool bbox_overlaps_box(const unsigned char* rec, const LiveBox& b)
 {
-    const uint2 bb = *reinterpret_cast<const uint2*>(rec + 32);
-    const int bx0 = (int)(short)(bb.x & 0xffffu), bx1 = (int)(short)(bb.x >> 16);
-    const int by0 = (int)(short)(bb.y & 0xffffu), by1 = (int)(short)(bb.y >> 16);
-    return bx0 <= b.x1 && bx1 >= b.x0 && by0 <= b.y1 && by1 >= b.y0;
+    const Foot f = unpack_foot(*reinterpret_cast<const uint32_t*>(rec + 32));
+    return f.w > 0 && f.x0 <= b.x1 && f.x0 + f.w - 1 >= b.x0 && f.y0 <= b.y1 && f.y0 + f.h - 1 >= b.y0;
 }
 
-// 32-bit mask (bit = 8*row + col of the warp's 8x4 block) of the block pixels inside a record's alpha-bounds.
+// 32-bit mask (bit = 8*row + col of the warp's 8x4 block) of the block pixels inside a record's (clipped) alpha-bounds.
 __device__ __forceinline__ unsigned block_pixel_mask(const unsigned char* rec, const WarpGeom& g)
 {
-    const uint2 bb = *reinterpret_cast<const uint2*>(rec + 32);
-    const int cx0 = max((int)(short)(bb.x & 0xffffu) - g.rx0, 0), cx1 = min((int)(short)(bb.x >> 16) - g.rx0, 7);
-    const int cy0 = max((int)(short)(bb.y & 0xffffu) - g.ry0, 0), cy1 = min((int)(short)(bb.y >> 16) - g.ry0, 3);
-    if (cx0 > cx1 || cy0 > cy1) return 0u;
+    const Foot f = unpack_foot(*reinterpret_cast<const uint32_t*>(rec + 32));
+    const int cx0 = max(f.x0 - g.bx, 0), cx1 = min(f.x0 + f.w - 1 - g.bx, 7);
+    const int cy0 = max(f.y0 - g.by, 0), cy1 = min(f.y0 + f.h - 1 - g.by, 3);
+    if (cx0 > cx1 || cy0 > cy1) return 0u;  // also the empty footprint (w = h = 0)
     const unsigned cols = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);                       // 8 bits
     const unsigned rows = (0xffffffffu >> (8 * (3 - cy1))) & (0xffffffffu << (8 * cy0));  // whole bytes
     return (cols * 0x01010101u) & rows;
@@ -171,7 +172,6 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
     const bool log_on = p.hdr->log_overflow == 0u;
     GHit* const hitlog = reinterpret_cast<GHit*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
     const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
-    const int lim_x = min(GSTAR_TILE - 1, p.W - 1 - tile_x0), lim_y = min(GSTAR_TILE - 1, p.H - 1 - tile_y0);
     const int lx = g.px - tile_x0, ly = g.py - tile_y0;
     if (blockIdx.x == 0 && tid == 0 && p.host_counts) {  // size the next call's log: slots this view needed
         const unsigned long long need = p.hdr->log_cursor;
@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                             C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
                             C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
                             if (log_on) {
-                                const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // bbox_x bbox_y b slot
-                                const Foot f = clip_foot(tail.x, tail.y, tile_x0, tile_y0, lim_x, lim_y);
+                                const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // foot gid b slot
+                                const Foot f = unpack_foot(tail.x);
                                 GHit h;
                                 h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
                                 hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
     __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE];
     __shared__ int s_kmax;
     if (p.hdr->overflow || p.hdr->log_overflow == 0u) return;  // with a hit log, k_blend_bwd_gather does the work
-    const uint32_t* const point_list = reinterpret_cast<const uint32_t*>(p.packed + p.hdr->off_point_list);
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     if (re == rs) return;
@@ -458,7 +457,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
                         const int rsel = lane >> 4;
                         const bool any_mine = rsel ? (anyB != 0) : (anyA != 0);
                         if (any_mine) {
-                            const uint32_t gid = point_list[rs + (uint32_t)(kbase - slot[rsel])];
+                            const uint32_t gid = *reinterpret_cast<const uint32_t*>(buf - slot[rsel] * RS + 36);
                             float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
                             if ((lane & 1) == 0) atomicAdd(dst + (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)), t);
                             else if ((lane & 15) == 1) atomicAdd(dst + 8, o);  // gacc row = the nine raw moments
@@ -495,7 +494,6 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
     if (re == rs) return;
     const int tid = threadIdx.x;
     const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
-    const int lim_x = min(GSTAR_TILE - 1, p.W - 1 - tile_x0), lim_y = min(GSTAR_TILE - 1, p.H - 1 - tile_y0);
     {
         const int px = tile_x0 + (tid & 15), py = tile_y0 + (tid >> 4);
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -520,7 +518,6 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
     }
     const uint32_t total = s_total;  // instances behind every pixel's last contributor were never blended
     const GHit* const hitlog = reinterpret_cast<const GHit*>(p.packed + p.hdr->off_log);
-    const uint32_t* const point_list = reinterpret_cast<const uint32_t*>(p.packed + p.hdr->off_point_list);
     const float4* const tile_packed = reinterpret_cast<const float4*>(p.packed + (size_t)rs * RS);
     const float tx0f = (float)tile_x0, ty0f = (float)tile_y0;
     // Lanes per instance, chosen per tile by the sort kernel from the mean footprint area and the list length: one for
@@ -530,8 +527,8 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
     if (L <= 1) {
 #pragma unroll 1
     for (uint32_t i = tid; i < total; i += GATHER_THREADS) {
-        const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // bbox_x bbox_y b slot
-        const Foot f = clip_foot(__float_as_uint(q2.x), __float_as_uint(q2.y), tile_x0, tile_y0, lim_x, lim_y);
+        const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // foot gid b slot
+        const Foot f = unpack_foot(__float_as_uint(q2.x));
         if (f.w <= 0 || f.h <= 0) continue;
         const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
         const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
@@ -570,7 +567,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
             any = true;
         }
         if (any) {
-            float* dst = p.gacc + (size_t)point_list[rs + i] * GSTAR_GACC;
+            float* dst = p.gacc + (size_t)__float_as_uint(q2.y) * GSTAR_GACC;
             red_add_v4(dst, m0, m1, m2, m3);
             red_add_v4(dst + 4, m4, m5, m6, m7);
             atomicAdd(dst + 8, m8);
@@ -591,9 +588,11 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
 #pragma unroll
         for (int c = 0; c < 9; c++) m[c] = 0.f;
         bool any = false;
+        uint32_t gid = 0;
         if (i < total) {
-            const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // bbox_x bbox_y b slot
-            const Foot f = clip_foot(__float_as_uint(q2.x), __float_as_uint(q2.y), tile_x0, tile_y0, lim_x, lim_y);
+            const float4 q2 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 2);  // foot gid b slot
+            const Foot f = unpack_foot(__float_as_uint(q2.x));
+            gid = __float_as_uint(q2.y);
             if (f.w > 0 && f.h > 0) {
                 const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
                 const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
@@ -637,7 +636,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
         }
         const unsigned grp = (anyb >> ((tid & 31) & ~(L - 1))) & ((1u << L) - 1u);
         if (grp != 0u && q == 0) {
-            float* dst = p.gacc + (size_t)point_list[rs + i] * GSTAR_GACC;
+            float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
             red_add_v4(dst, m[0], m[1], m[2], m[3]);
             red_add_v4(dst + 4, m[4], m[5], m[6], m[7]);
             atomicAdd(dst + 8, m[8]);

@@ -7,7 +7,8 @@
 //   point_list[R] per-tile depth-sorted gaussian indices == the reference's sorted value list
 //                 (DGR/cuda_rasterizer/rasterizer_impl.cu:303-308).
 //   ranges[T]     [start,end) of every tile in point_list (rasterizer_impl.cu:116-138).
-//   packed[R]     48-byte records in blend order (GRec[0:44] + the instance's first hit-log slot).
+//   packed[R]     48-byte records in blend order: x y A B | C o r g | foot gid b slot  (foot = the alpha-bounds clipped to
+//                 the tile, packed; gid = Gaussian index; slot = the instance's first hit-log slot).
 //   hitlog[A]     16-byte GHit per (instance, footprint pixel), written by blend_fwd for every blended pair.
 #pragma once
 #include <cuda_runtime.h>
@@ -150,6 +151,20 @@ __device__ __forceinline__ Foot clip_foot(uint32_t bbx, uint32_t bby, int tile_x
     f.y0 = max((int)(short)(bby & 0xffffu) - tile_y0, 0);
     f.w = min((int)(short)(bbx >> 16) - tile_x0, lim_x) - f.x0 + 1;
     f.h = min((int)(short)(bby >> 16) - tile_y0, lim_y) - f.y0 + 1;
+    return f;
+}
+
+// The packed records carry the footprint already clipped (tile_sort computes it once per instance):
+// x0 | y0 << 4 | w << 8 | h << 13, all tile-local, w and h in 0..16, 0 = the alpha-bounds miss the tile.
+__device__ __forceinline__ uint32_t pack_foot(const Foot& f)
+{
+    if (f.w <= 0 || f.h <= 0) return 0u;
+    return (uint32_t)f.x0 | ((uint32_t)f.y0 << 4) | ((uint32_t)f.w << 8) | ((uint32_t)f.h << 13);
+}
+__device__ __forceinline__ Foot unpack_foot(uint32_t v)
+{
+    Foot f;
+    f.x0 = (int)(v & 15u); f.y0 = (int)((v >> 4) & 15u); f.w = (int)((v >> 8) & 31u); f.h = (int)((v >> 13) & 31u);
     return f;
 }
 
