@@ -21,6 +21,7 @@ constexpr int SCAN_THREADS = 1024;
 constexpr uint32_t SORT_CAP = 8192;                // keys (64 KB, a power of two) one CTA sorts in shared memory
 constexpr int LPT_BUCKETS = 132;                   // quarter-octave size classes for the longest-first tile order
 constexpr int LPT_SMALL_END = 1 + 11 * 4;          // first LPT bucket with >= 2048 instances
+constexpr int LPT_MID_END = 1 + 12 * 4;            // first LPT bucket with >= 4096 instances
 constexpr int LPT_MED_END = 1 + 13 * 4;            // first LPT bucket with >= 8192 instances
 
 __device__ __forceinline__ int lpt_bucket(uint32_t c)
@@ -62,7 +63,7 @@ __device__ __forceinline__ uint32_t class_rank_add(uint32_t* hist, int bucket, b
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
 {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    __shared__ uint32_t s_max, s_total, s_cls[3];
+    __shared__ uint32_t s_max, s_total, s_cls[4];
     __shared__ uint32_t s_hist[LPT_BUCKETS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = p.num_tiles;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         if (lane == 0) {
             for (int b = LPT_BUCKETS - 1; b >= 0; b--) { const uint32_t h = s_hist[b]; s_hist[b] = acc; acc += h; }
             // s_hist[b] = tiles in classes > b = first position of class b: the list-length classes of the sort kernel
-            s_cls[0] = s_hist[LPT_MED_END - 1]; s_cls[1] = s_hist[LPT_SMALL_END - 1]; s_cls[2] = s_hist[0];
+            s_cls[0] = s_hist[LPT_MED_END - 1]; s_cls[1] = s_hist[LPT_MID_END - 1]; s_cls[2] = s_hist[LPT_SMALL_END - 1]; s_cls[3] = s_hist[0];
         }
     }
     __syncthreads();
@@ -176,8 +177,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         p.hdr->overflow = ovf;
         p.hdr->max_tile = s_max;
         p.hdr->pad0[0] = 0u; p.hdr->pad0[1] = 0u; p.hdr->pad0[2] = 0u;
-        for (int c = 0; c < 3; c++) { p.hdr->cls_end[c] = s_cls[c]; p.hdr->cls_cursor[c] = 0u; }
-        p.hdr->cls_end[3] = s_cls[2]; p.hdr->cls_cursor[3] = 0u;
+        for (int c = 0; c < 4; c++) { p.hdr->cls_end[c] = s_cls[c]; p.hdr->cls_cursor[c] = 0u; }
         p.hdr->log_overflow = p.log_capacity ? 0u : 1u;
         p.hdr->log_cursor = 0ull;
         p.hdr->log_capacity = p.log_capacity;
@@ -640,17 +640,22 @@ __device__ __forceinline__ void bucket_sort_tile(const BinParams& p, const Grp& 
 }
 
 // ---- K4: ONE persistent kernel sorts every tile list -------------------------------------------------------------
-// CTAs of 1024 threads, one per SM.  A CTA first pulls tiles of class 0 (>= 8192 instances, network) and class 1
-// (2048..8191, bucket sort with all 1024 threads), longest first; when those run out it splits into four 256-thread
-// groups (named barriers 1..4) that pull class-2 tiles (< 2048 instances) independently.  One launch, no tail between
-// the classes, and the short lists -- the bulk of a surface view -- are sorted four at a time per SM.
+// CTAs of 1024 threads, one per SM.  A CTA first pulls, with all its threads, the tiles of class 0 (>= 8192 instances,
+// network) and class 1 (4096..8191, bucket sort), longest first; then it splits into two 512-thread groups for class 2
+// (2048..4095) and into four 256-thread groups for class 3 (< 2048), each group pulling tiles independently on its own
+// named barrier.  One launch, no tail between the classes, and the shorter a list the more of them an SM sorts at once
+// (the per-list chain of dependent round trips is what a sort costs here, not its instructions).
 constexpr int SORT_CTA = 1024;
-constexpr uint32_t SMALL_CAP = 2048, MED_CAP = 8192;
+constexpr uint32_t SMALL_CAP = 2048, MID_CAP = 4096, MED_CAP = 8192;
 constexpr int SMALL_NT = 256, SMALL_GROUPS = SORT_CTA / SMALL_NT;
+constexpr int MID_NT = 512, MID_GROUPS = SORT_CTA / MID_NT;
 constexpr int SMALL_BYTES = SMALL_CAP * 8 + (SMALL_CAP + SMALL_CAP / SMALL_NT + 1) * 4;   // keys out + fine buckets
 constexpr int SMALL_STRIDE = (SMALL_BYTES + 127) / 128 * 128;
+constexpr int MID_BYTES = MID_CAP * 8 + (MID_CAP + MID_CAP / MID_NT + 1) * 4;
+constexpr int MID_STRIDE = (MID_BYTES + 127) / 128 * 128;
 constexpr int MED_BYTES = MED_CAP * 8 + (MED_CAP + MED_CAP / SORT_CTA + 1) * 4;
-constexpr int SORT_DYN_SMEM = (MED_BYTES > SMALL_GROUPS * SMALL_STRIDE ? MED_BYTES : SMALL_GROUPS * SMALL_STRIDE);
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int SORT_DYN_SMEM = cmax(MED_BYTES, cmax(MID_GROUPS * MID_STRIDE, SMALL_GROUPS * SMALL_STRIDE));
 
 __global__ void __launch_bounds__(SORT_CTA, 1) k_tile_sort(BinParams p)
 {
@@ -668,12 +673,21 @@ __global__ void __launch_bounds__(SORT_CTA, 1) k_tile_sort(BinParams p)
         __syncthreads();
     }
     {
+        const int grp = threadIdx.x / MID_NT;
+        Grp g{threadIdx.x % MID_NT, MID_NT, 1 + grp};
+        GrpSmem* sm = &s_grp[grp];
+        uint64_t* s_out = reinterpret_cast<uint64_t*>(s_raw + (size_t)grp * MID_STRIDE);
+        uint32_t* s_fine = reinterpret_cast<uint32_t*>(s_raw + (size_t)grp * MID_STRIDE + MID_CAP * 8);
+        while (next_tile(p, 2, g, sm, tile, start, n)) bucket_sort_tile<MID_CAP, MID_NT>(p, g, sm, s_out, s_fine, tile, start, n);
+        __syncthreads();  // both halves are done before the quarters reuse the shared memory
+    }
+    {
         const int grp = threadIdx.x / SMALL_NT;
-        Grp g{threadIdx.x % SMALL_NT, SMALL_NT, 1 + grp};
+        Grp g{threadIdx.x % SMALL_NT, SMALL_NT, 3 + grp};
         GrpSmem* sm = &s_grp[grp];
         uint64_t* s_out = reinterpret_cast<uint64_t*>(s_raw + (size_t)grp * SMALL_STRIDE);
         uint32_t* s_fine = reinterpret_cast<uint32_t*>(s_raw + (size_t)grp * SMALL_STRIDE + SMALL_CAP * 8);
-        while (next_tile(p, 2, g, sm, tile, start, n)) bucket_sort_tile<SMALL_CAP, SMALL_NT>(p, g, sm, s_out, s_fine, tile, start, n);
+        while (next_tile(p, 3, g, sm, tile, start, n)) bucket_sort_tile<SMALL_CAP, SMALL_NT>(p, g, sm, s_out, s_fine, tile, start, n);
     }
 }
 

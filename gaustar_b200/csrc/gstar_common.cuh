@@ -52,8 +52,8 @@ struct GHeader {
     unsigned long long off_point_list;  // byte offsets inside the binning buffer
     unsigned long long off_log;
     // tile_order lists the tiles longest first; class c = positions [cls_end[c-1], cls_end[c]) of it:
-    // 0: >= 8192 instances, 1: 2048..8191, 2: 1..2047 (cls_end[2] = number of non-empty tiles).  The sort kernels are
-    // persistent and pull tiles of their class through cls_cursor.
+    // 0: >= 8192 instances, 1: 4096..8191, 2: 2048..4095, 3: 1..2047 (cls_end[3] = number of non-empty tiles).  The sort
+    // kernel is persistent and pulls the tiles of a class through cls_cursor.
     uint32_t cls_end[4];
     uint32_t cls_cursor[4];
 };
