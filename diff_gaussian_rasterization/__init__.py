@@ -11,5 +11,7 @@ from gaustar_b200.rasterizer import (  # noqa: F401
     GaussianRasterizer,
     _RasterizeGaussians,
     rasterize_gaussians,
+    set_geometry_cache,
+    shared_geometry,
     _C,
 )

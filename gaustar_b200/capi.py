@@ -23,6 +23,7 @@ EXPORTED = [
     "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
     "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
     "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state", "gstar_debug_header", "gstar_knn3_mean_dist2",
+    "gstar_raster_reblend",
 ]
 STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
@@ -55,6 +56,15 @@ class BwdArgs(C.Structure):
     ]
 
 
+class ReblendArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("width", C.c_int), ("height", C.c_int),
+        ("background", C.c_void_p), ("colors_precomp", C.c_void_p),
+        ("src_binning_buffer", C.c_void_p), ("src_image_buffer", C.c_void_p),
+        ("out_color", C.c_void_p), ("debug", C.c_int), ("forward_only", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -75,6 +85,7 @@ def lib():
         L.gstar_binning_bytes.argtypes = [C.c_size_t]
         L.gstar_raster_forward.argtypes = [C.POINTER(FwdArgs), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p]
         L.gstar_raster_backward.argtypes = [C.POINTER(BwdArgs), C.c_void_p]
+        L.gstar_raster_reblend.argtypes = [C.POINTER(ReblendArgs), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p]
         L.gstar_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gstar_geom_unpack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.gstar_image_views.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -148,6 +159,24 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
     if P == 0:
         out_color.zero_()
     return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom[0], binning=binning[0], image=image[0], _keep=keep)
+
+
+def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False):
+    """gstar_raster_reblend: a second pass over the Gaussians/camera of forward (or re-blend) call `src` with other
+    per-Gaussian colours (and background).  Returns a dict shaped like forward()'s: the geometry buffer and radii are the
+    source call's (shared), binning and image are new -- pass it to backward() with colors_precomp=<these colours>."""
+    L = lib()
+    dev = src["geom"].device
+    keep = [_f32(colors_precomp, dev), _f32(bg, dev)]
+    col, bgc = keep
+    P = col.shape[0]
+    out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+    (binning, binning_cb), (image, image_cb) = _resizable(dev), _resizable(dev)
+    a = ReblendArgs(P, W, H, _ptr(bgc), _ptr(col), _ptr(src["binning"]), _ptr(src["image"]), _ptr(out_color), int(debug), int(forward_only))
+    with torch.cuda.device(dev):
+        R = _check(L.gstar_raster_reblend(C.byref(a), binning_cb, None, image_cb, None, _stream(dev)))
+    return dict(num_rendered=R, out_color=out_color, radii=src["radii"], geom=src["geom"], binning=binning[0], image=image[0],
+                _keep=keep + [src])
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,

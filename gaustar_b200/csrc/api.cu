@@ -52,6 +52,36 @@ struct DevCtx {
     double log_estimate = 0.0;  // running provision for the hit log (slots); 0 with log_have: log off for this workload
     int log_small_streak = 0;
     bool log_have = false;
+    // layouts of the most recent forward calls, keyed by their (aligned) image buffer: what gstar_raster_reblend needs
+    // to know on the host about the call it re-blends (the device header holds the same numbers, but reading it would
+    // stall the stream)
+    struct Recent {
+        const char* img = nullptr;
+        size_t cap = 0, log_slots = 0;
+        uint32_t R = 0;
+        int P = 0, W = 0, H = 0;
+    };
+    static constexpr int NRECENT = 16;
+    Recent recent[NRECENT];
+    int recent_next = 0;
+    void remember(const char* img, size_t cap, size_t log_slots, uint32_t R, int P, int W, int H)
+    {
+        int slot = -1;
+        for (int i = 0; i < NRECENT; i++)
+            if (recent[i].img == img) slot = i;
+        if (slot < 0) {
+            slot = recent_next;
+            recent_next = (recent_next + 1) % NRECENT;
+        }
+        recent[slot].img = img; recent[slot].cap = cap; recent[slot].log_slots = log_slots;
+        recent[slot].R = R; recent[slot].P = P; recent[slot].W = W; recent[slot].H = H;
+    }
+    const Recent* find(const char* img) const
+    {
+        for (int i = 0; i < NRECENT; i++)
+            if (recent[i].img == img) return &recent[i];
+        return nullptr;
+    }
 };
 int g_hit_log_mode = -1;  // -1: read GSTAR_HIT_LOG on first use; 0 off; 1 auto
 double g_hit_log_max_slots = 0.0;
@@ -287,6 +317,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
 
     size_t cap = ctx->have_estimate ? (size_t)ctx->estimate : 0;
     uint32_t R = 0;
+    size_t used_cap = 0, used_log_slots = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         char* bin = nullptr;
         if (cap > 0) {
@@ -298,6 +329,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             log_slots = (guess <= g_hit_log_max_slots && guess < 4.0e9) ? (size_t)guess : 0;
         }
         const BinLayout BL = bin_layout(cap, log_slots);
+        used_cap = cap; used_log_slots = log_slots;
         bp.capacity = (uint32_t)cap;
         bp.log_capacity = log_slots; bp.off_point_list = BL.point_list; bp.off_log = BL.log;
         if (cap > 0) {
@@ -370,8 +402,72 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             launch_tile_scan(bp, stream);
             launch_blend_fwd(bl, stream);
             STAGE_CHECK("blend_fwd(empty)");
+            used_cap = 1; used_log_slots = 0;
         }
     }
+    ctx->remember(img, used_cap, used_log_slots, R, a->P, W, H);
+    return (int)R;
+}
+
+// Shared-geometry re-blend.  GauSTAR rasterizes the same Gaussians from the same camera twice per training
+// step -- RGB, then depth as three equal channels (refine.py:552-564, :607-616) -- and the reference repeats preprocess,
+// duplicateWithKeys and the radix sort for the second call although only `colors_precomp` changed.  Here the second call
+// takes the first call's sorted, tile-contiguous record stream, rewrites its colour fields (k_recolor) into a binning
+// buffer of its own and blends.  The result is what gstar_raster_forward would return for (same geometry inputs,
+// colors_precomp): same records in the same order through the same blend kernel.
+int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_alloc, void* binning_user, gstar_alloc_fn image_alloc, void* image_user,
+                         void* stream_)
+{
+    using namespace gstar;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || !binning_alloc || !image_alloc) return fail(GSTAR_ERR_INVALID, "null argument");
+    if (a->P <= 0 || a->width <= 0 || a->height <= 0) return fail(GSTAR_ERR_INVALID, "bad sizes");
+    if (!a->colors_precomp || !a->background || !a->out_color) return fail(GSTAR_ERR_INVALID, "re-blend needs colors_precomp, background and out_color");
+    if (!a->src_image_buffer || !a->src_binning_buffer) return fail(GSTAR_ERR_INVALID, "re-blend needs the source call's binning and image buffers");
+    DevCtx* ctx;
+    int rc = get_ctx(&ctx);
+    if (rc < 0) return rc;
+    const char* src_img = aligned128((char*)a->src_image_buffer);
+    const DevCtx::Recent* src = ctx->find(src_img);
+    if (!src || src->P != a->P || src->W != a->width || src->H != a->height)
+        return fail(GSTAR_ERR_INVALID, "re-blend: the source buffers do not belong to a recent forward call of this thread with the same P, width and height");
+    const int W = a->width, H = a->height;
+    const int gx = (W + GSTAR_TILE - 1) / GSTAR_TILE, gy = (H + GSTAR_TILE - 1) / GSTAR_TILE;
+    const ImgLayout IL = img_layout(W, H);
+    // same layout as the source call (the header's offsets stay valid); an inference re-blend carries no hit log
+    const size_t cap = src->cap, R = src->R;
+    const size_t log_slots = a->forward_only ? 0 : src->log_slots;
+    const BinLayout BL = bin_layout(cap, log_slots);  // the offsets do not depend on the log's size
+    const size_t bin_bytes = BL.total + 128;
+    char* img = image_alloc(image_user, gstar_image_bytes(W, H));
+    char* bin = binning_alloc(binning_user, bin_bytes);
+    if (!img || !bin) return fail(GSTAR_ERR_ALLOC, "buffer callback returned NULL");
+    img = aligned128(img);
+    bin = aligned128(bin);
+    const char* src_bin = aligned128((char*)a->src_binning_buffer);
+    // header + everything binning left in the image buffer (ranges, tile order, gather lanes): a few hundred KB
+    CU_OK(cudaMemcpyAsync(img + IL.hdr, src_img + IL.hdr, sizeof(GHeader), cudaMemcpyDeviceToDevice, stream));
+    CU_OK(cudaMemcpyAsync(img + IL.ranges, src_img + IL.ranges, IL.total - IL.ranges, cudaMemcpyDeviceToDevice, stream));
+    GHeader* hdr = (GHeader*)(img + IL.hdr);
+    {
+        StageScope sc(GSTAR_STAGE_TILE_SORT, stream);  // takes the place of preprocess .. sort
+        launch_recolor((const unsigned char*)src_bin + BL.packed, (unsigned char*)bin + BL.packed, (uint32_t)R, a->colors_precomp, hdr,
+                       a->forward_only ? 1 : 0, stream);
+    }
+    STAGE_CHECK("recolor");
+    BlendParams bl;
+    bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
+    bl.recs = nullptr; bl.hdr = hdr; bl.ranges = (const uint32_t*)(img + IL.ranges); bl.tile_order = (const uint32_t*)(img + IL.tile_order);
+    bl.bg = a->background; bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
+    bl.dL_dpix = nullptr; bl.gacc = nullptr; bl.tile_lanes = (const unsigned char*)(img + IL.tile_lanes);
+    bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = ctx->host_counts_dev;
+    bl.packed = (const unsigned char*)bin + BL.packed;
+    {
+        StageScope sc(GSTAR_STAGE_BLEND_FWD, stream);
+        launch_blend_fwd(bl, stream);
+    }
+    STAGE_CHECK("blend_fwd");
+    ctx->remember(img, cap, log_slots, (uint32_t)R, a->P, W, H);  // a re-blend can itself be re-blended
     return (int)R;
 }
 

@@ -100,6 +100,39 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torc
     return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);
 }
 
+// Shared-geometry re-blend (gstar_raster_reblend): second pass over the Gaussians and camera of an earlier
+// forward call with other colours.  Returns (num_rendered, out_color, binningBuffer, imgBuffer); the geometry buffer and
+// radii of the source call serve the backward of this pass as well.
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor> ReblendGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& colors,
+                                                                                  const int image_height, const int image_width,
+                                                                                  const torch::Tensor& srcBinningBuffer,
+                                                                                  const torch::Tensor& srcImgBuffer, const bool debug)
+{
+    TORCH_CHECK(colors.is_cuda() && colors.dim() == 2 && colors.size(1) == 3, "gaustar_b200: re-blend needs CUDA colors_precomp of shape (P, 3)");
+    TORCH_CHECK(srcBinningBuffer.is_cuda() && srcImgBuffer.is_cuda() && srcImgBuffer.numel() > 0 && srcBinningBuffer.numel() > 0,
+                "gaustar_b200: re-blend needs the source call's buffers");
+    const torch::Device dev = colors.device();
+    c10::cuda::CUDAGuard guard(dev);
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(dev.index()).stream();
+    const int P = colors.size(0);
+    auto byte_opts = torch::TensorOptions(torch::kByte).device(dev);
+    torch::Tensor binningBuffer = torch::empty({0}, byte_opts);
+    torch::Tensor imgBuffer = torch::empty({0}, byte_opts);
+    torch::Tensor out_color = torch::empty({3, image_height, image_width}, colors.options().dtype(torch::kFloat32));
+    const torch::Tensor bg = prep(background, dev), col = prep(colors, dev);
+    gstar_reblend_args a;
+    a.P = P; a.width = image_width; a.height = image_height;
+    a.background = fptr(bg); a.colors_precomp = fptr(col);
+    a.src_binning_buffer = reinterpret_cast<const char*>(srcBinningBuffer.data_ptr());
+    a.src_image_buffer = reinterpret_cast<const char*>(srcImgBuffer.data_ptr());
+    a.out_color = out_color.data_ptr<float>();
+    a.debug = debug ? 1 : 0;
+    a.forward_only = t_forward_only ? 1 : 0;
+    const int rendered = gstar_raster_reblend(&a, resize_cb, &binningBuffer, resize_cb, &imgBuffer, stream);
+    check(rendered);
+    return std::make_tuple(rendered, out_color, binningBuffer, imgBuffer);
+}
+
 struct FusedTargets {
     torch::Tensor means3D, sh, opacity, scales, rotations;
 };
@@ -233,6 +266,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("rasterize_gaussians_backward_fused", &RasterizeGaussiansBackwardFusedCUDA);
+    m.def("rasterize_gaussians_reblend", &ReblendGaussiansCUDA);
     m.def("mark_visible", &markVisible);
     m.def("set_forward_only", &set_forward_only);
 }

@@ -50,6 +50,106 @@ def _fusable(t, needs):
             and g.shape == t.shape and g.device == t.device)
 
 
+# ---- shared-geometry re-blend ----
+# GauSTAR rasterizes the same Gaussians from the same camera twice per training step -- RGB, then depth as three equal
+# colour channels (gaustar_trainers/refine.py:552-564 and :607-616) -- and three times in refined_mesh.py:733-774.  The
+# reference repeats preprocess / duplicateWithKeys / radix sort every time.  Here a call that passes `colors_precomp`
+# and whose geometry inputs and camera are those of the previous full forward starts from that call's sorted record
+# stream (gstar_raster_reblend): only the blend runs again.  Two ways to say "same geometry":
+#   set_geometry_cache(True)   automatic and strict: the geometry tensors and camera matrices must be the very same
+#                              tensor objects' memory, unmodified (data_ptr + _version), same stream, same thread;
+#   with shared_geometry():    asserted by the caller for the calls inside the block (GauSTAR's properties rebuild
+#                              `points`/`scaling`/`quaternions` and the camera matrices on every call, so the tensors are
+#                              equal in value but not in identity); shared_geometry(check=True) verifies the values
+#                              (device->host syncs; for debugging).
+# Off by default: the source call's buffers (geometry, binning incl. hit log, image) stay alive until the next full
+# forward replaces them.
+import contextlib
+import os
+import threading
+
+_GEOM_CACHE = os.environ.get("GSTAR_GEOM_CACHE", "0") not in ("", "0")
+_tls = threading.local()
+
+
+class _GeomSource:
+    """What a later re-blend needs of a full forward call."""
+    __slots__ = ("key", "tensors", "rs", "geom", "binning", "image", "radii", "num_rendered")
+
+
+def set_geometry_cache(enabled: bool) -> bool:
+    """Automatic (identity-keyed) shared-geometry re-blend; returns the previous setting."""
+    global _GEOM_CACHE
+    old, _GEOM_CACHE = _GEOM_CACHE, bool(enabled)
+    if not enabled:
+        _tls.src = None
+    return old
+
+
+@contextlib.contextmanager
+def shared_geometry(check: bool = False):
+    """Every rasterizer call inside the block sees the same Gaussians (positions, opacities, scales/rotations or
+    covariances) through the same camera and image size; calls after the first that pass ``colors_precomp`` only
+    re-blend.  ``check=True`` compares the tensors' values with the first call's (slow; raises on mismatch)."""
+    old = getattr(_tls, "scope", None)
+    _tls.scope = {"check": bool(check)}
+    _tls.src = None
+    try:
+        yield
+    finally:
+        _tls.scope = old
+        _tls.src = None
+
+
+def _tkey(t):
+    if not isinstance(t, torch.Tensor) or t.numel() == 0:
+        return None
+    return (t.data_ptr(), t._version, tuple(t.shape), str(t.device), t.dtype)
+
+
+def _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs):
+    return (means3D, opacities, scales, rotations, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix)
+
+
+def _geom_key(tensors, rs, dev):
+    return (tuple(_tkey(t) for t in tensors), int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+            float(rs.scale_modifier), bool(rs.prefiltered), torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _remember_source(means3D, opacities, scales, rotations, cov3Ds_precomp, rs, geom, binning, image, radii, num_rendered):
+    if not (_GEOM_CACHE or getattr(_tls, "scope", None) is not None) or means3D.shape[0] == 0:
+        return
+    src = _GeomSource()
+    src.tensors = _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs)  # kept alive: their addresses cannot be recycled
+    src.key = _geom_key(src.tensors, rs, means3D.device)
+    src.rs = rs
+    src.geom, src.binning, src.image, src.radii, src.num_rendered = geom, binning, image, radii, num_rendered
+    _tls.src = src
+
+
+def _matching_source(means3D, opacities, scales, rotations, cov3Ds_precomp, colors_precomp, sh, rs):
+    """The remembered full forward this call may re-blend, or None."""
+    src = getattr(_tls, "src", None)
+    if src is None or rs.debug or sh.numel() != 0 or colors_precomp.numel() == 0 or not means3D.is_cuda:
+        return None
+    if not (colors_precomp.is_cuda and colors_precomp.dim() == 2 and colors_precomp.shape == (means3D.shape[0], 3)
+            and colors_precomp.dtype == torch.float32):
+        return None
+    tensors = _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs)
+    key = _geom_key(tensors, rs, means3D.device)
+    scope = getattr(_tls, "scope", None)
+    if scope is None:
+        return src if (_GEOM_CACHE and key == src.key) else None
+    # asserted by the caller: shapes, sizes and scalars must still agree (a different configuration is a full forward)
+    if key[1:] != src.key[1:] or any((a is None) != (b is None) or (a is not None and (a[2:] != b[2:])) for a, b in zip(key[0], src.key[0])):
+        return None
+    if scope["check"]:
+        for name, a, b in zip(("means3D", "opacities", "scales", "rotations", "cov3D_precomp", "viewmatrix", "projmatrix"), tensors, src.tensors):
+            if a.numel() and not torch.equal(a.to(b.device), b):
+                raise RuntimeError(f"shared_geometry(check=True): `{name}` differs from the first call of the block")
+    return src
+
+
 def _cpu_snapshot(args):
     # DGR/__init__.py:17-19: inputs are copied before the call so a crash can be replayed
     return tuple(a.cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
@@ -57,6 +157,9 @@ def _cpu_snapshot(args):
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
     """DGR/__init__.py:21-42."""
+    src = _matching_source(means3D, opacities, scales, rotations, cov3Ds_precomp, colors_precomp, sh, raster_settings)
+    if src is not None:
+        return _ReblendGaussians.apply(means3D, means2D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, src)
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                      raster_settings)
 
@@ -95,6 +198,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # the caller's own tensor objects (their .grad is the accumulation target of a fused backward)
         ctx.param_inputs = (means3D, sh, opacities, scales, rotations) if _GRAD_FUSION else None
         ctx.mark_non_differentiable(radii)
+        _remember_source(means3D, opacities, scales, rotations, cov3Ds_precomp, rs, geomBuffer, binningBuffer, imgBuffer, radii, num_rendered)
         return color, radii
 
     @staticmethod
@@ -125,6 +229,43 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations = out
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
                 grad_cov3Ds_precomp, None)
+
+
+class _ReblendGaussians(torch.autograd.Function):
+    """Second pass over the Gaussians and camera of full forward `src` with other per-Gaussian colours
+    (gstar_raster_reblend).  Same outputs and gradients as _RasterizeGaussians on the same inputs; the geometry buffer
+    and radii are the source call's.  Gradients in input order:
+    (means3D, means2D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, None, None)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, src):
+        rs = raster_settings
+        fwd_only = not any(ctx.needs_input_grad)
+        if fwd_only:
+            _C.set_forward_only(True)
+        try:
+            num_rendered, color, binningBuffer, imgBuffer = _C.rasterize_gaussians_reblend(
+                rs.bg, colors_precomp, rs.image_height, rs.image_width, src.binning, src.image, rs.debug)
+        finally:
+            if fwd_only:
+                _C.set_forward_only(False)
+        radii = src.radii.detach()  # a tensor object of this call's own (same memory)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, src.geom, binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        rs = ctx.raster_settings
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
+        out = _C.rasterize_gaussians_backward(rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                                              rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, torch.Tensor([]),
+                                              rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.debug)
+        grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, _grad_sh, grad_scales, grad_rotations = out
+        return (grad_means3D, grad_means2D, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations, grad_cov3Ds_precomp,
+                None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GSTAR_ABI_VERSION 3
+#define GSTAR_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define GSTAR_API __attribute__((visibility("default")))
@@ -130,6 +130,39 @@ typedef struct gstar_bwd_args {
 #define GSTAR_GRAD_SCRATCH_FLOATS 12
 
 GSTAR_API int gstar_raster_backward(const gstar_bwd_args* args, void* stream);
+
+/* ---- shared-geometry re-blend (no counterpart in the reference, which repeats the whole forward) ----
+ * GauSTAR rasterizes the same Gaussians from the same camera twice per training step: RGB, then depth as three equal
+ * channels through colors_precomp (gaustar_trainers/refine.py:552-564 and :607-616; refined_mesh.py:733-774 does it three
+ * times).  Preprocess, binning and the sort depend on neither colour nor background, so the second call can start from
+ * the first call's sorted record stream: gstar_raster_reblend copies it with the colour fields replaced by
+ * colors_precomp[gid] into a binning buffer of its own and runs the blend kernel.  out_color and the image buffer are
+ * what gstar_raster_forward would produce for (the source call's geometry inputs, colors_precomp, background),
+ * bit for bit.
+ *
+ * The source call is identified by its image buffer and must be one of the last 16 forward / re-blend calls made by THIS
+ * host thread on this device (their layouts are remembered on the host, so that nothing is read back from the device);
+ * otherwise GSTAR_ERR_INVALID.  The source buffers must still be alive and the work is enqueued on `stream`, which must
+ * be ordered behind the source call.  The backward of a re-blend is gstar_raster_backward with
+ *     geom_buffer    = the SOURCE call's geometry buffer (shared, read-only: positions, conics, opacities, radii),
+ *     binning_buffer / image_buffer = the ones allocated here,  colors_precomp = the colours given here,  shs = NULL,
+ *     R = the value returned here (the source call's num_rendered).
+ * forward_only != 0: no backward will follow; the new binning buffer then holds no hit log. */
+typedef struct gstar_reblend_args {
+    int P;                          /* gaussians of the source call */
+    int width, height;              /* as in the source call */
+    const float* background;        /* [3] */
+    const float* colors_precomp;    /* [P,3] the new per-gaussian colours */
+    const char* src_binning_buffer; /* the source call's binning buffer */
+    const char* src_image_buffer;   /* the source call's image buffer */
+    float* out_color;               /* [3,H,W] fully written */
+    int debug;
+    int forward_only;
+} gstar_reblend_args;
+GSTAR_API int gstar_raster_reblend(const gstar_reblend_args* args,
+                         gstar_alloc_fn binning_alloc, void* binning_user,
+                         gstar_alloc_fn image_alloc, void* image_user,
+                         void* stream /* cudaStream_t */);
 
 /* checkFrustum: present[i] = (view-space z > 0.2).  present is a byte array (C++ bool). */
 GSTAR_API int gstar_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_stage_names():
     L = capi.lib()
-    assert L.gstar_abi_version() == 3
+    assert L.gstar_abi_version() == 4
     assert [L.gstar_stage_name(i).decode() for i in range(len(capi.STAGES))] == capi.STAGES
     assert L.gstar_stage_name(99) == b""
 
@@ -96,19 +96,20 @@ def test_product_does_not_import_oracle():
 
 
 def test_ctypes_structs_match_the_header(tmp_path):
-    """The ctypes mirror of gstar_fwd_args / gstar_bwd_args (gaustar_b200/capi.py) must have the C compiler's layout of
+    """The ctypes mirror of gstar_fwd_args / gstar_bwd_args / gstar_reblend_args (gaustar_b200/capi.py) must have the C compiler's layout of
     include/gstar_raster.h: sizes and the offsets of the trailing fields (the ones that were appended over time)."""
     import ctypes
     import subprocess
     src = tmp_path / "abi.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gstar_raster.h"\nint main(void){\n'
-                   'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(gstar_fwd_args), offsetof(gstar_fwd_args, forward_only), offsetof(gstar_fwd_args, out_color),\n'
-                   '       sizeof(gstar_bwd_args), offsetof(gstar_bwd_args, accumulate_param_grads), offsetof(gstar_bwd_args, blend_grad_scratch));\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gstar_fwd_args), offsetof(gstar_fwd_args, forward_only), offsetof(gstar_fwd_args, out_color),\n'
+                   '       sizeof(gstar_bwd_args), offsetof(gstar_bwd_args, accumulate_param_grads), offsetof(gstar_bwd_args, blend_grad_scratch),\n'
+                   '       sizeof(gstar_reblend_args), offsetof(gstar_reblend_args, out_color), offsetof(gstar_reblend_args, forward_only));\n'
                    'return 0;}\n')
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    F, B = capi.FwdArgs, capi.BwdArgs
+    F, B, Rb = capi.FwdArgs, capi.BwdArgs, capi.ReblendArgs
     want = [ctypes.sizeof(F), F.forward_only.offset, F.out_color.offset, ctypes.sizeof(B), B.accumulate_param_grads.offset,
-            B.blend_grad_scratch.offset]
+            B.blend_grad_scratch.offset, ctypes.sizeof(Rb), Rb.out_color.offset, Rb.forward_only.offset]
     assert got == want, (got, want)

@@ -478,3 +478,22 @@ def test_forward_only_skips_hit_log_and_stays_exact():
         assert torch.equal(img, a["out_color"])
     finally:
         capi.set_hit_log(old)
+
+
+@pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref not built (reference sources absent at build time)")
+@pytest.mark.parametrize("shape", ["config2_200k_1080p", "config3_res_1352x1014"])
+def test_baseline_config_shapes_against_live_reference(shape):
+    """BASELINE.json configs #2 (200 k Gaussians, 1920x1080) and #3's resolution (1352x1014: 84.5 x 63.4 tiles, i.e.
+    partial tiles on both borders; 150 k Gaussians here) against the unmodified reference on the same inputs."""
+    if shape == "config2_200k_1080p":
+        d = Hh.scene_dict(scene.surface_gaussians(200000, 3, seed=0), scene.dome_cameras(16, 1920, 1080)[3])
+    else:
+        d = Hh.scene_dict(scene.surface_gaussians(150000, 3, seed=3), scene.dome_cameras(20, 1352, 1014)[7])
+    kw, fwd = run_mine(d)
+    ref = refgpu.forward(**kw)
+    rnp = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in ref.items()}
+    check_forward_against(fwd, kw, rnp, exact_image=True)
+    dpix = torch.randn(3, d["H"], d["W"], device="cuda", generator=torch.Generator("cuda").manual_seed(6)) / (d["H"] * d["W"])
+    mine = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
+    rg = refgpu.backward(ref, dpix, **Hh.bwd_kwargs(kw))
+    check_grads(mine, {k: v.cpu().numpy() for k, v in rg.items()}, per_key=LIVE_REF_TOL)
