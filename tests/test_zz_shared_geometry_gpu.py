@@ -73,7 +73,9 @@ def test_reblend_rejects_unknown_source_and_size_mismatch():
     kw, first = run_mine(d)
     col = depth_colors(kw)
     stale = dict(first)
-    stale["image"] = first["image"].clone()  # same bytes at another address: not a call this thread made
+    # same bytes at an address no call of this thread ever used (256 bytes into a fresh allocation: torch's allocations
+    # start on 512-byte boundaries, so this cannot be a recycled image buffer either)
+    stale["image"] = torch.cat([torch.zeros(256, dtype=torch.uint8, device="cuda"), first["image"]])[256:]
     with pytest.raises(capi.GstarError):
         capi.reblend(stale, col, kw["bg"], kw["W"], kw["H"])
     with pytest.raises(capi.GstarError):
