@@ -63,6 +63,34 @@ def timed(shared):
     return e0.elapsed_time(e1) / a.views, {k: q.grad.clone() for k, q in params.items()}
 
 
+def timed_inference(shared, passes=3):
+    """refined_mesh.py:733-774: three forward-only renders of one camera (RGB through SH, then two colors_precomp passes)."""
+    p = {k: v.detach() for k, v in params.items()}
+    cols = [torch.rand(g.P, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(100 + i)) for i in range(passes - 1)]
+
+    def view(v):
+        c = camkw[v % len(camkw)]
+        with torch.no_grad(), (dgr.shared_geometry() if shared else contextlib.nullcontext()):
+            outs = [dgr.GaussianRasterizer(settings(c, bg1, 3))(means3D=p["means3D"], means2D=torch.zeros_like(p["means3D"]), opacities=p["opacities"],
+                                                               shs=p["shs"], scales=p["scales"], rotations=p["rotations"])[0]]
+            for col in cols:
+                outs.append(dgr.GaussianRasterizer(settings(c, bg2, 0))(means3D=p["means3D"], means2D=torch.zeros_like(p["means3D"]),
+                                                                       opacities=p["opacities"], colors_precomp=col, scales=p["scales"],
+                                                                       rotations=p["rotations"])[0])
+        return outs
+
+    for v in range(3):
+        view(v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for v in range(a.views):
+        outs = view(v)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / a.views, outs
+
+
 full_ms, g_full = timed(False)
 shared_ms, g_shared = timed(True)
 full_ms2, _ = timed(False)
@@ -70,6 +98,10 @@ rel = {k: float((g_shared[k] - g_full[k]).abs().max() / (g_full[k].abs().max() +
 res = dict(workload=f"surface P={g.P} {a.W}x{a.H} SH3: RGB pass + depth pass (colors_precomp) + one backward through both, per view",
            views=a.views, two_full_calls_ms_per_view=round(min(full_ms, full_ms2), 4), shared_geometry_ms_per_view=round(shared_ms, 4),
            speedup=round(min(full_ms, full_ms2) / shared_ms, 4), grad_rel_diff_accumulated_over_views=rel, device=torch.cuda.get_device_name(0))
+inf_full, o_full = timed_inference(False)
+inf_shared, o_shared = timed_inference(True)
+res["inference_3_passes"] = dict(three_full_calls_ms_per_view=round(inf_full, 4), shared_geometry_ms_per_view=round(inf_shared, 4),
+                                 speedup=round(inf_full / inf_shared, 4), images_identical=bool(all(torch.equal(x, y) for x, y in zip(o_full, o_shared))))
 print(json.dumps(res))
 if a.out:
     with open(a.out, "w") as f:
