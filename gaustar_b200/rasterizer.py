@@ -112,8 +112,21 @@ def _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs):
 
 
 def _geom_key(tensors, rs, dev):
+    stream = torch.cuda.current_stream(dev).cuda_stream if torch.device(dev).type == "cuda" else 0
     return (tuple(_tkey(t) for t in tensors), int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
-            float(rs.scale_modifier), bool(rs.prefiltered), torch.cuda.current_stream(dev).cuda_stream)
+            float(rs.scale_modifier), bool(rs.prefiltered), stream)
+
+
+def _reblend_allowed(key, src_key, scope_active: bool, cache_on: bool) -> bool:
+    """May a call with geometry key `key` re-blend the remembered call `src_key`?  (pure host logic)
+    Outside a shared_geometry() block: only with the cache on and IDENTICAL keys (same memory, same versions, same sizes,
+    scalars and stream).  Inside a block the caller vouches for the values: sizes, scalars, stream and every tensor's
+    presence / shape / device / dtype must still agree -- anything else is a different configuration, i.e. a full forward."""
+    if not scope_active:
+        return cache_on and key == src_key
+    if key[1:] != src_key[1:]:
+        return False
+    return all((a is None) == (b is None) and (a is None or a[2:] == b[2:]) for a, b in zip(key[0], src_key[0]))
 
 
 def _remember_source(means3D, opacities, scales, rotations, cov3Ds_precomp, rs, geom, binning, image, radii, num_rendered):
@@ -138,12 +151,9 @@ def _matching_source(means3D, opacities, scales, rotations, cov3Ds_precomp, colo
     tensors = _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs)
     key = _geom_key(tensors, rs, means3D.device)
     scope = getattr(_tls, "scope", None)
-    if scope is None:
-        return src if (_GEOM_CACHE and key == src.key) else None
-    # asserted by the caller: shapes, sizes and scalars must still agree (a different configuration is a full forward)
-    if key[1:] != src.key[1:] or any((a is None) != (b is None) or (a is not None and (a[2:] != b[2:])) for a, b in zip(key[0], src.key[0])):
+    if not _reblend_allowed(key, src.key, scope is not None, _GEOM_CACHE):
         return None
-    if scope["check"]:
+    if scope is not None and scope["check"]:
         for name, a, b in zip(("means3D", "opacities", "scales", "rotations", "cov3D_precomp", "viewmatrix", "projmatrix"), tensors, src.tensors):
             if a.numel() and not torch.equal(a.to(b.device), b):
                 raise RuntimeError(f"shared_geometry(check=True): `{name}` differs from the first call of the block")

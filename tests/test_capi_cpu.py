@@ -113,3 +113,40 @@ def test_ctypes_structs_match_the_header(tmp_path):
     want = [ctypes.sizeof(F), F.forward_only.offset, F.out_color.offset, ctypes.sizeof(B), B.accumulate_param_grads.offset,
             B.blend_grad_scratch.offset, ctypes.sizeof(Rb), Rb.out_color.offset, Rb.forward_only.offset]
     assert got == want, (got, want)
+
+
+def test_shared_geometry_host_logic():
+    """Which calls may re-blend a remembered forward (gaustar_b200/rasterizer.py) -- the decision is pure host
+    logic over (data_ptr, _version, shape, device, dtype) keys and is checked here without a GPU."""
+    import torch
+    from gaustar_b200 import rasterizer as R
+    P = 10
+    mk = lambda: (torch.rand(P, 3), torch.rand(P, 1), torch.rand(P, 3), torch.rand(P, 4), torch.Tensor([]), torch.eye(4), torch.eye(4))
+    rs = R.GaussianRasterizationSettings(32, 48, 0.5, 0.6, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3), False, False)
+    t = mk()
+    k0 = R._geom_key(t, rs, "cpu")
+    # the cache: identity only
+    assert R._reblend_allowed(R._geom_key(t, rs, "cpu"), k0, False, True)
+    assert not R._reblend_allowed(R._geom_key(t, rs, "cpu"), k0, False, False)  # cache off
+    clone = tuple(x.clone() for x in t)
+    assert not R._reblend_allowed(R._geom_key(clone, rs, "cpu"), k0, False, True)  # equal values, other memory
+    t[0].add_(1.0)  # an optimizer step: same memory, new version
+    assert not R._reblend_allowed(R._geom_key(t, rs, "cpu"), k0, False, True)
+    # inside shared_geometry(): the caller vouches for the values, the configuration must still agree
+    assert R._reblend_allowed(R._geom_key(clone, rs, "cpu"), k0, True, False)
+    assert not R._reblend_allowed(R._geom_key(clone, rs._replace(image_width=64), "cpu"), k0, True, False)
+    assert not R._reblend_allowed(R._geom_key(clone, rs._replace(scale_modifier=0.5), "cpu"), k0, True, False)
+    fewer = tuple(x[:-1].clone() if x.dim() == 2 and x.shape[0] == P else x for x in clone)
+    assert not R._reblend_allowed(R._geom_key(fewer, rs, "cpu"), k0, True, False)
+    cov = clone[:2] + (torch.Tensor([]), torch.Tensor([]), torch.rand(P, 6)) + clone[5:]  # cov3D_precomp instead of scales/rotations
+    assert not R._reblend_allowed(R._geom_key(cov, rs, "cpu"), k0, True, False)
+    # the block clears what it remembered on both ends, and nests
+    R._tls.src = "stale"
+    with R.shared_geometry():
+        assert R._tls.src is None and R._tls.scope == {"check": False}
+        with R.shared_geometry(check=True):
+            assert R._tls.scope == {"check": True}
+        assert R._tls.scope == {"check": False}
+        R._tls.src = "inside"
+    assert R._tls.src is None and R._tls.scope is None
+    assert R.set_geometry_cache(True) in (False, True) and R.set_geometry_cache(False) is True

@@ -15,6 +15,7 @@ ap.add_argument("--P", type=int, default=1000000)
 ap.add_argument("--W", type=int, default=1920)
 ap.add_argument("--H", type=int, default=1080)
 ap.add_argument("--views", type=int, default=12)
+ap.add_argument("--passes", type=int, default=2, help="feature passes per view in the training step (config #5: 3 = RGB, depth, normal)")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 
@@ -27,6 +28,7 @@ bg1 = torch.tensor([0., 1., 0.], device="cuda")
 bg2 = torch.full((3,), 10.0, device="cuda")
 target = torch.rand(3, a.H, a.W, device="cuda")
 dtarget = torch.rand(a.H, a.W, device="cuda") * 5
+center = torch.tensor([0.0, 1.0, 0.0], device="cuda")
 
 
 def settings(c, bg, deg):
@@ -43,7 +45,15 @@ def step(v, shared):
         dimg, _ = dgr.GaussianRasterizer(settings(c, bg2, 0))(means3D=p["means3D"], means2D=torch.zeros_like(p["means3D"], requires_grad=True),
                                                              opacities=p["opacities"], colors_precomp=depth, scales=p["scales"],
                                                              rotations=p["rotations"])
+        extra = []
+        for _k in range(a.passes - 2):  # config #5's third pass: a per-Gaussian direction as colour (normal xyz)
+            nrm = torch.nn.functional.normalize(p["means3D"] - center, dim=-1)
+            extra.append(dgr.GaussianRasterizer(settings(c, bg1, 0))(means3D=p["means3D"], means2D=torch.zeros_like(p["means3D"], requires_grad=True),
+                                                                    opacities=p["opacities"], colors_precomp=nrm, scales=p["scales"],
+                                                                    rotations=p["rotations"])[0])
     loss = (img - target).abs().mean() + (dimg[0] - dtarget).abs().mean()
+    for e in extra:
+        loss = loss + (e - target).abs().mean()
     loss.backward()
     return loss
 
@@ -95,8 +105,8 @@ full_ms, g_full = timed(False)
 shared_ms, g_shared = timed(True)
 full_ms2, _ = timed(False)
 rel = {k: float((g_shared[k] - g_full[k]).abs().max() / (g_full[k].abs().max() + 1e-30)) for k in g_full}
-res = dict(workload=f"surface P={g.P} {a.W}x{a.H} SH3: RGB pass + depth pass (colors_precomp) + one backward through both, per view",
-           views=a.views, two_full_calls_ms_per_view=round(min(full_ms, full_ms2), 4), shared_geometry_ms_per_view=round(shared_ms, 4),
+res = dict(workload=f"surface P={g.P} {a.W}x{a.H} SH3: {a.passes} feature passes (RGB through SH, then colors_precomp) + one backward through all, per view",
+           views=a.views, full_calls_ms_per_view=round(min(full_ms, full_ms2), 4), shared_geometry_ms_per_view=round(shared_ms, 4),
            speedup=round(min(full_ms, full_ms2) / shared_ms, 4), grad_rel_diff_accumulated_over_views=rel, device=torch.cuda.get_device_name(0))
 inf_full, o_full = timed_inference(False)
 inf_shared, o_shared = timed_inference(True)
