@@ -7,6 +7,9 @@ gaussian_splatting/submodules/diff-gaussian-rasterization), so that
 ``gaussian_splatting/gaussian_renderer/__init__.py:36-93`` run unchanged.  All
 compute happens in ``_C`` (gaustar_b200/csrc/torch_ext.cpp -> C ABI -> CUDA).
 """
+import contextlib
+import os
+import threading
 from typing import NamedTuple
 
 import torch
@@ -64,10 +67,6 @@ def _fusable(t, needs):
 #                              (device->host syncs; for debugging).
 # Off by default: the source call's buffers (geometry, binning incl. hit log, image) stay alive until the next full
 # forward replaces them.
-import contextlib
-import os
-import threading
-
 _GEOM_CACHE = os.environ.get("GSTAR_GEOM_CACHE", "0") not in ("", "0")
 _tls = threading.local()
 
