@@ -121,13 +121,15 @@ struct StageScope {
     }
 };
 
-int get_ctx(DevCtx** out)
+int get_ctx(DevCtx** out, bool capturing = false)
 {
     int dev = 0;
     CU_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_DEV) return fail(GSTAR_ERR_INVALID, "device index out of range");
     DevCtx& c = t_ctx[dev];
     if (!c.inited) {
+        if (capturing)  // pinned allocation / event creation / function attributes are not legal inside a capture
+            return fail(GSTAR_ERR_INVALID, "the first call of a thread on a device must not be captured into a CUDA graph");
         CU_OK(cudaHostAlloc((void**)&c.host_counts, 64, cudaHostAllocMapped));
         memset(c.host_counts, 0, 64);
         CU_OK(cudaHostGetDevicePointer((void**)&c.host_counts_dev, c.host_counts, 0));
@@ -242,9 +244,20 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     if (!a->cov3D_precomp && (!a->scales || !a->rotations))
         return fail(GSTAR_ERR_INVALID, "provide scales+rotations or cov3D_precomp");
     if (a->width > 32767 || a->height > 32767) return fail(GSTAR_ERR_INVALID, "image larger than 32767 pixels");
+    // CUDA-graph capture: while `stream` is being captured the forward stays entirely on the device -- no
+    // event wait, no read of the instance count.  The binning buffer then has the size the earlier un-captured calls of
+    // this thread provisioned, the return value is that capacity (an upper bound of num_rendered, good for the matching
+    // backward), and a replay whose view needs more leaves the header's overflow flag set (gstar_debug_header) and the
+    // outputs untouched by the later kernels.
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    CU_OK(cudaStreamIsCapturing(stream, &cap_status));
+    const bool capturing = cap_status != cudaStreamCaptureStatusNone;
+    if (capturing && a->debug) return fail(GSTAR_ERR_INVALID, "debug mode synchronizes the device: not available while capturing a CUDA graph");
     DevCtx* ctx;
-    int rc = get_ctx(&ctx);
+    int rc = get_ctx(&ctx, capturing);
     if (rc < 0) return rc;
+    if (capturing && !(ctx->have_estimate && ctx->estimate >= 1.0))
+        return fail(GSTAR_ERR_INVALID, "a captured forward takes its instance capacity from earlier un-captured calls of this thread: run one first");
 
     const int W = a->width, H = a->height;
     const int gx = (W + GSTAR_TILE - 1) / GSTAR_TILE, gy = (H + GSTAR_TILE - 1) / GSTAR_TILE;
@@ -345,7 +358,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             StageScope sc(GSTAR_STAGE_TILE_SCAN, stream);
             launch_tile_scan(bp, stream);
         }
-        CU_OK(cudaEventRecord(ctx->scan_done, stream));
+        if (!capturing) CU_OK(cudaEventRecord(ctx->scan_done, stream));
         STAGE_CHECK("tile_scan");
         if (cap > 0) {
             {
@@ -363,6 +376,10 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
                 launch_blend_fwd(bl, stream);
             }
             STAGE_CHECK("blend_fwd");
+        }
+        if (capturing) {
+            R = (uint32_t)cap;
+            break;
         }
         // everything is enqueued; only now wait for the scan result (the GPU keeps working)
         CU_OK(cudaEventSynchronize(ctx->scan_done));

@@ -77,7 +77,13 @@ typedef struct gstar_fwd_args {
                                   * these buffers is still correct (it takes the walk-back kernel) */
 } gstar_fwd_args;
 
-/* Forward pass.  Returns num_rendered (sum of tiles touched), exactly like Rasterizer::forward. */
+/* Forward pass.  Returns num_rendered (sum of tiles touched), exactly like Rasterizer::forward.
+ * CUDA graphs: if `stream` is being captured, nothing is waited for or read back on the host; the binning
+ * buffer gets the capacity that earlier un-captured calls of this thread provisioned (at least one such call is
+ * required; it also performs the one-time setup that is illegal inside a capture), the return value is that capacity
+ * -- an upper bound of num_rendered, valid as `R` of the matching backward -- and a replay whose view needs more
+ * instances leaves the overflow flag of its header set (gstar_debug_header) instead of growing the buffer.  debug != 0
+ * is rejected while capturing.  gstar_raster_backward and gstar_raster_reblend never touch the host and capture as is. */
 GSTAR_API int gstar_raster_forward(const gstar_fwd_args* args,
                          gstar_alloc_fn geom_alloc, void* geom_user,
                          gstar_alloc_fn binning_alloc, void* binning_user,

@@ -1,5 +1,4 @@
-# round-1 evidence run (gpurun): GPU tests, two-pass tool at the headline shape, three feature passes at config #5's shape
+# round-1 evidence run (gpurun): GPU tests (incl. CUDA-graph capture), bench
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/r1u_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r1u_pytest.log; tail -4 gpurun_out/r1u_pytest.log
-timeout 150 python tools/two_pass_times.py --out gpurun_out/r1u_two_pass.json > gpurun_out/r1u_two_pass.log 2>&1; tail -1 gpurun_out/r1u_two_pass.log
-timeout 250 python tools/two_pass_times.py --P 4000000 --W 3840 --H 2160 --views 6 --passes 3 --out gpurun_out/r1u_config5_three_pass.json > gpurun_out/r1u_config5.log 2>&1; tail -2 gpurun_out/r1u_config5.log
+python -m pytest tests -m gpu -q > gpurun_out/r1v_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r1v_pytest.log; tail -30 gpurun_out/r1v_pytest.log
+timeout 200 python bench.py > gpurun_out/r1v_bench_ours.json 2> gpurun_out/r1v_bench_ours.err; head -c 250 gpurun_out/r1v_bench_ours.json; echo
