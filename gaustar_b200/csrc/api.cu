@@ -468,8 +468,8 @@ int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_all
     GHeader* hdr = (GHeader*)(img + IL.hdr);
     {
         StageScope sc(GSTAR_STAGE_TILE_SORT, stream);  // takes the place of preprocess .. sort
-        launch_recolor((const unsigned char*)src_bin + BL.packed, (unsigned char*)bin + BL.packed, (uint32_t)R, a->colors_precomp, hdr,
-                       a->forward_only ? 1 : 0, stream);
+        launch_recolor((const unsigned char*)src_bin + BL.packed, (unsigned char*)bin + BL.packed, (uint32_t*)(bin + BL.point_list), (uint32_t)R,
+                       a->colors_precomp, hdr, a->forward_only ? 1 : 0, stream);
     }
     STAGE_CHECK("recolor");
     BlendParams bl;

@@ -648,10 +648,10 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
 // colours (GauSTAR renders RGB, then depth as three equal channels: refine.py:552-564 / :607-616).  Everything the first
 // pass computed up to and including the sort is reused; only the colour fields of the blend-order records change.  One
 // thread per instance streams its 48-byte record from the first pass's packed stream into the new one with r,g,b taken
-// from colors[gid] (what preprocess_fwd stores for colors_precomp, forward.cu:241-248 skipped).  HBM: 96 B per instance
+// from colors[gid] (what preprocess_fwd stores for colors_precomp, forward.cu:241-248 skipped).  HBM: 100 B per instance
 // + an L2-resident gather of 12 B per instance.
-__global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src, float4* __restrict__ dst, uint32_t R, const float* __restrict__ colors,
-                                                 GHeader* hdr, int disable_log)
+__global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src, float4* __restrict__ dst, uint32_t* __restrict__ dst_point_list,
+                                                 uint32_t R, const float* __restrict__ colors, GHeader* hdr, int disable_log)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && disable_log) hdr->log_overflow = 1u;  // inference re-blend: no hit log (the new binning buffer has none)
@@ -659,16 +659,18 @@ __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src,
     const float4 a = ldg_nc_f4(src + (size_t)i * 3);
     float4 b = ldg_nc_f4(src + (size_t)i * 3 + 1);
     float4 c = ldg_nc_f4(src + (size_t)i * 3 + 2);
-    const float* col = colors + (size_t)__float_as_uint(c.y) * 3;  // c = (foot, gid, b, slot)
+    const uint32_t gid = __float_as_uint(c.y);  // c = (foot, gid, b, slot)
+    const float* col = colors + (size_t)gid * 3;
+    dst_point_list[i] = gid;  // the new binning buffer is a complete BinningState (the sorted value list, rasterizer_impl.h:58-68)
     b.z = __ldg(col); b.w = __ldg(col + 1); c.z = __ldg(col + 2);
     dst[(size_t)i * 3] = a; dst[(size_t)i * 3 + 1] = b; dst[(size_t)i * 3 + 2] = c;
 }
-void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t R, const float* colors, GHeader* hdr, int disable_log,
-                    cudaStream_t s)
+void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
+                    int disable_log, cudaStream_t s)
 {
     const uint32_t n = R > 0u ? R : 1u;  // at least one thread: the header patch
-    k_recolor<<<(n + 255u) / 256u, 256, 0, s>>>(reinterpret_cast<const float4*>(src_packed), reinterpret_cast<float4*>(dst_packed), R, colors, hdr,
-                                                disable_log);
+    k_recolor<<<(n + 255u) / 256u, 256, 0, s>>>(reinterpret_cast<const float4*>(src_packed), reinterpret_cast<float4*>(dst_packed), dst_point_list, R, colors,
+                                                hdr, disable_log);
 }
 
 int blend_setup() { return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM); }

@@ -114,9 +114,9 @@ int  blend_setup();
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s);
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s);         // walk-back path (no hit log)
 void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s);  // instance-parallel path over the hit log
-// re-blend (shared geometry): copy the packed stream with the colour fields replaced by colors[gid]; optionally switch the
-// new header's hit log off
-void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t R, const float* colors, GHeader* hdr, int disable_log,
-                    cudaStream_t s);
+// re-blend (shared geometry): copy the packed stream with the colour fields replaced by colors[gid] and rebuild the sorted
+// value list from the records' ids; optionally switch the new header's hit log off
+void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
+                    int disable_log, cudaStream_t s);
 
 }  // namespace gstar

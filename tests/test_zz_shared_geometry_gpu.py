@@ -15,7 +15,9 @@ import torch
 from gaustar_b200 import capi
 
 import helpers as Hh
-from test_parity_gpu import GRAD_TOL, LIVE_REF_TOL, SCENES, backward_path, check_grads, run_mine  # noqa: F401 (backward_path: autouse fixture)
+from oracle import oracle as O
+from test_parity_gpu import (GRAD_TOL, LIVE_REF_TOL, SCENES, backward_path, check_forward_against, check_grads,  # noqa: F401
+                             run_mine)  # backward_path: autouse fixture
 
 pytestmark = pytest.mark.gpu
 
@@ -66,6 +68,30 @@ def test_reblend_equals_full_forward_through_the_c_abi(name, backward_path):
     torch.cuda.synchronize()
     assert torch.equal(rb3["out_color"], full3["out_color"])
     assert not capi.hit_log_state(rb3)[2]
+
+
+def test_reblend_against_the_cpu_oracle():
+    """Independent check: the re-blended second pass (first pass: SH colours) against the CPU oracle run on
+    (same geometry, colors_precomp, other background) -- intermediates, sorted list, image and gradients."""
+    d = SCENES["surface_sh3"]()
+    kw, first = run_mine(d)
+    W, H, P = kw["W"], kw["H"], kw["means3D"].shape[0]
+    rng = np.random.default_rng(9)
+    col = rng.uniform(0, 1, (P, 3)).astype(np.float32)
+    d2 = {k: v for k, v in d.items() if k not in ("shs", "sh_degree")}
+    d2.update(colors_precomp=col, bg=np.array([10.0, 10.0, 10.0], np.float32), sh_degree=0)  # refine.py:609: the depth pass's background
+    kw2 = Hh.to_torch_kwargs(d2)
+    rb = capi.reblend(first, kw2["colors_precomp"], kw2["bg"], W, H)
+    torch.cuda.synchronize()
+    inp = Hh.oracle_inputs_from_dict(d2)
+    of = O.forward(inp)
+    _, st = check_forward_against(rb, kw2, dict(of.__dict__), exact_image=False, n_contrib_slack=max(2, W * H // 20000))
+    dpix = rng.normal(0, 1, (3, H, W)).astype(np.float32)
+    mine = capi.backward(rb, torch.from_numpy(dpix).cuda(), **Hh.bwd_kwargs(kw2))
+    torch.cuda.synchronize()
+    of.n_contrib = st["n_contrib"].astype(np.uint32)
+    of.final_T = st["final_T"].copy()
+    check_grads(mine, O.backward(inp, of, dpix).__dict__)
 
 
 def test_reblend_rejects_unknown_source_and_size_mismatch():
