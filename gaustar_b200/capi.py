@@ -53,6 +53,7 @@ class BwdArgs(C.Structure):
         ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dcolor", C.c_void_p),
         ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p), ("blend_grad_scratch", C.c_void_p), ("debug", C.c_int), ("accumulate_param_grads", C.c_int),
+        ("blend_only", C.c_int),
     ]
 
 
@@ -180,8 +181,11 @@ def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False):
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,
-             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None, lean=False):
+             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None, lean=False,
+             scratch=None):
     """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts).
+    scratch: optional [P,12] moment buffer pre-loaded by blend_moments() calls of other passes over the same geometry (the
+    per-Gaussian stage then serves all of them at once); default: a fresh zero-filled one.
     lean: do not materialise the intermediates dL_dconic and -- for inputs that were not given -- dL_dcolors / dL_dcov3D
     (NULL in the C ABI; the dict then holds empty tensors for them).
     accumulate_into: optional dict with dL_dmeans3D/dL_dscales/dL_drotations/dL_dopacity/dL_dsh tensors; the
@@ -207,7 +211,9 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
             t = accumulate_into[k]
             assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == g[k].numel(), k
             g[k] = t
-    scratch = torch.zeros(P, 12, dtype=torch.float32, device=dev)
+    if scratch is None:
+        scratch = torch.zeros(P, 12, dtype=torch.float32, device=dev)
+    assert scratch.shape == (P, 12) and scratch.dtype == torch.float32 and scratch.is_contiguous()
     a = BwdArgs(P, sh_degree, M, int(fwd["num_rendered"]), _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(sc), scale_modifier, _ptr(rot),
                 _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]), _ptr(fwd["binning"]),
                 _ptr(fwd["image"]), _ptr(dpix), _ptr(g["dL_dmeans2D"]), _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolors"]),
@@ -217,6 +223,26 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
         _check(L.gstar_raster_backward(C.byref(a), _stream(dev)))
     g["_keep"] = keep + [scratch]
     return g
+
+
+def blend_moments(fwd, dL_dout_color, bg, scratch):
+    """gstar_raster_backward with blend_only=1: ADD the raw blend-stage moments of pass `fwd` (a forward or re-blend result)
+    into `scratch` [P,12]; columns 6..8 are then this pass's dL_dcolors, columns 0..5 the geometric moments that add over
+    the passes of one view.  Nothing else is computed."""
+    L = lib()
+    dev = scratch.device
+    keep = [_f32(dL_dout_color, dev), _f32(bg, dev)]
+    dpix, bgc = keep
+    P = scratch.shape[0]
+    assert scratch.shape == (P, 12) and scratch.dtype == torch.float32 and scratch.is_contiguous()
+    a = BwdArgs()
+    a.P, a.R, a.width, a.height = P, int(fwd["num_rendered"]), dpix.shape[2], dpix.shape[1]
+    a.background, a.dL_dpix, a.blend_grad_scratch = _ptr(bgc), _ptr(dpix), _ptr(scratch)
+    a.radii, a.geom_buffer, a.binning_buffer, a.image_buffer = _ptr(fwd["radii"]), _ptr(fwd["geom"]), _ptr(fwd["binning"]), _ptr(fwd["image"])
+    a.blend_only = 1
+    with torch.cuda.device(dev):
+        _check(L.gstar_raster_backward(C.byref(a), _stream(dev)))
+    return keep
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -523,6 +523,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         }
         STAGE_CHECK("blend_bwd");
     }
+    if (a->blend_only) return 0;  // the moments stay in the scratch for the full backward of another pass over this geometry
     PreBwdParams pb;
     pb.P = a->P; pb.D = a->D; pb.M = a->M; pb.W = W; pb.H = H;
     pb.means3D = a->means3D; pb.scales = a->scales; pb.scale_modifier = a->scale_modifier; pb.rotations = a->rotations;

@@ -142,7 +142,8 @@ static BwdTuple backward_impl(const torch::Tensor& background, const torch::Tens
                               const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
                               const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& sh,
                               const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
-                              const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const FusedTargets* fused);
+                              const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const FusedTargets* fused,
+                              const torch::Tensor* preloaded_scratch = nullptr);
 
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
 RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
@@ -190,7 +191,7 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
               const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
               const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
               const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
-              const bool debug, const FusedTargets* fused)
+              const bool debug, const FusedTargets* fused, const torch::Tensor* preloaded_scratch)
 {
     TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
     const torch::Device dev = means3D.device();
@@ -216,7 +217,7 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
     torch::Tensor dL_dscales = fused ? fused->scales : torch::empty({P, 3}, opts);
     torch::Tensor dL_drotations = fused ? fused->rotations : torch::empty({P, 4}, opts);
     if (P != 0) {
-        torch::Tensor scratch = torch::zeros({P, GSTAR_GRAD_SCRATCH_FLOATS}, opts);
+        torch::Tensor scratch = preloaded_scratch ? *preloaded_scratch : torch::zeros({P, GSTAR_GRAD_SCRATCH_FLOATS}, opts);
         const torch::Tensor bg = prep(background, dev), m3 = prep(means3D, dev), col = prep(colors, dev), sc = prep(scales, dev),
                             rot = prep(rotations, dev), cov = prep(cov3D_precomp, dev), vm = prep(viewmatrix, dev),
                             pm = prep(projmatrix, dev), shc = prep(sh, dev), cp = prep(campos, dev), dpix = prep(dL_dout_color, dev);
@@ -241,9 +242,61 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
         a.blend_grad_scratch = scratch.data_ptr<float>();
         a.debug = debug ? 1 : 0;
         a.accumulate_param_grads = fused ? 1 : 0;
+        a.blend_only = 0;
         check(gstar_raster_backward(&a, stream));
     }
     return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
+}
+
+static void check_scratch(const torch::Tensor& scratch, const torch::Tensor& like, int64_t P)
+{
+    TORCH_CHECK(scratch.is_cuda() && scratch.device() == like.device() && scratch.scalar_type() == torch::kFloat32 && scratch.is_contiguous() &&
+                    scratch.dim() == 2 && scratch.size(0) == P && scratch.size(1) == GSTAR_GRAD_SCRATCH_FLOATS,
+                "gaustar_b200: the moment scratch must be a contiguous float32 CUDA tensor of shape (P, 12)");
+}
+
+// Several feature passes over one geometry (gstar_bwd_args.blend_only): ADD the blend-stage moments of one pass into
+// `scratch` (P x 12); nothing else is computed.  Columns 6..8 are then that pass's dL_dcolors.
+void BlendBackwardCUDA(const torch::Tensor& background, const torch::Tensor& dL_dout_color, const torch::Tensor& radii,
+                       const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+                       torch::Tensor scratch, const bool debug)
+{
+    TORCH_CHECK(dL_dout_color.is_cuda() && dL_dout_color.dim() == 3, "gaustar_b200: dL_dout_color must be a CUDA tensor of shape (3, H, W)");
+    const torch::Device dev = dL_dout_color.device();
+    c10::cuda::CUDAGuard guard(dev);
+    const int64_t P = scratch.size(0);
+    check_scratch(scratch, dL_dout_color, P);
+    if (P == 0) return;
+    const torch::Tensor bg = prep(background, dev), dpix = prep(dL_dout_color, dev);
+    const torch::Tensor rad = radii.contiguous(), gb = geomBuffer.contiguous(), bb = binningBuffer.contiguous(), ib = imageBuffer.contiguous();
+    gstar_bwd_args a = {};
+    a.P = (int)P; a.R = R;
+    a.background = fptr(bg); a.width = (int)dL_dout_color.size(2); a.height = (int)dL_dout_color.size(1);
+    a.radii = rad.data_ptr<int>();
+    a.geom_buffer = reinterpret_cast<char*>(gb.data_ptr());
+    a.binning_buffer = bb.numel() ? reinterpret_cast<char*>(bb.data_ptr()) : nullptr;
+    a.image_buffer = reinterpret_cast<char*>(ib.data_ptr());
+    a.dL_dpix = fptr(dpix);
+    a.blend_grad_scratch = scratch.data_ptr<float>();
+    a.debug = debug ? 1 : 0;
+    a.blend_only = 1;
+    check(gstar_raster_backward(&a, c10::cuda::getCurrentCUDAStream(dev.index()).stream()));
+}
+
+// The full backward of one pass on a scratch that blend-only calls of other passes pre-loaded (same 21 arguments as
+// rasterize_gaussians_backward + the scratch).
+BwdTuple RasterizeGaussiansBackwardPreloadedCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                                                 const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                                 const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                                 const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                                                 const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree,
+                                                 const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                                                 const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug,
+                                                 torch::Tensor scratch)
+{
+    check_scratch(scratch, means3D, means3D.size(0));
+    return backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                         tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, nullptr, &scratch);
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix)
@@ -267,6 +320,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("rasterize_gaussians_backward_fused", &RasterizeGaussiansBackwardFusedCUDA);
     m.def("rasterize_gaussians_reblend", &ReblendGaussiansCUDA);
+    m.def("rasterize_gaussians_blend_backward", &BlendBackwardCUDA);
+    m.def("rasterize_gaussians_backward_preloaded", &RasterizeGaussiansBackwardPreloadedCUDA);
     m.def("mark_visible", &markVisible);
     m.def("set_forward_only", &set_forward_only);
 }

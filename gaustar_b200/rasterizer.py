@@ -277,6 +277,77 @@ class _ReblendGaussians(torch.autograd.Function):
                 None, None)
 
 
+class _RasterizePasses(torch.autograd.Function):
+    """ONE autograd node for several feature passes over the same Gaussians and camera (config #5: RGB through SH, depth,
+    normals): a full forward for the first pass, a re-blend per extra (colours, background) pair, and a backward whose
+    per-Gaussian stage (cov2D / projection / SH / cov3D, backward.cu:144-396) runs ONCE for all passes -- the six
+    geometric blend moments of the passes add, the three colour moments of an extra pass are its dL_dcolors
+    (gstar_bwd_args.blend_only).  Inputs: the nine of _RasterizeGaussians, a tuple of backgrounds, then the extra colour
+    tensors.  Outputs: (color, radii, *extra_images).  dL_dmeans2D is the sum over the passes."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, extra_bgs,
+                *extra_colors):
+        rs = raster_settings
+        args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix,
+                rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered,
+                rs.debug)
+        fwd_only = not any(ctx.needs_input_grad) and not rs.debug
+        if fwd_only:
+            _C.set_forward_only(True)
+        try:
+            num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+            extras, bufs = [], []
+            for bg_k, col_k in zip(extra_bgs, extra_colors):
+                if means3D.shape[0] == 0:
+                    extras.append(torch.zeros_like(color))
+                    continue
+                _, img_k, bin_k, ib_k = _C.rasterize_gaussians_reblend(bg_k, col_k, rs.image_height, rs.image_width, binningBuffer, imgBuffer,
+                                                                       rs.debug)
+                extras.append(img_k)
+                bufs += [bin_k, ib_k]
+        finally:
+            if fwd_only:
+                _C.set_forward_only(False)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.extra_bgs = tuple(extra_bgs)
+        ctx.set_materialize_grads(False)  # an extra image nobody differentiated costs no backward pass
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, *bufs)
+        ctx.mark_non_differentiable(radii)
+        return (color, radii, *extras)
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, *grad_extras):
+        rs = ctx.raster_settings
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, *bufs = ctx.saved_tensors
+        P = means3D.shape[0]
+        n_extra = len(ctx.extra_bgs)
+        extra_grads = [None] * n_extra
+        if grad_out_color is None:
+            grad_out_color = torch.zeros(3, rs.image_height, rs.image_width, dtype=torch.float32, device=means3D.device)
+        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix,
+                rs.tanfovx, rs.tanfovy, grad_out_color, sh, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer,
+                rs.debug)
+        if P == 0:
+            out = _C.rasterize_gaussians_backward(*args)
+            extra_grads = [torch.zeros(0, 3, device=means3D.device) if ctx.needs_input_grad[10 + k] else None for k in range(n_extra)]
+        else:
+            scratch = torch.zeros(P, 12, dtype=torch.float32, device=means3D.device)
+            for k, g_k in enumerate(grad_extras):
+                if g_k is None:
+                    continue
+                _C.rasterize_gaussians_blend_backward(ctx.extra_bgs[k], g_k, radii, geomBuffer, ctx.num_rendered, bufs[2 * k], bufs[2 * k + 1],
+                                                      scratch, rs.debug)
+                if ctx.needs_input_grad[10 + k]:
+                    extra_grads[k] = scratch[:, 6:9].clone()
+                scratch[:, 6:9].zero_()  # the colour moments are per pass; the geometric ones (columns 0..5) add
+            out = _C.rasterize_gaussians_backward_preloaded(*args, scratch)
+        grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations = out
+        return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
+                grad_cov3Ds_precomp, None, None, *extra_grads)
+
+
 class GaussianRasterizationSettings(NamedTuple):
     """DGR/__init__.py:157-169 -- field order is part of the contract (callers build it by keyword)."""
     image_height: int
@@ -305,17 +376,35 @@ class GaussianRasterizer(nn.Module):
             rs = self.raster_settings
             return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
 
-    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
-        rs = self.raster_settings
+    def _checked_inputs(self, shs, colors_precomp, scales, rotations, cov3D_precomp):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         empty = torch.Tensor([])  # absent inputs travel as empty CPU tensors -> NULL in the C ABI
-        shs = empty if shs is None else shs
-        colors_precomp = empty if colors_precomp is None else colors_precomp
-        scales = empty if scales is None else scales
-        rotations = empty if rotations is None else rotations
-        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return tuple(empty if t is None else t for t in (shs, colors_precomp, scales, rotations, cov3D_precomp))
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        shs, colors_precomp, scales, rotations, cov3D_precomp = self._checked_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs)
+
+    def forward_passes(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
+                       extra_passes=()):
+        """Several feature passes over one geometry in ONE call (no counterpart in the reference).
+        The arguments of forward() describe the first pass; ``extra_passes`` is a sequence of ``(colors [P,3], bg [3])``
+        pairs, each rendered like a forward() call with ``colors_precomp=colors`` and that background.  Returns
+        ``(color, radii, [extra images])``.  Preprocess, binning and sort run once, and so does the per-Gaussian stage of
+        the backward; ``means2D.grad`` receives the sum over the passes."""
+        rs = self.raster_settings
+        shs, colors_precomp, scales, rotations, cov3D_precomp = self._checked_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        cols, bgs = [], []
+        for col, bg in extra_passes:
+            if not (isinstance(col, torch.Tensor) and col.is_cuda and col.dtype == torch.float32 and col.dim() == 2
+                    and col.shape == (means3D.shape[0], 3)):
+                raise Exception('extra_passes: colors must be float32 CUDA tensors of shape (P, 3)')
+            cols.append(col)
+            bgs.append(bg)
+        out = _RasterizePasses.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs, tuple(bgs), *cols)
+        return out[0], out[1], list(out[2:])

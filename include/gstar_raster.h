@@ -122,7 +122,7 @@ typedef struct gstar_bwd_args {
     float* dL_dsh;               /* [P,M,3] (NULL if M == 0) */
     float* dL_dscale;            /* [P,3] */
     float* dL_drot;              /* [P,4] */
-    /* Scratch: P * GSTAR_GRAD_SCRATCH_FLOATS floats, ZERO-FILLED by the caller. The blend
+    /* Scratch: P * GSTAR_GRAD_SCRATCH_FLOATS floats, ZERO-FILLED by the caller (or pre-loaded, see blend_only). The blend
      * backward reduces per-(gaussian,tile) partial sums into it with one vector of atomics per
      * warp instead of the reference's nine atomics per (gaussian,pixel). */
     float* blend_grad_scratch;
@@ -132,6 +132,13 @@ typedef struct gstar_bwd_args {
      * straight into the flat buffer that is all-reduced once per step, with no separate
      * accumulation pass.  Invisible Gaussians are then not touched at all.  The other outputs are unaffected. */
     int accumulate_param_grads;
+    /* Several feature passes over one geometry (gstar_raster_reblend): if non-zero, only the blend stage runs -- the nine
+     * raw moments of this pass ([S, S dx, S dy, S dx2, S dxdy, S dy2] and the three colour moments = this pass's
+     * dL_dcolor) are ADDED into blend_grad_scratch and no gradient output is written (all may be NULL).  The six
+     * geometric moments of the passes of one view add, so the caller copies floats 6..8 of every row out as the pass's
+     * dL_dcolor, zeroes them, and hands the same scratch -- now pre-loaded -- to the full backward of the last pass: the
+     * per-Gaussian stage then runs ONCE for all passes.  (A scratch that is not zero on entry is simply added to.) */
+    int blend_only;
 } gstar_bwd_args;
 #define GSTAR_GRAD_SCRATCH_FLOATS 12
 

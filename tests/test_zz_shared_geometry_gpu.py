@@ -243,3 +243,64 @@ def test_identity_keyed_cache_reuses_only_unmodified_tensors():
         dgr.set_geometry_cache(old)
     d2, _ = call(colA)
     assert "Reblend" not in type(d2.grad_fn).__name__
+
+
+def test_forward_passes_one_node_matches_separate_calls():
+    """GaussianRasterizer.forward_passes (config #5's RGB + depth + normal passes as ONE autograd node: preprocess/sort once,
+    the per-Gaussian backward stage once for all passes) against three ordinary calls: identical images, and the step's
+    gradients -- including the ones that reach means3D through the extra passes' colours, and means2D summed over the
+    passes -- agree within the atomics' spread."""
+    import diff_gaussian_rasterization as dgr
+    d = SCENES["surface_sh3"]()
+    kw = Hh.to_torch_kwargs(d)
+    P, H, W = kw["means3D"].shape[0], kw["H"], kw["W"]
+    leaves = {k: kw[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    vm = kw["viewmatrix"].view(4, 4)
+    gen = torch.Generator("cuda").manual_seed(21)
+    ws = [torch.randn(3, H, W, device="cuda", generator=gen) for _ in range(3)]
+    bg2, bg3 = torch.full((3,), 10.0, device="cuda"), torch.tensor([0.5, 0.5, 1.0], device="cuda")
+    center = torch.tensor([0.0, 1.0, 0.0], device="cuda")
+    free_col = torch.rand(P, 3, device="cuda", generator=gen)  # an extra pass whose colours need no gradient
+
+    def run(fused, use=(True, True, True)):
+        for t in leaves.values():
+            t.grad = None
+        m, o, sc, rot, shs = (leaves[k] for k in ("means3D", "opacities", "scales", "rotations", "shs"))
+        m2 = torch.zeros(P, 3, device="cuda", requires_grad=True)
+        depth = (m @ vm[:3, 2] + vm[3, 2])[:, None].expand(-1, 3)
+        nrm = torch.nn.functional.normalize(m - center, dim=-1)
+        r1 = dgr.GaussianRasterizer(_settings(dgr, kw, kw["bg"], 3))
+        if fused:
+            img, radii, extra = r1.forward_passes(means3D=m, means2D=m2, opacities=o, shs=shs, scales=sc, rotations=rot,
+                                                  extra_passes=[(depth, bg2), (nrm, bg3), (free_col, bg3)])
+        else:
+            img, radii = r1(means3D=m, means2D=m2, opacities=o, shs=shs, scales=sc, rotations=rot)
+            extra = [dgr.GaussianRasterizer(_settings(dgr, kw, bg, 0))(means3D=m, means2D=m2, opacities=o, colors_precomp=c, scales=sc,
+                                                                      rotations=rot)[0] for c, bg in ((depth, bg2), (nrm, bg3), (free_col, bg3))]
+        loss = sum((x * w).sum() for x, w, u in zip([img] + extra[:2], ws, use) if u)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {k: (torch.zeros_like(t) if t.grad is None else t.grad.clone()) for k, t in leaves.items()}
+        grads["means2D"] = m2.grad.clone()
+        return [img.detach()] + [e.detach() for e in extra], radii, grads
+
+    for use in ((True, True, True), (True, False, False), (False, True, False)):
+        imgs0, radii0, g0 = run(False, use)
+        imgs1, radii1, g1 = run(True, use)
+        assert torch.equal(radii0, radii1)
+        for a, b in zip(imgs0, imgs1):
+            assert torch.equal(a, b)
+        tol = {"scales": 3e-3, "rotations": 3e-3}
+        for k in g0:
+            assert torch.isfinite(g1[k]).all(), k
+            assert Hh.rel_err(g1[k].cpu(), g0[k].cpu()) < max(GRAD_TOL, tol.get(k, 0.0)), (use, k, Hh.rel_err(g1[k].cpu(), g0[k].cpu()))
+    # inference and the empty scene
+    with torch.no_grad():
+        img, radii, extra = dgr.GaussianRasterizer(_settings(dgr, kw, kw["bg"], 3)).forward_passes(
+            means3D=kw["means3D"], means2D=torch.zeros(P, 3, device="cuda"), opacities=kw["opacities"], shs=kw["shs"], scales=kw["scales"],
+            rotations=kw["rotations"], extra_passes=[(free_col, bg3)])
+    assert torch.equal(img, imgs0[0]) and torch.equal(extra[0], imgs0[3])
+    z3, z4, z1 = torch.zeros(0, 3, device="cuda"), torch.zeros(0, 4, device="cuda"), torch.zeros(0, 1, device="cuda")
+    img, radii, extra = dgr.GaussianRasterizer(_settings(dgr, kw, kw["bg"], 0)).forward_passes(z3, z3, z1, colors_precomp=z3, scales=z3, rotations=z4,
+                                                                                                 extra_passes=[(z3, bg2)])
+    assert float(img.abs().max()) == 0.0 and float(extra[0].abs().max()) == 0.0 and radii.numel() == 0

@@ -35,7 +35,27 @@ def settings(c, bg, deg):
     return dgr.GaussianRasterizationSettings(a.H, a.W, c["tx"], c["ty"], bg, 1.0, c["vm"], c["pm"], deg, c["campos"], False, False)
 
 
+def step_fused(v):
+    """The same step through GaussianRasterizer.forward_passes: one autograd node for all passes."""
+    c = camkw[v % len(camkw)]
+    p = params
+    depth = (p["means3D"] @ c["vm"][:3, 2] + c["vm"][3, 2])[:, None].expand(-1, 3)
+    passes = [(depth, bg2)]
+    for _k in range(a.passes - 2):
+        passes.append((torch.nn.functional.normalize(p["means3D"] - center, dim=-1), bg1))
+    img, _, extra = dgr.GaussianRasterizer(settings(c, bg1, 3)).forward_passes(
+        means3D=p["means3D"], means2D=torch.zeros_like(p["means3D"], requires_grad=True), opacities=p["opacities"], shs=p["shs"],
+        scales=p["scales"], rotations=p["rotations"], extra_passes=passes)
+    loss = (img - target).abs().mean() + (extra[0][0] - dtarget).abs().mean()
+    for e in extra[1:]:
+        loss = loss + (e - target).abs().mean()
+    loss.backward()
+    return loss
+
+
 def step(v, shared):
+    if shared == "fused":
+        return step_fused(v)
     c = camkw[v % len(camkw)]
     p = params
     with (dgr.shared_geometry() if shared else contextlib.nullcontext()):
@@ -104,10 +124,13 @@ def timed_inference(shared, passes=3):
 full_ms, g_full = timed(False)
 shared_ms, g_shared = timed(True)
 full_ms2, _ = timed(False)
+fused_ms, g_fused = timed("fused")
 rel = {k: float((g_shared[k] - g_full[k]).abs().max() / (g_full[k].abs().max() + 1e-30)) for k in g_full}
 res = dict(workload=f"surface P={g.P} {a.W}x{a.H} SH3: {a.passes} feature passes (RGB through SH, then colors_precomp) + one backward through all, per view",
            views=a.views, full_calls_ms_per_view=round(min(full_ms, full_ms2), 4), shared_geometry_ms_per_view=round(shared_ms, 4),
-           speedup=round(min(full_ms, full_ms2) / shared_ms, 4), grad_rel_diff_accumulated_over_views=rel, device=torch.cuda.get_device_name(0))
+           speedup=round(min(full_ms, full_ms2) / shared_ms, 4), grad_rel_diff_accumulated_over_views=rel, device=torch.cuda.get_device_name(0),
+           forward_passes_ms_per_view=round(fused_ms, 4), forward_passes_speedup=round(min(full_ms, full_ms2) / fused_ms, 4),
+           forward_passes_grad_rel_diff={k: float((g_fused[k] - g_full[k]).abs().max() / (g_full[k].abs().max() + 1e-30)) for k in g_full})
 inf_full, o_full = timed_inference(False)
 inf_shared, o_shared = timed_inference(True)
 res["inference_3_passes"] = dict(three_full_calls_ms_per_view=round(inf_full, 4), shared_geometry_ms_per_view=round(inf_shared, 4),
