@@ -73,7 +73,7 @@ _tls = threading.local()
 
 class _GeomSource:
     """What a later re-blend needs of a full forward call."""
-    __slots__ = ("key", "tensors", "rs", "geom", "binning", "image", "radii", "num_rendered")
+    __slots__ = ("key", "tensors", "geom", "binning", "image", "radii", "num_rendered")
 
 
 def set_geometry_cache(enabled: bool) -> bool:
@@ -134,7 +134,6 @@ def _remember_source(means3D, opacities, scales, rotations, cov3Ds_precomp, rs, 
     src = _GeomSource()
     src.tensors = _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs)  # kept alive: their addresses cannot be recycled
     src.key = _geom_key(src.tensors, rs, means3D.device)
-    src.rs = rs
     src.geom, src.binning, src.image, src.radii, src.num_rendered = geom, binning, image, radii, num_rendered
     _tls.src = src
 
