@@ -9,6 +9,10 @@
 // event recorded right behind K2 only AFTER it has enqueued everything -- the GPU never idles, and
 // the exact R is still returned.  If R exceeded the provision (rare) the kernels behind K2 no-op'd
 // on the device flag and binning + blend are re-enqueued with an exact-size buffer.
+//
+// Beyond the reference: gstar_raster_reblend (shared-geometry second pass: k_recolor -> K6 on the first pass's sorted
+// record stream), gstar_bwd_args.blend_only (K7 alone, moments left in the caller's scratch), and a forward that stays
+// on the device while its stream is being captured into a CUDA graph.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -13,6 +13,10 @@
  *   gstar_mark_visible     <->  Rasterizer::markVisible DGR/cuda_rasterizer/rasterizer.h:24-29
  *                                                      (impl. rasterizer_impl.cu:141-153)
  *
+ * Beyond the reference (no counterpart there): gstar_raster_reblend -- a second feature pass over the same
+ * Gaussians and camera that reuses the first pass's sorted record stream -- with gstar_bwd_args.blend_only for running
+ * the per-Gaussian backward stage once for all passes of a view; and CUDA-graph capture of forward / backward / re-blend.
+ *
  * Plain pointers and sizes only: no torch types, no C++ types, no exceptions cross this boundary.
  * All data pointers are DEVICE pointers on the current CUDA device unless stated otherwise; all
  * work is enqueued on `stream`.  The reference binding that a maintainer would write against this
