@@ -63,6 +63,7 @@ class ReblendArgs(C.Structure):
         ("background", C.c_void_p), ("colors_precomp", C.c_void_p),
         ("src_binning_buffer", C.c_void_p), ("src_image_buffer", C.c_void_p),
         ("out_color", C.c_void_p), ("debug", C.c_int), ("forward_only", C.c_int),
+        ("src_viewmatrix", C.c_void_p), ("src_projmatrix", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
     ]
 
 
@@ -159,25 +160,31 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
         R = _check(L.gstar_raster_forward(C.byref(a), geom_cb, None, binning_cb, None, image_cb, None, _stream(dev)))
     if P == 0:
         out_color.zero_()
-    return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom[0], binning=binning[0], image=image[0], _keep=keep)
+    return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom[0], binning=binning[0], image=image[0], viewmatrix=vm, projmatrix=pm,
+                _keep=keep)
 
 
-def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False):
+def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False, viewmatrix=None, projmatrix=None):
     """gstar_raster_reblend: a second pass over the Gaussians/camera of forward (or re-blend) call `src` with other
     per-Gaussian colours (and background).  Returns a dict shaped like forward()'s: the geometry buffer and radii are the
-    source call's (shared), binning and image are new -- pass it to backward() with colors_precomp=<these colours>."""
+    source call's (shared), binning and image are new -- pass it to backward() with colors_precomp=<these colours>.
+    viewmatrix/projmatrix: this call's camera; if given it is compared with the source call's on the device and a
+    mismatch yields a NaN image (header overflow word 2) instead of a picture of the wrong view."""
     L = lib()
     dev = src["geom"].device
-    keep = [_f32(colors_precomp, dev), _f32(bg, dev)]
-    col, bgc = keep
+    keep = [_f32(colors_precomp, dev), _f32(bg, dev), _f32(viewmatrix, dev), _f32(projmatrix, dev)]
+    col, bgc, vm, pm = keep
+    guard = vm is not None and pm is not None
     P = col.shape[0]
     out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
     (binning, binning_cb), (image, image_cb) = _resizable(dev), _resizable(dev)
-    a = ReblendArgs(P, W, H, _ptr(bgc), _ptr(col), _ptr(src["binning"]), _ptr(src["image"]), _ptr(out_color), int(debug), int(forward_only))
+    a = ReblendArgs(P, W, H, _ptr(bgc), _ptr(col), _ptr(src["binning"]), _ptr(src["image"]), _ptr(out_color), int(debug), int(forward_only),
+                    _ptr(src["viewmatrix"]) if guard else None, _ptr(src["projmatrix"]) if guard else None, _ptr(vm) if guard else None,
+                    _ptr(pm) if guard else None)
     with torch.cuda.device(dev):
         R = _check(L.gstar_raster_reblend(C.byref(a), binning_cb, None, image_cb, None, _stream(dev)))
     return dict(num_rendered=R, out_color=out_color, radii=src["radii"], geom=src["geom"], binning=binning[0], image=image[0],
-                _keep=keep + [src])
+                viewmatrix=src["viewmatrix"], projmatrix=src["projmatrix"], _keep=keep + [src])
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,

@@ -472,8 +472,11 @@ int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_all
     GHeader* hdr = (GHeader*)(img + IL.hdr);
     {
         StageScope sc(GSTAR_STAGE_TILE_SORT, stream);  // takes the place of preprocess .. sort
+        CameraCheck cam = {nullptr, nullptr, nullptr, nullptr};
+        if (a->src_viewmatrix && a->src_projmatrix && a->viewmatrix && a->projmatrix)
+            cam = CameraCheck{a->src_viewmatrix, a->src_projmatrix, a->viewmatrix, a->projmatrix};
         launch_recolor((const unsigned char*)src_bin + BL.packed, (unsigned char*)bin + BL.packed, (uint32_t*)(bin + BL.point_list), (uint32_t)R,
-                       a->colors_precomp, hdr, a->forward_only ? 1 : 0, stream);
+                       a->colors_precomp, hdr, a->forward_only ? 1 : 0, cam, stream);
     }
     STAGE_CHECK("recolor");
     BlendParams bl;
@@ -487,6 +490,7 @@ int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_all
         StageScope sc(GSTAR_STAGE_BLEND_FWD, stream);
         launch_blend_fwd(bl, stream);
     }
+    launch_poison(hdr, a->out_color, (size_t)3 * W * H, stream);  // no-op unless this call (or the one it re-blends) was refused on the device
     STAGE_CHECK("blend_fwd");
     ctx->remember(img, cap, log_slots, (uint32_t)R, a->P, W, H);  // a re-blend can itself be re-blended
     return (int)R;

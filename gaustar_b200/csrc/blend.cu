@@ -651,10 +651,20 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
 // from colors[gid] (what preprocess_fwd stores for colors_precomp, forward.cu:241-248 skipped).  HBM: 100 B per instance
 // + an L2-resident gather of 12 B per instance.
 __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src, float4* __restrict__ dst, uint32_t* __restrict__ dst_point_list,
-                                                 uint32_t R, const float* __restrict__ colors, GHeader* hdr, int disable_log)
+                                                 uint32_t R, const float* __restrict__ colors, GHeader* hdr, int disable_log, CameraCheck cam)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && disable_log) hdr->log_overflow = 1u;  // inference re-blend: no hit log (the new binning buffer has none)
+    if (i == 0 && cam.src_view) {
+        // the caller's "same camera" claim, verified where it costs nothing: a re-blend through another camera must not
+        // produce a plausible image of the wrong view.  overflow = 2 makes the blend kernels skip this call; k_poison
+        // then fills the image with NaN.
+        bool same = true;
+        for (int k = 0; k < 16; k++)
+            same = same && __float_as_uint(cam.src_view[k]) == __float_as_uint(cam.view[k]) &&
+                   __float_as_uint(cam.src_proj[k]) == __float_as_uint(cam.proj[k]);
+        if (!same) hdr->overflow = 2u;
+    }
     if (i >= R) return;
     const float4 a = ldg_nc_f4(src + (size_t)i * 3);
     float4 b = ldg_nc_f4(src + (size_t)i * 3 + 1);
@@ -665,12 +675,20 @@ __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src,
     b.z = __ldg(col); b.w = __ldg(col + 1); c.z = __ldg(col + 2);
     dst[(size_t)i * 3] = a; dst[(size_t)i * 3 + 1] = b; dst[(size_t)i * 3 + 2] = c;
 }
+__global__ void __launch_bounds__(256) k_poison(const GHeader* __restrict__ hdr, float* __restrict__ out, size_t n)
+{
+    if (hdr->overflow != 2u) return;  // the usual case: one load per thread
+    const float nan = __uint_as_float(0x7fc00000u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = nan;
+}
+void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s) { k_poison<<<296, 256, 0, s>>>(hdr, out, n); }
+
 void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
-                    int disable_log, cudaStream_t s)
+                    int disable_log, const CameraCheck& cam, cudaStream_t s)
 {
     const uint32_t n = R > 0u ? R : 1u;  // at least one thread: the header patch
     k_recolor<<<(n + 255u) / 256u, 256, 0, s>>>(reinterpret_cast<const float4*>(src_packed), reinterpret_cast<float4*>(dst_packed), dst_point_list, R, colors,
-                                                hdr, disable_log);
+                                                hdr, disable_log, cam);
 }
 
 int blend_setup() { return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM); }

@@ -116,7 +116,16 @@ void launch_blend_bwd(const BlendParams& p, cudaStream_t s);         // walk-bac
 void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s);  // instance-parallel path over the hit log
 // re-blend (shared geometry): copy the packed stream with the colour fields replaced by colors[gid] and rebuild the sorted
 // value list from the records' ids; optionally switch the new header's hit log off
+// the cameras of the source call and of the re-blend (device pointers to 16 floats each; src_view == NULL: not checked)
+struct CameraCheck {
+    const float* src_view;
+    const float* src_proj;
+    const float* view;
+    const float* proj;
+};
 void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
-                    int disable_log, cudaStream_t s);
+                    int disable_log, const CameraCheck& cam, cudaStream_t s);
+// fills `out` with NaN if the header says the re-blend was refused on the device (overflow == 2)
+void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s);
 
 }  // namespace gstar

@@ -106,7 +106,10 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torc
 std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor> ReblendGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& colors,
                                                                                   const int image_height, const int image_width,
                                                                                   const torch::Tensor& srcBinningBuffer,
-                                                                                  const torch::Tensor& srcImgBuffer, const bool debug)
+                                                                                  const torch::Tensor& srcImgBuffer, const bool debug,
+                                                                                  const torch::Tensor& srcViewmatrix,
+                                                                                  const torch::Tensor& srcProjmatrix,
+                                                                                  const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix)
 {
     TORCH_CHECK(colors.is_cuda() && colors.dim() == 2 && colors.size(1) == 3, "gaustar_b200: re-blend needs CUDA colors_precomp of shape (P, 3)");
     TORCH_CHECK(srcBinningBuffer.is_cuda() && srcImgBuffer.is_cuda() && srcImgBuffer.numel() > 0 && srcBinningBuffer.numel() > 0,
@@ -128,6 +131,12 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor> ReblendGaussiansCUD
     a.out_color = out_color.data_ptr<float>();
     a.debug = debug ? 1 : 0;
     a.forward_only = t_forward_only ? 1 : 0;
+    // camera guard (checked on the device): all four 4x4 matrices or none (empty tensors)
+    const bool cam_check = srcViewmatrix.numel() == 16 && srcProjmatrix.numel() == 16 && viewmatrix.numel() == 16 && projmatrix.numel() == 16;
+    const torch::Tensor svm = cam_check ? prep(srcViewmatrix, dev) : srcViewmatrix, spm = cam_check ? prep(srcProjmatrix, dev) : srcProjmatrix,
+                        cvm = cam_check ? prep(viewmatrix, dev) : viewmatrix, cpm = cam_check ? prep(projmatrix, dev) : projmatrix;
+    a.src_viewmatrix = cam_check ? fptr(svm) : nullptr; a.src_projmatrix = cam_check ? fptr(spm) : nullptr;
+    a.viewmatrix = cam_check ? fptr(cvm) : nullptr; a.projmatrix = cam_check ? fptr(cpm) : nullptr;
     const int rendered = gstar_raster_reblend(&a, resize_cb, &binningBuffer, resize_cb, &imgBuffer, stream);
     check(rendered);
     return std::make_tuple(rendered, out_color, binningBuffer, imgBuffer);

@@ -89,7 +89,9 @@ def set_geometry_cache(enabled: bool) -> bool:
 def shared_geometry(check: bool = False):
     """Every rasterizer call inside the block sees the same Gaussians (positions, opacities, scales/rotations or
     covariances) through the same camera and image size; calls after the first that pass ``colors_precomp`` only
-    re-blend.  ``check=True`` compares the tensors' values with the first call's (slow; raises on mismatch)."""
+    re-blend.  Put it around the renders of ONE camera, not around a loop over cameras.  The camera matrices of a
+    re-blend are verified on the device (a mismatch yields a NaN image); the per-Gaussian tensors are not --
+    ``check=True`` compares all values with the first call's (slow, synchronizes; raises on mismatch)."""
     old = getattr(_tls, "scope", None)
     _tls.scope = {"check": bool(check)}
     _tls.src = None
@@ -252,8 +254,11 @@ class _ReblendGaussians(torch.autograd.Function):
         if fwd_only:
             _C.set_forward_only(True)
         try:
+            # the camera of this call is compared with the source call's on the device: a mismatch (a shared_geometry() block
+            # put around a loop over cameras) gives a NaN image, not a plausible picture of the wrong view
             num_rendered, color, binningBuffer, imgBuffer = _C.rasterize_gaussians_reblend(
-                rs.bg, colors_precomp, rs.image_height, rs.image_width, src.binning, src.image, rs.debug)
+                rs.bg, colors_precomp, rs.image_height, rs.image_width, src.binning, src.image, rs.debug, src.tensors[5], src.tensors[6],
+                rs.viewmatrix, rs.projmatrix)
         finally:
             if fwd_only:
                 _C.set_forward_only(False)
@@ -301,8 +306,9 @@ class _RasterizePasses(torch.autograd.Function):
                 if means3D.shape[0] == 0:
                     extras.append(torch.zeros_like(color))
                     continue
+                e = torch.Tensor([])  # same camera by construction: no guard
                 _, img_k, bin_k, ib_k = _C.rasterize_gaussians_reblend(bg_k, col_k, rs.image_height, rs.image_width, binningBuffer, imgBuffer,
-                                                                       rs.debug)
+                                                                       rs.debug, e, e, e, e)
                 extras.append(img_k)
                 bufs += [bin_k, ib_k]
         finally:

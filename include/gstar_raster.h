@@ -175,6 +175,14 @@ typedef struct gstar_reblend_args {
     float* out_color;               /* [3,H,W] fully written */
     int debug;
     int forward_only;
+    /* Optional guard (all four or none; device pointers to 16 floats): the source call's camera and this call's.  They
+     * are compared bit for bit ON THE DEVICE (no host round trip); if they differ the re-blend is refused there: the
+     * blend kernels skip the call, out_color is filled with NaN and the new header's overflow word reads 2
+     * (gstar_debug_header) -- a re-blend through another camera must not return a plausible image of the wrong view. */
+    const float* src_viewmatrix;
+    const float* src_projmatrix;
+    const float* viewmatrix;
+    const float* projmatrix;
 } gstar_reblend_args;
 GSTAR_API int gstar_raster_reblend(const gstar_reblend_args* args,
                          gstar_alloc_fn binning_alloc, void* binning_user,

@@ -113,6 +113,46 @@ def test_reblend_rejects_unknown_source_and_size_mismatch():
     assert torch.isfinite(ok["out_color"]).all()
 
 
+def test_reblend_through_another_camera_is_refused_on_the_device():
+    """The optional camera guard: equal matrices in other memory pass; another camera gives a NaN image and overflow word 2
+    (never a plausible picture of the wrong view) -- through the C ABI and for a shared_geometry() block that was
+    wrongly put around two cameras."""
+    import diff_gaussian_rasterization as dgr
+    from gaustar_b200 import scene
+    g = scene.surface_gaussians(12000, 3, seed=2)
+    cams = scene.dome_cameras(6, 320, 200)
+    kwA, first = run_mine(Hh.scene_dict(g, cams[1]))
+    kwB = Hh.to_torch_kwargs(Hh.scene_dict(g, cams[3]))
+    W, H = kwA["W"], kwA["H"]
+    col = depth_colors(kwA)
+    plain = capi.reblend(first, col, kwA["bg"], W, H)
+    same = capi.reblend(first, col, kwA["bg"], W, H, viewmatrix=kwA["viewmatrix"].clone(), projmatrix=kwA["projmatrix"].clone())
+    other = capi.reblend(first, col, kwA["bg"], W, H, viewmatrix=kwB["viewmatrix"], projmatrix=kwB["projmatrix"])
+    torch.cuda.synchronize()
+    assert torch.equal(same["out_color"], plain["out_color"]) and capi.debug_header(same)["overflow"] == 0
+    assert torch.isnan(other["out_color"]).all() and capi.debug_header(other)["overflow"] == 2
+    chained = capi.reblend(other, col, kwA["bg"], W, H)  # a refused call stays refused down the chain
+    torch.cuda.synchronize()
+    assert torch.isnan(chained["out_color"]).all()
+    # backward of a refused call: no work, zero gradients, nothing out of bounds
+    gr = capi.backward(other, torch.ones(3, H, W, device="cuda"), **Hh.bwd_kwargs(second_pass_kwargs(kwA, col, kwA["bg"])))
+    torch.cuda.synchronize()
+    assert float(gr["dL_dmeans3D"].abs().max()) == 0.0 and float(gr["dL_dcolors"].abs().max()) == 0.0
+
+    def call(kw):
+        return dgr.GaussianRasterizer(_settings(dgr, kw, kw["bg"], 0))(means3D=kw["means3D"], means2D=torch.zeros_like(kw["means3D"]),
+                                                                      opacities=kw["opacities"], colors_precomp=col, scales=kw["scales"],
+                                                                      rotations=kw["rotations"])[0]
+    with torch.no_grad():
+        refA, refB = call(kwA), call(kwB)
+        with dgr.shared_geometry():
+            a1, a2 = call(kwA), call(kwA)  # full forward, then a legitimate re-blend
+            b = call(kwB)                  # the block wrongly spans a second camera
+    torch.cuda.synchronize()
+    assert torch.equal(a1, refA) and torch.equal(a2, refA) and not torch.equal(refA, refB)
+    assert torch.isnan(b).all()
+
+
 def test_reblend_of_a_view_without_instances_is_the_background():
     dev = "cuda"
     P, W, H = 64, 56, 40
