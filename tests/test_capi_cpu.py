@@ -102,16 +102,18 @@ def test_ctypes_structs_match_the_header(tmp_path):
     import subprocess
     src = tmp_path / "abi.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gstar_raster.h"\nint main(void){\n'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gstar_fwd_args), offsetof(gstar_fwd_args, forward_only), offsetof(gstar_fwd_args, out_color),\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gstar_fwd_args), offsetof(gstar_fwd_args, forward_only), offsetof(gstar_fwd_args, out_color),\n'
                    '       sizeof(gstar_bwd_args), offsetof(gstar_bwd_args, accumulate_param_grads), offsetof(gstar_bwd_args, blend_grad_scratch),\n'
-                   '       sizeof(gstar_reblend_args), offsetof(gstar_reblend_args, out_color), offsetof(gstar_reblend_args, forward_only));\n'
+                   '       sizeof(gstar_reblend_args), offsetof(gstar_reblend_args, out_color), offsetof(gstar_reblend_args, forward_only),\n'
+                   '       offsetof(gstar_bwd_args, blend_only), offsetof(gstar_reblend_args, projmatrix));\n'
                    'return 0;}\n')
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     F, B, Rb = capi.FwdArgs, capi.BwdArgs, capi.ReblendArgs
     want = [ctypes.sizeof(F), F.forward_only.offset, F.out_color.offset, ctypes.sizeof(B), B.accumulate_param_grads.offset,
-            B.blend_grad_scratch.offset, ctypes.sizeof(Rb), Rb.out_color.offset, Rb.forward_only.offset]
+            B.blend_grad_scratch.offset, ctypes.sizeof(Rb), Rb.out_color.offset, Rb.forward_only.offset, B.blend_only.offset,
+            Rb.projmatrix.offset]
     assert got == want, (got, want)
 
 
