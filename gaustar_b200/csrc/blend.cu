@@ -665,7 +665,9 @@ __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src,
                    __float_as_uint(cam.src_proj[k]) == __float_as_uint(cam.proj[k]);
         if (!same) hdr->overflow = 2u;
     }
-    if (i >= R) return;
+    // R is the host's count; for a source call that was captured into a CUDA graph that is only the capacity, and the
+    // records behind the device's own count are uninitialised (their ids must not be used as indices)
+    if (i >= R || i >= hdr->num_rendered) return;
     const float4 a = ldg_nc_f4(src + (size_t)i * 3);
     float4 b = ldg_nc_f4(src + (size_t)i * 3 + 1);
     float4 c = ldg_nc_f4(src + (size_t)i * 3 + 2);
