@@ -25,6 +25,7 @@
 #include "../../include/gstar_raster.h"
 #include "gstar_common.cuh"
 #include "gstar_kernels.h"
+#include "recent_calls.h"
 
 namespace {
 
@@ -56,36 +57,7 @@ struct DevCtx {
     double log_estimate = 0.0;  // running provision for the hit log (slots); 0 with log_have: log off for this workload
     int log_small_streak = 0;
     bool log_have = false;
-    // layouts of the most recent forward calls, keyed by their (aligned) image buffer: what gstar_raster_reblend needs
-    // to know on the host about the call it re-blends (the device header holds the same numbers, but reading it would
-    // stall the stream)
-    struct Recent {
-        const char* img = nullptr;
-        size_t cap = 0, log_slots = 0;
-        uint32_t R = 0;
-        int P = 0, W = 0, H = 0;
-    };
-    static constexpr int NRECENT = 16;
-    Recent recent[NRECENT];
-    int recent_next = 0;
-    void remember(const char* img, size_t cap, size_t log_slots, uint32_t R, int P, int W, int H)
-    {
-        int slot = -1;
-        for (int i = 0; i < NRECENT; i++)
-            if (recent[i].img == img) slot = i;
-        if (slot < 0) {
-            slot = recent_next;
-            recent_next = (recent_next + 1) % NRECENT;
-        }
-        recent[slot].img = img; recent[slot].cap = cap; recent[slot].log_slots = log_slots;
-        recent[slot].R = R; recent[slot].P = P; recent[slot].W = W; recent[slot].H = H;
-    }
-    const Recent* find(const char* img) const
-    {
-        for (int i = 0; i < NRECENT; i++)
-            if (recent[i].img == img) return &recent[i];
-        return nullptr;
-    }
+    RecentCalls calls;  // layouts of the most recent forward / re-blend calls (recent_calls.h)
 };
 int g_hit_log_mode = -1;  // -1: read GSTAR_HIT_LOG on first use; 0 off; 1 auto
 double g_hit_log_max_slots = 0.0;
@@ -426,7 +398,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             used_cap = 1; used_log_slots = 0;
         }
     }
-    ctx->remember(img, used_cap, used_log_slots, R, a->P, W, H);
+    ctx->calls.remember(img, used_cap, used_log_slots, R, a->P, W, H);
     return (int)R;
 }
 
@@ -449,7 +421,7 @@ int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_all
     int rc = get_ctx(&ctx);
     if (rc < 0) return rc;
     const char* src_img = aligned128((char*)a->src_image_buffer);
-    const DevCtx::Recent* src = ctx->find(src_img);
+    const RecentCalls::Entry* src = ctx->calls.find(src_img);
     if (!src || src->P != a->P || src->W != a->width || src->H != a->height)
         return fail(GSTAR_ERR_INVALID, "re-blend: the source buffers do not belong to a recent forward call of this thread with the same P, width and height");
     const int W = a->width, H = a->height;
@@ -492,7 +464,7 @@ int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_all
     }
     launch_poison(hdr, a->out_color, (size_t)3 * W * H, stream);  // no-op unless this call (or the one it re-blends) was refused on the device
     STAGE_CHECK("blend_fwd");
-    ctx->remember(img, cap, log_slots, (uint32_t)R, a->P, W, H);  // a re-blend can itself be re-blended
+    ctx->calls.remember(img, cap, log_slots, (uint32_t)R, a->P, W, H);  // a re-blend can itself be re-blended
     return (int)R;
 }
 

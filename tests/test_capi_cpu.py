@@ -152,3 +152,45 @@ def test_shared_geometry_host_logic():
         R._tls.src = "inside"
     assert R._tls.src is None and R._tls.scope is None
     assert R.set_geometry_cache(True) in (False, True) and R.set_geometry_cache(False) is True
+
+
+def test_recent_calls_replacement_is_least_recently_used(tmp_path):
+    """gaustar_b200/csrc/recent_calls.h (host-side memory of the last calls, what gstar_raster_reblend looks its source up
+    in), exercised through a g++ harness: a refreshed or looked-up entry survives the calls that follow -- the scenario
+    a FIFO cursor got wrong (the source of a multi-pass call evicted by its own first re-blend) -- and the least recently
+    used entry is the one replaced."""
+    import subprocess
+    src = tmp_path / "rc.cpp"
+    src.write_text(r'''
+#include <stdio.h>
+#include "recent_calls.h"
+static const char* A(int i) { return (const char*)(size_t)(0x1000 * (i + 1)); }
+int main() {
+    RecentCalls rc;
+    if (rc.find(A(0)) || rc.find(nullptr)) return 1;                 // empty: nothing is found, not even NULL
+    for (int i = 0; i < RecentCalls::N; i++) rc.remember(A(i), 100 + i, 0, i, 7, 8, 9);
+    // the oldest address comes back from the allocator (a new forward at A(0)) ...
+    rc.remember(A(0), 555, 66, 77, 1, 2, 3);
+    // ... and the calls that follow (its re-blends, at fresh addresses) must not evict it
+    rc.remember(A(100), 1, 0, 0, 1, 2, 3);
+    const RecentCalls::Entry* s = rc.find(A(0));
+    if (!s || s->cap != 555 || s->log_slots != 66 || s->R != 77 || s->P != 1 || s->W != 2 || s->H != 3) return 2;
+    if (rc.find(A(1))) return 3;                                      // the least recently used one went instead
+    // a source that is looked up again and again outlives any number of newer calls
+    for (int i = 0; i < 5 * RecentCalls::N; i++) {
+        rc.remember(A(200 + i), 1, 0, 0, 1, 2, 3);
+        if (!rc.find(A(0))) return 4;
+    }
+    // without look-ups an entry goes after N newer ones
+    for (int i = 0; i < RecentCalls::N; i++) rc.remember(A(1000 + i), 1, 0, 0, 1, 2, 3);
+    if (rc.find(A(0))) return 5;
+    int live = 0;
+    for (int i = 0; i < RecentCalls::N; i++) live += rc.find(A(1000 + i)) != nullptr;
+    if (live != RecentCalls::N) return 6;
+    printf("ok\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "rc"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "gaustar_b200", "csrc"), str(src), "-o", str(exe)])
+    assert subprocess.check_output([str(exe)]).strip() == b"ok"
