@@ -61,3 +61,67 @@ def test_differentiable():
     R = T.quaternion_to_matrix(q)
     (T.matrix_to_quaternion(R) * torch.arange(4.0, dtype=torch.float64)).sum().backward()
     assert torch.isfinite(q.grad).all() and q.grad.abs().max() > 0
+
+
+def _cube():
+    v = torch.tensor([[x, y, z] for x in (0.0, 1.0) for y in (0.0, 1.0) for z in (0.0, 1.0)], dtype=torch.float64)
+    f = torch.tensor([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
+                      [1, 5, 7], [1, 7, 3]])
+    return v, f
+
+
+def test_meshes_packing_edges_areas_normals():
+    from pytorch3d.structures import Meshes
+    v, f = _cube()
+    m = Meshes(verts=[v, v + 5.0], faces=[f, f])
+    assert len(m) == 2 and m.verts_packed().shape == (16, 3) and m.faces_packed().shape == (24, 3)
+    assert m.faces_packed()[12:].min() == 8  # the second mesh's indices are offset
+    e = m.edges_packed()
+    assert e.shape == (36, 2) and (e[:, 0] < e[:, 1]).all()  # 12 cube edges + 6 face diagonals per mesh, each once
+    key = e[:, 0] * 16 + e[:, 1]
+    assert (key[1:] > key[:-1]).all()  # sorted lexicographically
+    f2e, F = m.faces_packed_to_edges_packed(), m.faces_packed()
+    for k, (i, j) in enumerate(((1, 2), (2, 0), (0, 1))):  # column k is the edge opposite vertex k
+        pair = torch.stack([torch.minimum(F[:, i], F[:, j]), torch.maximum(F[:, i], F[:, j])], 1)
+        assert torch.equal(e[f2e[:, k]], pair)
+    assert torch.allclose(m.faces_areas_packed(), torch.full((24,), 0.5, dtype=torch.float64))
+    n = m.faces_normals_packed()
+    centre = torch.tensor([0.5, 0.5, 0.5], dtype=torch.float64)
+    fc = v[f].mean(1)
+    assert torch.allclose(n.norm(dim=1), torch.ones(24, dtype=torch.float64)) and ((n[:12] * (fc - centre)).sum(1) > 0).all()  # outward winding
+    assert [x.shape for x in m.faces_normals_list()] == [(12, 3), (12, 3)] and [x.shape for x in m.verts_list()] == [(8, 3), (8, 3)]
+
+
+def test_normal_consistency_closed_forms():
+    from pytorch3d.loss import mesh_normal_consistency
+    from pytorch3d.structures import Meshes
+    # a flat strip: every interior edge joins coplanar faces
+    gx, gy = torch.meshgrid(torch.arange(4.0), torch.arange(3.0), indexing="ij")
+    pv = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.zeros(12)], 1)
+    idx = lambda i, j: i * 3 + j
+    pf = torch.tensor([t for i in range(3) for j in range(2) for t in ([idx(i, j), idx(i + 1, j), idx(i + 1, j + 1)], [idx(i, j), idx(i + 1, j + 1), idx(i, j + 1)])])
+    assert abs(float(mesh_normal_consistency(Meshes([pv], [pf])))) < 1e-6
+    # cube: 12 right-angle edges (1 - cos 90 = 1) and 6 coplanar face diagonals (0) -> 12 / 18
+    v, f = _cube()
+    assert abs(float(mesh_normal_consistency(Meshes([v], [f]))) - 12.0 / 18.0) < 1e-9
+    # regular tetrahedron: outward normals of adjacent faces have cosine -1/3 -> 4/3 on each of the 6 edges
+    tv = torch.tensor([[1.0, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], dtype=torch.float64)
+    tf = torch.tensor([[0, 1, 2], [0, 3, 1], [0, 2, 3], [1, 3, 2]])
+    assert abs(float(mesh_normal_consistency(Meshes([tv], [tf]))) - 4.0 / 3.0) < 1e-9
+    # a batch is the mean of its meshes; the loss is differentiable
+    both = mesh_normal_consistency(Meshes([v, tv], [f, tf]))
+    assert abs(float(both) - 0.5 * (12.0 / 18.0 + 4.0 / 3.0)) < 1e-9
+    vv = v.clone().requires_grad_(True)
+    mesh_normal_consistency(Meshes([vv], [f])).backward()
+    assert torch.isfinite(vv.grad).all()
+
+
+def test_uniform_laplacian_closed_forms():
+    from pytorch3d.loss import mesh_laplacian_smoothing
+    from pytorch3d.structures import Meshes
+    # regular tetrahedron centred at the origin: every vertex's neighbours average to -v/3, so ||L v|| = (4/3) |v|
+    tv = torch.tensor([[1.0, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], dtype=torch.float64)
+    tf = torch.tensor([[0, 1, 2], [0, 3, 1], [0, 2, 3], [1, 3, 2]])
+    assert abs(float(mesh_laplacian_smoothing(Meshes([tv], [tf]), method="uniform")) - 4.0 / 3.0 * 3.0 ** 0.5) < 1e-9
+    # scaling the mesh scales the loss; translating it does not change it
+    assert abs(float(mesh_laplacian_smoothing(Meshes([2 * tv + 7.0], [tf]))) - 8.0 / 3.0 * 3.0 ** 0.5) < 1e-9
