@@ -392,13 +392,16 @@ __device__ __forceinline__ uint32_t group_excl_scan(uint32_t v, const Grp& g, ui
 // Write the sorted list of one tile: point_list (the reference's sorted value list) and the tile-contiguous packed
 // record stream the blend kernels read with one TMA bulk copy per batch: the first 44 bytes of the Gaussian's GRec
 // followed by the instance's first HIT-LOG slot.  Every instance owns one 16-byte slot per pixel of its alpha-bounds
-// inside this tile (clip_foot); slots of a tile are contiguous (exclusive scan over the group, any order), tiles take
-// their block from a global cursor.  The cursor keeps counting when the log is too small (or disabled) so that the host
-// learns the size this view needs.  Random 48-byte reads hit the L2-resident GRec array; writes are contiguous.
-// Every gather is issued for U instances at once: the loops are latency-bound (one L2 round trip per step).
+// inside this tile (clip_foot).  The slots of a tile are contiguous and handed out IN LIST ORDER (instance i's slots
+// directly follow instance i-1's): the slot numbers double as the tile's (instance, pixel) PAIR index, which is what
+// lets blend_fwd evaluate alpha with lanes = pairs (see blend.cu).  Tiles take their block from a global cursor; it
+// keeps counting when the log is too small (or disabled) so that the host learns the size this view needs.  Random
+// 48-byte reads hit the L2-resident GRec array; writes are contiguous.  Every gather is issued for U instances at
+// once: the loops are latency-bound (one L2 round trip per step).
+// s_area: shared-memory scratch of `scap` words (the areas of a chunk of the list, then their exclusive prefix).
 template <int U>
 __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, uint32_t start, const uint64_t* keys, uint32_t n, const Grp& g,
-                                             GrpSmem* sm)
+                                             GrpSmem* sm, uint32_t* s_area, uint32_t scap)
 {
     const float4* recs = reinterpret_cast<const float4*>(p.recs);
     float4* out = reinterpret_cast<float4*>(p.packed + (size_t)start * GSTAR_REC_SMEM);
@@ -406,58 +409,86 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
     const int limx = min(GSTAR_TILE - 1, p.W - 1 - tx0), limy = min(GSTAR_TILE - 1, p.H - 1 - ty0);
     const unsigned char* recb = reinterpret_cast<const unsigned char*>(p.recs);
     const uint32_t tid = g.tid, nt = g.nt;
-    uint32_t mine = 0;
-    for (uint32_t i0 = tid; i0 < n; i0 += U * nt) {
-        uint2 bb[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + u * nt;
-            bb[u] = make_uint2(1u, 0u);  // empty box
-            if (i < n) bb[u] = *reinterpret_cast<const uint2*>(recb + (size_t)(uint32_t)keys[i] * GSTAR_REC_BYTES + 32);
+    uint32_t tile_total = 0;
+    if (n > scap) {  // a list longer than the scratch (rare): its total first, so that the tile still gets ONE block of slots
+        uint32_t mine = 0;
+        for (uint32_t i = tid; i < n; i += nt) {
+            const uint2 bb = *reinterpret_cast<const uint2*>(recb + (size_t)(uint32_t)keys[i] * GSTAR_REC_BYTES + 32);
+            mine += foot_area(bb.x, bb.y, tx0, ty0, limx, limy);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (i0 + u * nt < n) mine += foot_area(bb[u].x, bb[u].y, tx0, ty0, limx, limy);
+        group_excl_scan(mine, g, sm->w, &tile_total);
     }
-    uint32_t tile_total;
-    const uint32_t excl = group_excl_scan(mine, g, sm->w, &tile_total);
-    if (tid == 0) {
-        const unsigned long long base = atomicAdd(&p.hdr->log_cursor, (unsigned long long)tile_total);
-        if (base + tile_total > p.log_capacity) p.hdr->log_overflow = 1u;
-        sm->base = base;
-        // lanes per instance for the gather backward: about a dozen footprint pixels per lane, and more lanes when the
-        // tile has fewer instances than the gather CTA has threads
-        const uint32_t mean = tile_total / max(n, 1u);
-        uint32_t lanes = mean <= 14u ? 1u : mean <= 28u ? 2u : mean <= 64u ? 4u : 8u;
-        while (lanes < 8u && n * lanes < 256u && mean > 3u * lanes) lanes <<= 1;
-        p.tile_lanes[tile] = (unsigned char)lanes;
-    }
-    gsync(g);
-    uint32_t slot = (uint32_t)sm->base + excl;
-    for (uint32_t i0 = tid; i0 < n; i0 += U * nt) {
-        uint32_t id[U];
-        float4 a[U], b[U], c[U];
+    uint32_t done_slots = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += scap) {
+        const uint32_t m = min(scap, n - c0);
+        for (uint32_t i0 = tid; i0 < m; i0 += U * nt) {
+            uint2 bb[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + u * nt;
-            id[u] = i < n ? (uint32_t)keys[i] : 0u;
-            if (i < n) {
-                a[u] = recs[(size_t)id[u] * 3]; b[u] = recs[(size_t)id[u] * 3 + 1]; c[u] = recs[(size_t)id[u] * 3 + 2];
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * nt;
+                bb[u] = make_uint2(1u, 0u);  // empty box
+                if (i < m) bb[u] = *reinterpret_cast<const uint2*>(recb + (size_t)(uint32_t)keys[c0 + i] * GSTAR_REC_BYTES + 32);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (i0 + u * nt < m) s_area[i0 + u * nt] = foot_area(bb[u].x, bb[u].y, tx0, ty0, limx, limy);
+        }
+        gsync(g);
+        // exclusive prefix of the areas in list order: thread t owns the entries [t*per, (t+1)*per)
+        const uint32_t per = (m + nt - 1) / nt;
+        uint32_t mine = 0;
+        for (uint32_t e = 0; e < per; e++) {
+            const uint32_t i = tid * per + e;
+            if (i < m) mine += s_area[i];
+        }
+        uint32_t chunk_total;
+        uint32_t run = group_excl_scan(mine, g, sm->w, &chunk_total);
+        for (uint32_t e = 0; e < per; e++) {
+            const uint32_t i = tid * per + e;
+            if (i < m) { const uint32_t a = s_area[i]; s_area[i] = run; run += a; }
+        }
+        if (c0 == 0) {
+            if (n <= scap) tile_total = chunk_total;
+            if (tid == 0) {
+                const unsigned long long base = atomicAdd(&p.hdr->log_cursor, (unsigned long long)tile_total);
+                if (base + tile_total > p.log_capacity) p.hdr->log_overflow = 1u;
+                sm->base = base;
+                // lanes per instance for the gather backward: about a dozen footprint pixels per lane, and more lanes when the
+                // tile has fewer instances than the gather CTA has threads
+                const uint32_t mean = tile_total / max(n, 1u);
+                uint32_t lanes = mean <= 14u ? 1u : mean <= 28u ? 2u : mean <= 64u ? 4u : 8u;
+                while (lanes < 8u && n * lanes < 256u && mean > 3u * lanes) lanes <<= 1;
+                p.tile_lanes[tile] = (unsigned char)lanes;
             }
         }
+        gsync(g);
+        const uint32_t slot0 = (uint32_t)sm->base + done_slots;
+        for (uint32_t i0 = tid; i0 < m; i0 += U * nt) {
+            uint32_t id[U];
+            float4 a[U], b[U], c[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + u * nt;
-            if (i < n) {
-                p.point_list[start + i] = id[u];
-                const Foot ft = clip_foot(__float_as_uint(c[u].x), __float_as_uint(c[u].y), tx0, ty0, limx, limy);
-                c[u].x = __uint_as_float(pack_foot(ft));  // the blend kernels get the clipped footprint ready-made
-                c[u].y = __uint_as_float(id[u]);
-                c[u].w = __uint_as_float(slot);
-                slot += (ft.w > 0 && ft.h > 0) ? (uint32_t)(ft.w * ft.h) : 0u;
-                out[(size_t)i * 3] = a[u]; out[(size_t)i * 3 + 1] = b[u]; out[(size_t)i * 3 + 2] = c[u];
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * nt;
+                id[u] = i < m ? (uint32_t)keys[c0 + i] : 0u;
+                if (i < m) {
+                    a[u] = recs[(size_t)id[u] * 3]; b[u] = recs[(size_t)id[u] * 3 + 1]; c[u] = recs[(size_t)id[u] * 3 + 2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * nt;
+                if (i < m) {
+                    p.point_list[start + c0 + i] = id[u];
+                    const Foot ft = clip_foot(__float_as_uint(c[u].x), __float_as_uint(c[u].y), tx0, ty0, limx, limy);
+                    c[u].x = __uint_as_float(pack_foot(ft));  // the blend kernels get the clipped footprint ready-made
+                    c[u].y = __uint_as_float(id[u]);
+                    c[u].w = __uint_as_float(slot0 + s_area[i]);
+                    out[(size_t)(c0 + i) * 3] = a[u]; out[(size_t)(c0 + i) * 3 + 1] = b[u]; out[(size_t)(c0 + i) * 3 + 2] = c[u];
+                }
             }
         }
+        done_slots += chunk_total;
+        gsync(g);  // s_area is rewritten by the next chunk
     }
 }
 
@@ -490,7 +521,7 @@ __device__ __forceinline__ void network_sort_tile(const BinParams& p, const Grp&
         for (uint32_t i = tid; i < n; i += nt) s_keys[i] = gk[i];
         gsync(g);
         bitonic_sort(s_keys, n, g);
-        write_sorted<2>(p, tile, start, s_keys, n, g, sm);
+        write_sorted<2>(p, tile, start, s_keys, n, g, sm, reinterpret_cast<uint32_t*>(s_keys + CH), CH);  // the fine-bucket region behind the keys
         return;
     }
     uint32_t npad = CH;
@@ -529,7 +560,7 @@ __device__ __forceinline__ void network_sort_tile(const BinParams& p, const Grp&
             gsync(g);
         }
     }
-    write_sorted<2>(p, tile, start, gk, n, g, sm);
+    write_sorted<2>(p, tile, start, gk, n, g, sm, reinterpret_cast<uint32_t*>(s_keys), 2 * CH);
 }
 
 // Classes 1 and 2 (lists shorter than CAP): two-level adaptive bucket sort, O(n) and ~a dozen barriers instead of the
@@ -636,7 +667,7 @@ __device__ __forceinline__ void bucket_sort_tile(const BinParams& p, const Grp& 
         gsync(g);
         bitonic_sort(s_out, n, g);
     }
-    write_sorted<2>(p, tile, start, s_out, n, g, sm);
+    write_sorted<2>(p, tile, start, s_out, n, g, sm, s_fine, CAP);
 }
 
 // ---- K4: ONE persistent kernel sorts every tile list -------------------------------------------------------------

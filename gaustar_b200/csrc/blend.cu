@@ -128,172 +128,441 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
 }
 
 // ---- K6: forward blend ---------------------------------------------------------------------------------------------
-// One CTA per tile, eight warps, one per 8x4 pixel block, and NO coupling between them: every warp streams the tile's
-// packed records through its OWN shared-memory ring (FWD_NST stages of FWD_SB records; lane 0 issues one TMA bulk copy per
-// stage, completion on the stage's mbarrier), so a warp whose pixels are finished simply leaves, a warp with few hits
-// runs ahead, and nobody polls a barrier for somebody else's progress.  (The first version shared one ring per CTA
-// behind a producer warp: ~15 % of its issued instructions were mbarrier polls of warps waiting for the tile's slowest
-// warp.)  The records come out of L2; fetching them once per warp costs L2->shared bandwidth, not HBM.
-// Per batch: every lane turns ONE record's alpha-bounds into a 32-bit mask of the block's pixels, a 32x32 bit transpose
-// hands every pixel the records that can touch it (one register word per 32 records = the pixel's hit queue), and the
-// set bits are walked four at a time in list order with the reference's arithmetic.
-#ifndef GSTAR_FWD_SB
-#define GSTAR_FWD_SB 64
-#define GSTAR_FWD_NST 2
-#define GSTAR_FWD_CTAS 4
+// One CTA (256 threads) per 16x16 tile; the tile's packed records arrive in batches of FWD_NB through a ring of TMA bulk
+// copies (thread 0 issues one cp.async.bulk per batch; completion on the stage's mbarrier).  A batch goes through two
+// phases (what a phase leaves for the next is double-buffered, so fast warps run ahead into the next batch's P1):
+//
+//  P1  alpha for every (record, pixel-of-its-footprint) PAIR, lanes = pairs.  tile_sort handed every instance one
+//      hit-log slot per pixel of its clipped alpha-bounds, in list order, so the slot numbers of a 32-record group ARE its
+//      pair index space.  The group's first warp marks the record starts in a bit vector; lane j of chunk c finds the
+//      record of pair 32c+j by a popcount -- no search, no imbalance: a 3x3 splat costs 9 lane-evaluations, not 256
+//      (reference: every pixel of the tile evaluates every record, forward.cu:329-345) and not "as many passes as the
+//      busiest pixel of a warp" (round 1).  Survivors of the reference's two tests (power > 0, alpha < 1/255) store
+//      alpha at their pair index and set the record's bit in their pixel's hit word (shared-memory atomicOr).
+//  P2  the serial part: per pixel, its hits in list order -- load alpha, the T recurrence in the reference's order and
+//      rounding (forward.cu:346-358), the hit-log row at the pair's own slot.  Consecutive records of a depth-sorted
+//      list lie on an iso-depth band of the surface, so only a fraction of the tile's pixels has hits in a given batch:
+//      the pixels that do are COMPACTED into a work list first (pixel state lives in shared memory), and only as many
+//      warps as the list needs run P2 while the others go on to the next batch's P1.
+//
+// A group whose pairs do not fit the alpha buffer (fat splats: a generic 3DGS cloud) gets its hit words straight from
+// the footprint rectangles (bit-matrix transposes, as round 1 did for everything) and P2 evaluates those pairs itself
+// -- with footprints that cover most of a tile, lanes = pixels is dense anyway.  The arithmetic per pair is the
+// reference's in both paths, so out_color / final_T / n_contrib are bit-identical.
+#ifndef GSTAR_FWD_ACAP
+#define GSTAR_FWD_ACAP 3584
 #endif
-constexpr int FWD_SB = GSTAR_FWD_SB;   // records per stage
-constexpr int FWD_NW = FWD_SB / 32;
-constexpr int FWD_NST = GSTAR_FWD_NST;    // stages per warp
+#ifndef GSTAR_FWD_CTAS
+#define GSTAR_FWD_CTAS 3
+#endif
+constexpr int FWD_NB = 128;                 // records per batch
+constexpr int FWD_NG = FWD_NB / 32;         // 32-record groups per batch == hit words per pixel
+constexpr int FWD_WARPS = 8;
+constexpr int FWD_WPG = FWD_WARPS / FWD_NG; // warps sharing a group's pairs
+constexpr int FWD_NST = 3;                  // record stages in flight
+constexpr int FWD_ACAP = GSTAR_FWD_ACAP;    // alpha slots per batch
+constexpr int FWD_GCAP = 2048;              // pairs of a group that goes through the alpha buffer
+constexpr int FWD_GW = FWD_GCAP / 32;       // words of its record-start vector
 constexpr int FWD_CTAS_PER_SM = GSTAR_FWD_CTAS;
-constexpr int FWD_THREADS = NCONS * 32;
-constexpr int FWD_DYN_SMEM = NCONS * FWD_NST * FWD_SB * RS;  // 48 KB
+constexpr int FWD_THREADS = FWD_WARPS * 32;
+static_assert(FWD_NG == 4 && FWD_GW == 64, "P1 assumes four groups per batch and two start words per lane");
+
+struct __align__(16) FwdHdr {   // what P2 needs of a record
+    float r, g, b;
+    uint32_t pk;  // footprint width | direct << 5 | (256 + pair index of the record's (virtual) pair for tile pixel (0,0), batch-relative) << 6
+};
+struct FwdGroup {               // P1 scratch of a 32-record group, written by the warp that drew the group's header ticket
+    uint32_t words[FWD_GW];     // record starts in the group's pair space (bit q: a record's first pair is q)
+    uint32_t pref[FWD_GW];      // records that start in the words before word c
+    uint2 prec[32];             // rank -> (first pair | w << 16 | record's lane << 24,  magic | x0 << 16 | y0 << 24)
+    uint32_t total, light, rel0, pad;
+};
+struct FwdSmem {
+    float alpha[2][FWD_ACAP];
+    FwdHdr hdr[2][FWD_NB];
+    uint32_t mask[2][FWD_NG][256];   // hit words, [word][pixel]
+    uint32_t item[FWD_NG + 1][256];  // P2 work list: pixel id, its hit words
+    float4 state[256];               // per pixel (C0, C1, C2, T)
+    uint32_t last[256];              // per pixel last contributor
+    FwdGroup grp[FWD_NG];
+    uint32_t magic[17];              // floor(t / w) == t * magic[w] >> 12 for t < 256, w <= 16
+    uint32_t done[8];                // pixels that reached T < 1e-4 (or lie outside the image)
+    uint32_t hist[2][32];            // P2 work list, counting sort by chain length: pixels per length class
+    // P1 work of a batch is drawn by whichever warp is free (the warps still busy with the previous batch's P2 draw less)
+    uint32_t tick_c[2], hdone[2], anyfat[2];
+    uint64_t full[FWD_NST];
+};
+constexpr int FWD_DYN_SMEM = FWD_NST * FWD_NB * RS + (int)sizeof(FwdSmem);
+constexpr int FWD_UNITS = 4;  // P1 work units per group (strided chunks)
 
 __device__ __forceinline__ void fwd_fetch(unsigned char* stage, uint64_t* bar, const unsigned char* tile_packed, int b, int n)
 {
-    const uint32_t bytes = (uint32_t)min(FWD_SB, n - b * FWD_SB) * RS;
+    const uint32_t bytes = (uint32_t)min(FWD_NB, n - b * FWD_NB) * RS;
     mbar_arrive_expect_tx(bar, bytes);
-    bulk_g2s(stage, tile_packed + (size_t)b * FWD_SB * RS, bytes, bar);
+    bulk_g2s(stage, tile_packed + (size_t)b * FWD_NB * RS, bytes, bar);
+}
+
+// 32-bit mask over the pixels [32 wr, 32 wr + 32) of the tile (rows 2 wr and 2 wr + 1) inside a footprint
+__device__ __forceinline__ unsigned rows_pixel_mask(const Foot& f, int wr)
+{
+    if (f.w <= 0) return 0u;
+    const unsigned cols = ((1u << f.w) - 1u) << f.x0;  // 16 bits
+    const int y = 2 * wr;
+    unsigned m = 0u;
+    if (y >= f.y0 && y < f.y0 + f.h) m |= cols;
+    if (y + 1 >= f.y0 && y + 1 < f.y0 + f.h) m |= cols << 16;
+    return m;
+}
+// exact (float) of an integer below 2^23 without the conversion pipe: kbase = 0x4B000000 + integer
+__device__ __forceinline__ float small_int_to_float(uint32_t kbase_plus_i) { return __uint_as_float(kbase_plus_i) - 8388608.0f; }
+__device__ __forceinline__ uint32_t lds_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ uint32_t warp_ticket(uint32_t* ctr, int lane)
+{
+    uint32_t t = 0u;
+    if (lane == 0) t = atomicAdd(ctr, 1u);
+    return __shfl_sync(FULL, t, 0);
+}
+
+// P1, group header: record starts, rank table, and what P2 needs of every record of the group
+__device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned char* stage, int buf, int grp, int cnt, uint32_t slot_b0, int lane)
+{
+    FwdGroup& G = sm.grp[grp];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int ri = grp * 32 + lane;
+    const bool valid = ri < cnt;
+    float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) q2 = *reinterpret_cast<const float4*>(stage + ri * RS + 32);  // foot gid b slot
+    const Foot f = unpack_foot(__float_as_uint(q2.x));
+    const uint32_t area = valid ? (uint32_t)(f.w * f.h) : 0u;
+    const uint32_t slot = __float_as_uint(q2.w);
+    const uint32_t slot_g0 = __shfl_sync(FULL, slot, 0);
+    const uint32_t total = __reduce_add_sync(FULL, area);
+    const uint32_t rel0 = slot_g0 - slot_b0;
+    const bool light = total <= (uint32_t)FWD_GCAP && rel0 + total <= (uint32_t)FWD_ACAP;
+    const uint32_t s0 = slot - slot_g0;  // my first pair in the group's pair space (list-order slots: binning.cu)
+    if (valid) {
+        const float4 q1 = *reinterpret_cast<const float4*>(stage + ri * RS + 16);  // C o r g
+        FwdHdr h;
+        h.r = q1.z; h.g = q1.w; h.b = q2.z;
+        h.pk = (uint32_t)f.w | (light ? 0u : 32u) | ((256u + (slot - slot_b0) - (uint32_t)(f.y0 * f.w + f.x0)) << 6);
+        sm.hdr[buf][ri] = h;
+    }
+    if (lane == 0) {
+        G.total = total; G.light = light ? 1u : 0u; G.rel0 = rel0;
+        if (!light) sm.anyfat[buf] = 1u;
+    }
+    if (light && total > 0u) {
+        const unsigned nonempty = __ballot_sync(FULL, area > 0u);
+        G.words[lane] = 0u; G.words[lane + 32] = 0u;
+        __syncwarp();
+        if (area > 0u) {
+            atomicOr(&G.words[s0 >> 5], 1u << (s0 & 31u));
+            G.prec[__popc(nonempty & lt_mask)] =
+                make_uint2(s0 | ((uint32_t)f.w << 16) | ((uint32_t)lane << 24), sm.magic[f.w] | ((uint32_t)f.x0 << 16) | ((uint32_t)f.y0 << 24));
+        }
+        __syncwarp();
+        const uint2 ww = *reinterpret_cast<const uint2*>(&G.words[2 * lane]);  // lane owns words 2*lane, 2*lane+1
+        const uint32_t c0 = (uint32_t)__popc(ww.x), c1 = (uint32_t)__popc(ww.y);
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t ex = incl - c0 - c1;
+        *reinterpret_cast<uint2*>(&G.pref[2 * lane]) = make_uint2(ex, ex + c0);
+    }
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(BlendParams p)
 {
-    extern __shared__ __align__(128) unsigned char s_dyn[];
-    __shared__ __align__(8) uint64_t s_full[NCONS][FWD_NST];
+    extern __shared__ __align__(128) unsigned char s_dyn[];  // (no pointer arithmetic through integers: it would demote every access to generic LD/ST/ATOM)
     if (p.hdr->overflow) return;
+    unsigned char* const s_stage = s_dyn;  // [FWD_NST][FWD_NB * RS]
+    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(s_dyn + FWD_NST * FWD_NB * RS);
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
     const int n = (int)(re - rs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const WarpGeom g = warp_geom(tile, p.gx, p.W, p.H);
-    const float pxf = (float)g.px, pyf = (float)g.py;
+    const int tile_ty = tile / p.gx;
+    const int tile_x0 = (tile - tile_ty * p.gx) * GSTAR_TILE, tile_y0 = tile_ty * GSTAR_TILE;
+    const bool inside = tile_x0 + (tid & 15) < p.W && tile_y0 + (tid >> 4) < p.H;  // thread <-> pixel for setup and output
     // hit log (see k_blend_bwd_gather): every blended (instance, pixel) pair records the transmittance in front of it
     // and the colour accumulated up to and including it in the instance's slot for this pixel
     const bool log_on = p.hdr->log_overflow == 0u;
     GHit* const hitlog = reinterpret_cast<GHit*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
-    const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
-    const int lx = g.px - tile_x0, ly = g.py - tile_y0;
     if (blockIdx.x == 0 && tid == 0 && p.host_counts) {  // size the next call's log: slots this view needed
         const unsigned long long need = p.hdr->log_cursor;
         p.host_counts[4] = (uint32_t)need;
         p.host_counts[5] = (uint32_t)(need >> 32);
     }
+    float4 fin = make_float4(0.f, 0.f, 0.f, 1.0f);  // (C, T) of my pixel
+    uint32_t fin_last = 0;
 
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t last = 0;
-    bool done = !g.inside;
-
-    if (n > 0 && __any_sync(FULL, !done)) {
-        unsigned char* const ring = s_dyn + (size_t)warp * FWD_NST * FWD_SB * RS;
-        uint64_t* const full = s_full[warp];
+    if (n > 0) {
         const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
-        const int nb = (n + FWD_SB - 1) / FWD_SB;
-        if (lane == 0) {
+        const int nb = (n + FWD_NB - 1) / FWD_NB;
+        for (int i = tid; i < 2 * FWD_NG * 256; i += FWD_THREADS) (&sm.mask[0][0][0])[i] = 0u;
+        sm.state[tid] = fin;
+        sm.last[tid] = 0u;
+        if (tid < 17) sm.magic[tid] = tid ? (4096u + (uint32_t)tid - 1u) / (uint32_t)tid : 0u;
+        if (tid < 64) (&sm.hist[0][0])[tid] = 0u;
+        if (tid < 2) { sm.tick_c[tid] = 0u; sm.hdone[tid] = 0u; sm.anyfat[tid] = 0u; }
+        {
+            const unsigned out = __ballot_sync(FULL, !inside);
+            if (lane == 0) sm.done[warp] = out;
+        }
+        if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < FWD_NST; s++) mbar_init(&full[s], 1);
+            for (int s = 0; s < FWD_NST; s++) mbar_init(&sm.full[s], 1);
             fence_mbar_init();
 #pragma unroll
             for (int s = 0; s < FWD_NST; s++)
-                if (s < nb) fwd_fetch(ring + s * FWD_SB * RS, &full[s], tile_packed, s, n);
+                if (s < nb) fwd_fetch(s_stage + s * FWD_NB * RS, &sm.full[s], tile_packed, s, n);
         }
-        __syncwarp();
+        int issued = min(nb, FWD_NST);  // batches whose copy has been issued (meaningful in thread 0)
+        __syncthreads();
+        const uint32_t kx = 0x4B000000u + (uint32_t)tile_x0, ky = 0x4B000000u + (uint32_t)tile_y0;
+        const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
         int b = 0;
 #pragma unroll 1
         for (; b < nb; b++) {
-            const int s = b % FWD_NST;
-            const unsigned char* buf = ring + s * FWD_SB * RS;
-            mbar_wait(&full[s], (uint32_t)(b / FWD_NST) & 1u);
-            const unsigned live = __ballot_sync(FULL, !done);
-            if (live == 0) break;  // every pixel of the block is finished: this warp is done with the tile
-            const int cnt = min(FWD_SB, n - b * FWD_SB);
-            // per-pixel hit queue of the batch: bit k of word r = record 32 r + k may touch my pixel
-            unsigned w[FWD_NW];
-            int left = 0;
-#pragma unroll
-            for (int r = 0; r < FWD_NW; r++) {
-                w[r] = 0u;
-                if (r * 32 < cnt) {
-                    const unsigned pm = (r * 32 + lane < cnt) ? (block_pixel_mask(buf + (r * 32 + lane) * RS, g) & live) : 0u;
-                    if (__any_sync(FULL, pm != 0u)) w[r] = transpose32(pm, lane);
+            const int st = b % FWD_NST, buf = b & 1;
+            const unsigned char* stage = s_stage + st * FWD_NB * RS;
+            mbar_wait(&sm.full[st], (uint32_t)(b / FWD_NST) & 1u);
+            const int cnt = min(FWD_NB, n - b * FWD_NB);
+            const uint32_t slot_b0 = *reinterpret_cast<const uint32_t*>(stage + 44);  // first pair of the batch
+            // ================= P1: group headers (warps 4..7), then the batch's pairs in 16 work units drawn by ticket =================
+            {
+                const uint32_t ng = (uint32_t)(cnt + 31) >> 5;
+                if (warp >= FWD_NG && (uint32_t)(warp - FWD_NG) < ng) {
+                    fwd_group_header(sm, stage, buf, warp - FWD_NG, cnt, slot_b0, lane);
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); atomicAdd(&sm.hdone[buf], 1u); }
                 }
-                left += __popc(w[r]);
-            }
-            unsigned cw = w[0];  // word being walked, and its index
-            int cr = 0;
+                while (lds_volatile(&sm.hdone[buf]) < ng) {}
+                __threadfence_block();
+                float* const abase = sm.alpha[buf];
 #pragma unroll 1
-            while (__any_sync(FULL, left > 0)) {
-                int sl[4];
-                bool ok[4];
-                float al[4], cr_[4], cg[4], cbv[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool have = left > 0;
-                    if (have) {
-                        while (cw == 0u) {  // next non-empty word (left > 0 guarantees there is one)
-                            cr++;
-                            unsigned nx = 0u;
-#pragma unroll
-                            for (int r = 1; r < FWD_NW; r++) nx = (cr == r) ? w[r] : nx;
-                            cw = nx;
-                        }
-                        sl[u] = cr * 32 + __ffs(cw) - 1;
-                        cw &= cw - 1u;
-                        left--;
-                    } else {
-                        sl[u] = 0;
-                    }
-                    const unsigned char* rp = buf + sl[u] * RS;
-                    const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
-                    const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
-                    cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
-                    cr_[u] = q1.z; cg[u] = q1.w;
-                    float dx, dy;
-                    const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
-                    al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
-                    ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (ok[u] && !done) {
-                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            C0 = __fmaf_rn(T, __fmul_rn(al[u], cr_[u]), C0);
-                            C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
-                            C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
-                            if (log_on) {
-                                const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // foot gid b slot
-                                const Foot f = unpack_foot(tail.x);
-                                GHit h;
-                                h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
-                                hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
+                for (;;) {
+                    const uint32_t t = warp_ticket(&sm.tick_c[buf], lane);
+                    if (t >= ng * FWD_UNITS) break;
+                    const int g = (int)(t / FWD_UNITS);
+                    const uint32_t j = t % FWD_UNITS;
+                    const FwdGroup& G = sm.grp[g];
+                    if (G.light) {
+                        const uint32_t total = G.total;
+                        float* const ab = abase + G.rel0;
+                        uint32_t* const mk = sm.mask[buf][g];
+                        const unsigned char* const gstage = stage + g * 32 * RS;
+#pragma unroll 1
+                        for (uint32_t q = j * 32u + (uint32_t)lane; q < total; q += FWD_UNITS * 32u) {
+                            const uint32_t c = q >> 5;
+                            const uint2 pr = G.prec[G.pref[c] + (uint32_t)__popc(G.words[c] & le_mask) - 1u];
+                            const uint32_t rl = pr.x >> 24;
+                            const uint32_t off = q - (pr.x & 0xffffu), fw = __byte_perm(pr.x, 0u, 0x4442);
+                            const uint32_t yy = (off * (pr.y & 0xffffu)) >> 12, xx = off - yy * fw;
+                            const uint32_t plx = __byte_perm(pr.y, 0u, 0x4442) + xx, ply = (pr.y >> 24) + yy;
+                            const unsigned char* rp = gstage + rl * RS;
+                            const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
+                            const float2 co = *reinterpret_cast<const float2*>(rp + 16);  // C o
+                            float dx, dy;
+                            const float power = eval_power(q0.x, q0.y, q0.z, q0.w, co.x, small_int_to_float(kx + plx), small_int_to_float(ky + ply), dx, dy);
+                            const float al = fminf(0.99f, __fmul_rn(co.y, expf(power)));
+                            if (!(power > 0.0f) && !(al < 1.0f / 255.0f)) {  // forward.cu:336-345
+                                ab[q] = al;
+                                atomicOr(&mk[ply * 16u + plx], 1u << rl);
                             }
-                            T = test_T;
-                            last = (uint32_t)(b * FWD_SB + sl[u] + 1);
+                        }
+                    } else {
+                        // fat group: hit words straight from the footprint rectangles, one transpose per 32 pixels
+                        const int ri = g * 32 + lane;
+                        uint32_t fw = 0u;
+                        if (ri < cnt) fw = *reinterpret_cast<const uint32_t*>(stage + ri * RS + 32);
+                        const Foot f = unpack_foot(fw);
+#pragma unroll 1
+                        for (uint32_t wr = j; wr < (uint32_t)FWD_WARPS; wr += FWD_UNITS) {
+                            const unsigned pm = rows_pixel_mask(f, (int)wr);
+                            if (__any_sync(FULL, pm != 0u)) sm.mask[buf][g][wr * 32u + (uint32_t)lane] = transpose32(pm, lane);
                         }
                     }
                 }
-                if (done) left = 0;  // a finished pixel drops the rest of its queue
             }
-            __syncwarp();
-            if (lane == 0 && b + FWD_NST < nb) {
-                fence_proxy_async();  // the warp's reads of this stage are ordered before the copy that overwrites it
-                fwd_fetch(ring + s * FWD_SB * RS, &full[s], tile_packed, b + FWD_NST, n);
+            const int alive = __syncthreads_or(sm.done[lane & 7] != 0xffffffffu);  // barrier A: the batch's hit words are complete
+            if (alive == 0) break;  // every pixel of the tile is finished (forward.cu:309-311)
+            if (tid == 0 && b >= 1 && b - 1 + FWD_NST < nb) {
+                // every warp is past P2 of batch b-1: its stage can be refilled
+                fence_proxy_async();
+                fwd_fetch(s_stage + ((b - 1) % FWD_NST) * FWD_NB * RS, &sm.full[(b - 1) % FWD_NST], tile_packed, b - 1 + FWD_NST, n);
+                issued = b + FWD_NST;
+            }
+            // ---- work list of the pixels that have hits in this batch, longest chains first (counting sort): a P2 warp then
+            // holds 32 chains of about the same length ----
+            const bool fat = sm.anyfat[buf] != 0u;
+            {
+                unsigned w[FWD_NG], any = 0u;
+#pragma unroll
+                for (int k = 0; k < FWD_NG; k++) {
+                    w[k] = (k * 32 < cnt) ? sm.mask[buf][k][tid] : 0u;
+                    if (w[k]) sm.mask[buf][k][tid] = 0u;  // the buffer is clean again for batch b+2
+                    any |= w[k];
+                }
+                const bool act = any != 0u && !((sm.done[warp] >> lane) & 1u);
+                int hits = 0;
+#pragma unroll
+                for (int k = 0; k < FWD_NG; k++) hits += __popc(w[k]);
+                const int cls = 31 - min(hits - 1, 31);  // class 0 = the longest chains
+                uint32_t rank = 0;
+                if (act) rank = atomicAdd(&sm.hist[buf][cls], 1u);
+                if (tid < 32) sm.hist[buf ^ 1][tid] = 0u;  // every warp is past P2 of batch b-1; nobody is at batch b+1's list yet
+                if (tid == 32) { sm.tick_c[buf ^ 1] = 0u; sm.hdone[buf ^ 1] = 0u; sm.anyfat[buf ^ 1] = 0u; }  // batch b+1's P1 starts behind barrier B
+                __syncthreads();
+                uint32_t incl = sm.hist[buf][lane];
+                const uint32_t mine = incl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t base = __shfl_sync(FULL, incl - mine, cls);
+                if (act) {
+                    const uint32_t j = base + rank;
+                    sm.item[0][j] = (uint32_t)tid;
+#pragma unroll
+                    for (int k = 0; k < FWD_NG; k++) sm.item[1 + k][j] = w[k];
+                }
+                __syncthreads();  // barrier B: the work list is complete
+            }
+            // ================= P2: one listed pixel per lane, its hits in list order =================
+            int nact;
+            {
+                uint32_t tot = sm.hist[buf][lane];
+                tot = __reduce_add_sync(FULL, tot);
+                nact = (int)tot;
+            }
+            if (warp * 32 < nact) {
+                const bool have = tid < nact;
+                const int pid = have ? (int)sm.item[0][tid] : 0;
+                unsigned w[FWD_NG];
+                int left = 0;
+#pragma unroll
+                for (int k = 0; k < FWD_NG; k++) {
+                    w[k] = have ? sm.item[1 + k][tid] : 0u;
+                    left += __popc(w[k]);
+                }
+                const uint32_t lx = (uint32_t)pid & 15u, ly = (uint32_t)pid >> 4;
+                float4 S = sm.state[pid];  // C0 C1 C2 T
+                uint32_t lastr = 0xffffffffu, fin_flag = 0;
+                unsigned cw = w[0];
+                int ck = 0;
+                const float* const abuf = sm.alpha[buf] - 256;
+                const FwdHdr* const hbuf = sm.hdr[buf];
+                GHit* const hl = hitlog + slot_b0 - 256;
+                int rounds = __reduce_max_sync(FULL, left);
+                if (!fat) {
+#pragma unroll 1
+                    for (; rounds > 0; rounds--) {
+                        if (left > 0) {
+                            while (cw == 0u) {  // next non-empty word (left > 0 guarantees there is one)
+                                ck++;
+                                unsigned nx = 0u;
+#pragma unroll
+                                for (int k = 1; k < FWD_NG; k++) nx = (ck == k) ? w[k] : nx;
+                                cw = nx;
+                            }
+                            const uint32_t r = (uint32_t)(ck * 32 + __ffs(cw) - 1);
+                            cw &= cw - 1u;
+                            left--;
+                            const float4 h = *reinterpret_cast<const float4*>(&hbuf[r]);
+                            const uint32_t pk = __float_as_uint(h.w);
+                            const uint32_t idx = (pk >> 6) + ly * (pk & 31u) + lx;  // 256 + the pair's index in the batch
+                            const float al = abuf[idx];
+                            const float test_T = __fmul_rn(S.w, __fsub_rn(1.0f, al));
+                            if (test_T < 0.0001f) {
+                                fin_flag = 1u;
+                                left = 0;  // a finished pixel drops the rest of its queue
+                            } else {
+                                S.x = __fmaf_rn(S.w, __fmul_rn(al, h.x), S.x);
+                                S.y = __fmaf_rn(S.w, __fmul_rn(al, h.y), S.y);
+                                S.z = __fmaf_rn(S.w, __fmul_rn(al, h.z), S.z);
+                                if (log_on) *reinterpret_cast<float4*>(hl + idx) = S;  // (C_i, T_i): colour including the pair, transmittance in front of it
+                                S.w = test_T;
+                                lastr = r;
+                            }
+                        }
+                    }
+                } else {
+                    // a batch with fat groups: their pairs are evaluated here, by the pixel (the reference's own loop body)
+#pragma unroll 1
+                    for (; rounds > 0; rounds--) {
+                        if (left > 0) {
+                            while (cw == 0u) {
+                                ck++;
+                                unsigned nx = 0u;
+#pragma unroll
+                                for (int k = 1; k < FWD_NG; k++) nx = (ck == k) ? w[k] : nx;
+                                cw = nx;
+                            }
+                            const uint32_t r = (uint32_t)(ck * 32 + __ffs(cw) - 1);
+                            cw &= cw - 1u;
+                            left--;
+                            const float4 h = *reinterpret_cast<const float4*>(&hbuf[r]);
+                            const uint32_t pk = __float_as_uint(h.w);
+                            const uint32_t idx = (pk >> 6) + ly * (pk & 31u) + lx;
+                            float al;
+                            bool ok = true;
+                            if (!(pk & 32u)) {
+                                al = abuf[idx];
+                            } else {
+                                const unsigned char* rp = stage + r * RS;
+                                const float4 q0 = *reinterpret_cast<const float4*>(rp);
+                                const float2 co = *reinterpret_cast<const float2*>(rp + 16);
+                                float dx, dy;
+                                const float power = eval_power(q0.x, q0.y, q0.z, q0.w, co.x, small_int_to_float(kx + lx), small_int_to_float(ky + ly), dx, dy);
+                                al = fminf(0.99f, __fmul_rn(co.y, expf(power)));
+                                ok = !(power > 0.0f) && !(al < 1.0f / 255.0f);
+                            }
+                            if (ok) {
+                                const float test_T = __fmul_rn(S.w, __fsub_rn(1.0f, al));
+                                if (test_T < 0.0001f) {
+                                    fin_flag = 1u;
+                                    left = 0;
+                                } else {
+                                    S.x = __fmaf_rn(S.w, __fmul_rn(al, h.x), S.x);
+                                    S.y = __fmaf_rn(S.w, __fmul_rn(al, h.y), S.y);
+                                    S.z = __fmaf_rn(S.w, __fmul_rn(al, h.z), S.z);
+                                    if (log_on) *reinterpret_cast<float4*>(hl + idx) = S;
+                                    S.w = test_T;
+                                    lastr = r;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (have) {
+                    sm.state[pid] = S;
+                    if (lastr != 0xffffffffu) sm.last[pid] = (uint32_t)(b * FWD_NB + 1) + lastr;
+                    if (fin_flag) atomicOr(&sm.done[pid >> 5], 1u << (pid & 31));
+                }
             }
         }
-        // leaving early: the copies already issued for the next stages must have landed before the CTA can retire
-        for (int pb = b + 1; pb < min(nb, b + FWD_NST); pb++) mbar_wait(&full[pb % FWD_NST], (uint32_t)(pb / FWD_NST) & 1u);
+        // leaving early: the copies already issued must have landed before the CTA can retire
+        if (b < nb && tid == 0)
+            for (int pb = b + 1; pb < issued; pb++) mbar_wait(&sm.full[pb % FWD_NST], (uint32_t)(pb / FWD_NST) & 1u);
+        __syncthreads();
+        fin = sm.state[tid];
+        fin_last = sm.last[tid];
     }
-    if (g.inside) {
+    if (inside) {
+        const int px = tile_x0 + (tid & 15), py = tile_y0 + (tid >> 4);
         const size_t HW = (size_t)p.H * p.W;
-        const size_t pid = (size_t)g.py * p.W + g.px;
-        p.final_T[pid] = T;
-        p.n_contrib[pid] = last;
-        if (n > 0 && log_on) p.pixstate[pid] = make_float4(C0, C1, C2, T);  // read back by the hit-log backward only
-        p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), T, C0);  // forward.cu:372
-        p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), T, C1);
-        p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), T, C2);
+        const size_t pid = (size_t)py * p.W + px;
+        p.final_T[pid] = fin.w;
+        p.n_contrib[pid] = fin_last;
+        if (n > 0 && log_on) p.pixstate[pid] = fin;  // (C, T): read back by the hit-log backward only
+        p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), fin.w, fin.x);  // forward.cu:372
+        p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), fin.w, fin.y);
+        p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), fin.w, fin.z);
     }
 }
 

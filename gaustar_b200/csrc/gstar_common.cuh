@@ -62,7 +62,7 @@ static_assert(sizeof(GHeader) == 96, "GHeader layout");
 // One hit-log slot per (instance, pixel of its clipped footprint): what the forward blend knew when it blended the
 // pair -- transmittance in front of it and the colour accumulated up to and including it (blend.cu).
 struct __align__(16) GHit {
-    float T, c0, c1, c2;
+    float c0, c1, c2, T;  // the order of blend_fwd's per-pixel state registers: one 128-bit store, no moves
 };
 
 namespace gstar {
