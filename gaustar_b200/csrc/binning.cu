@@ -458,7 +458,8 @@ __device__ __forceinline__ void write_sorted(const BinParams& p, uint32_t tile, 
                 const uint32_t mean = tile_total / max(n, 1u);
                 uint32_t lanes = mean <= 14u ? 1u : mean <= 28u ? 2u : mean <= 64u ? 4u : 8u;
                 while (lanes < 8u && n * lanes < 256u && mean > 3u * lanes) lanes <<= 1;
-                p.tile_lanes[tile] = (unsigned char)lanes;
+                // bit 7: a fat tile (mean footprint above 24 pixels) -- blend_fwd takes the pixel-parallel path for it
+                p.tile_lanes[tile] = (unsigned char)(lanes | (mean > 24u ? 0x80u : 0u));
             }
         }
         gsync(g);

@@ -17,6 +17,9 @@
 //    one multi-value butterfly warp reduction and 9 RED ops per (Gaussian, warp) instead of 9 atomics per pair.
 #include "gstar_common.cuh"
 #include "gstar_kernels.h"
+#ifdef GSTAR_FWD_DEBUG_TIME
+#include <cstdio>
+#endif
 
 namespace gstar {
 
@@ -127,6 +130,186 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
     __syncwarp();
 }
 
+// ---- K6, fat tiles ---------------------------------------------------------------------------------------------------
+#ifndef GSTAR_FAT_SB
+#define GSTAR_FAT_SB 64
+#define GSTAR_FAT_NST 2
+#endif
+constexpr int FAT_SB = GSTAR_FAT_SB;   // records per stage
+constexpr int FAT_NW = FAT_SB / 32;
+constexpr int FAT_NST = GSTAR_FAT_NST;    // stages per warp
+constexpr int FAT_DYN_SMEM = NCONS * FAT_NST * FAT_SB * RS;  // 48 KB
+
+__device__ __forceinline__ void fat_fetch(unsigned char* stage, uint64_t* bar, const unsigned char* tile_packed, int b, int n)
+{
+    const uint32_t bytes = (uint32_t)min(FAT_SB, n - b * FAT_SB) * RS;
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(stage, tile_packed + (size_t)b * FAT_SB * RS, bytes, bar);
+}
+
+// (round 1's forward blend, kept for the tiles whose splats are fat: footprints that cover a large part of the tile make
+// lanes = pixels dense, and every warp streams the list on its own -- no CTA-wide phases)
+__device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const int tile, unsigned char* s_dyn)
+{
+    __shared__ __align__(8) uint64_t s_full[NCONS][FAT_NST];
+    const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
+    const int n = (int)(re - rs);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WarpGeom g = warp_geom(tile, p.gx, p.W, p.H);
+    const float pxf = (float)g.px, pyf = (float)g.py;
+    // hit log (see k_blend_bwd_gather): every blended (instance, pixel) pair records the transmittance in front of it
+    // and the colour accumulated up to and including it in the instance's slot for this pixel
+    const bool log_on = p.hdr->log_overflow == 0u;
+    GHit* const hitlog = reinterpret_cast<GHit*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
+    const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
+    const int lx = g.px - tile_x0, ly = g.py - tile_y0;
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t last = 0;
+    bool done = !g.inside;
+
+    if (n > 0 && __any_sync(FULL, !done)) {
+        unsigned char* const ring = s_dyn + (size_t)warp * FAT_NST * FAT_SB * RS;
+        uint64_t* const full = s_full[warp];
+        const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
+        const int nb = (n + FAT_SB - 1) / FAT_SB;
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < FAT_NST; s++) mbar_init(&full[s], 1);
+            fence_mbar_init();
+#pragma unroll
+            for (int s = 0; s < FAT_NST; s++)
+                if (s < nb) fat_fetch(ring + s * FAT_SB * RS, &full[s], tile_packed, s, n);
+        }
+        __syncwarp();
+        int b = 0;
+#pragma unroll 1
+        for (; b < nb; b++) {
+            const int s = b % FAT_NST;
+            const unsigned char* buf = ring + s * FAT_SB * RS;
+            mbar_wait(&full[s], (uint32_t)(b / FAT_NST) & 1u);
+            const unsigned live = __ballot_sync(FULL, !done);
+            if (live == 0) break;  // every pixel of the block is finished: this warp is done with the tile
+            const int cnt = min(FAT_SB, n - b * FAT_SB);
+            // per-pixel hit queue of the batch: bit k of word r = record 32 r + k may touch my pixel
+            unsigned w[FAT_NW];
+            int left = 0;
+#pragma unroll
+            for (int r = 0; r < FAT_NW; r++) {
+                w[r] = 0u;
+                if (r * 32 < cnt) {
+                    const unsigned pm = (r * 32 + lane < cnt) ? (block_pixel_mask(buf + (r * 32 + lane) * RS, g) & live) : 0u;
+                    if (__any_sync(FULL, pm != 0u)) w[r] = transpose32(pm, lane);
+                }
+                left += __popc(w[r]);
+            }
+            unsigned cw = w[0];  // word being walked, and its index
+            int cr = 0;
+#pragma unroll 1
+            while (__any_sync(FULL, left > 0)) {
+                int sl[4];
+                bool ok[4];
+                float al[4], cr_[4], cg[4], cbv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool have = left > 0;
+                    if (have) {
+                        while (cw == 0u) {  // next non-empty word (left > 0 guarantees there is one)
+                            cr++;
+                            unsigned nx = 0u;
+#pragma unroll
+                            for (int r = 1; r < FAT_NW; r++) nx = (cr == r) ? w[r] : nx;
+                            cw = nx;
+                        }
+                        sl[u] = cr * 32 + __ffs(cw) - 1;
+                        cw &= cw - 1u;
+                        left--;
+                    } else {
+                        sl[u] = 0;
+                    }
+                    const unsigned char* rp = buf + sl[u] * RS;
+                    const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
+                    const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
+                    cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
+                    cr_[u] = q1.z; cg[u] = q1.w;
+                    float dx, dy;
+                    const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
+                    al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
+                    ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (ok[u] && !done) {
+                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            C0 = __fmaf_rn(T, __fmul_rn(al[u], cr_[u]), C0);
+                            C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
+                            C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
+                            if (log_on) {
+                                const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // foot gid b slot
+                                const Foot f = unpack_foot(tail.x);
+                                GHit h;
+                                h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
+                                hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
+                            }
+                            T = test_T;
+                            last = (uint32_t)(b * FAT_SB + sl[u] + 1);
+                        }
+                    }
+                }
+                if (done) left = 0;  // a finished pixel drops the rest of its queue
+            }
+            __syncwarp();
+            if (lane == 0 && b + FAT_NST < nb) {
+                fence_proxy_async();  // the warp's reads of this stage are ordered before the copy that overwrites it
+                fat_fetch(ring + s * FAT_SB * RS, &full[s], tile_packed, b + FAT_NST, n);
+            }
+        }
+        // leaving early: the copies already issued for the next stages must have landed before the CTA can retire
+        for (int pb = b + 1; pb < min(nb, b + FAT_NST); pb++) mbar_wait(&full[pb % FAT_NST], (uint32_t)(pb / FAT_NST) & 1u);
+        __syncwarp();
+        if (lane == 0) {  // the persistent caller runs the next marked tile through the same barriers
+#pragma unroll
+            for (int s = 0; s < FAT_NST; s++) mbar_inval(&full[s]);
+        }
+        __syncwarp();
+    }
+    if (g.inside) {
+        const size_t HW = (size_t)p.H * p.W;
+        const size_t pid = (size_t)g.py * p.W + g.px;
+        p.final_T[pid] = T;
+        p.n_contrib[pid] = last;
+        if (n > 0 && log_on) p.pixstate[pid] = make_float4(C0, C1, C2, T);  // read back by the hit-log backward only
+        p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), T, C0);  // forward.cu:372
+        p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), T, C1);
+        p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), T, C2);
+    }
+}
+
+
+// Persistent: a few CTAs per SM stride over the non-empty tiles and take the marked ones (none on a surface scene: the
+// kernel then costs a launch).
+constexpr int FAT_CTAS_PER_SM = 4;
+__global__ void __launch_bounds__(NCONS * 32, FAT_CTAS_PER_SM) k_blend_fwd_fat(BlendParams p)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    if (p.hdr->overflow || !p.tile_lanes) return;
+    const uint32_t ntiles = p.hdr->cls_end[3];  // the non-empty tiles lead tile_order, longest list first
+    __shared__ uint32_t s_item;
+    uint32_t* const cursor = const_cast<uint32_t*>(&p.hdr->pad0[2]);  // zeroed by tile_scan (and by k_recolor for a re-blend)
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const uint32_t i = s_item;
+        __syncthreads();  // (everyone has read the ticket before the next one overwrites it; also fences the previous tile's rings)
+        if (i >= ntiles) break;
+        const int tile = (int)p.tile_order[i];
+        if (p.tile_lanes[tile] & 0x80u) blend_fwd_fat_tile(p, tile, s_dyn);
+    }
+}
+
 // ---- K6: forward blend ---------------------------------------------------------------------------------------------
 // One CTA (256 threads) per 16x16 tile; the tile's packed records arrive in batches of FWD_NB through a ring of TMA bulk
 // copies (thread 0 issues one cp.async.bulk per batch; completion on the stage's mbarrier).  A batch goes through two
@@ -158,8 +341,10 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
 constexpr int FWD_NB = 128;                 // records per batch
 constexpr int FWD_NG = FWD_NB / 32;         // 32-record groups per batch == hit words per pixel
 constexpr int FWD_WARPS = 8;
-constexpr int FWD_WPG = FWD_WARPS / FWD_NG; // warps sharing a group's pairs
-constexpr int FWD_NST = 3;                  // record stages in flight
+#ifndef GSTAR_FWD_NST
+#define GSTAR_FWD_NST 3
+#endif
+constexpr int FWD_NST = GSTAR_FWD_NST;      // record stages in flight
 constexpr int FWD_ACAP = GSTAR_FWD_ACAP;    // alpha slots per batch
 constexpr int FWD_GCAP = 2048;              // pairs of a group that goes through the alpha buffer
 constexpr int FWD_GW = FWD_GCAP / 32;       // words of its record-start vector
@@ -173,7 +358,7 @@ struct __align__(16) FwdHdr {   // what P2 needs of a record
 };
 struct FwdGroup {               // P1 scratch of a 32-record group, written by the warp that drew the group's header ticket
     uint32_t words[FWD_GW];     // record starts in the group's pair space (bit q: a record's first pair is q)
-    uint32_t pref[FWD_GW];      // records that start in the words before word c
+    uint2 wp[FWD_GW];           // (words[c], records that start in the words before word c)
     uint2 prec[32];             // rank -> (first pair | w << 16 | record's lane << 24,  magic | x0 << 16 | y0 << 24)
     uint32_t total, light, rel0, pad;
 };
@@ -181,7 +366,7 @@ struct FwdSmem {
     float alpha[2][FWD_ACAP];
     FwdHdr hdr[2][FWD_NB];
     uint32_t mask[2][FWD_NG][256];   // hit words, [word][pixel]
-    uint32_t item[FWD_NG + 1][256];  // P2 work list: pixel id, its hit words
+    uint32_t item[256];              // P2 work list: pixel ids, longest chains first
     float4 state[256];               // per pixel (C0, C1, C2, T)
     uint32_t last[256];              // per pixel last contributor
     FwdGroup grp[FWD_NG];
@@ -189,11 +374,19 @@ struct FwdSmem {
     uint32_t done[8];                // pixels that reached T < 1e-4 (or lie outside the image)
     uint32_t hist[2][32];            // P2 work list, counting sort by chain length: pixels per length class
     // P1 work of a batch is drawn by whichever warp is free (the warps still busy with the previous batch's P2 draw less)
-    uint32_t tick_c[2], hdone[2], anyfat[2];
+    uint32_t tick_c[2], anyfat[2];
     uint64_t full[FWD_NST];
+    uint64_t hbar[2];                // the batch's group headers are complete (4 arrivals: warps 4..7)
 };
-constexpr int FWD_DYN_SMEM = FWD_NST * FWD_NB * RS + (int)sizeof(FwdSmem);
+#ifndef GSTAR_FWD_SMEM_PAD
+#define GSTAR_FWD_SMEM_PAD 0
+#endif
+constexpr int FWD_DYN_SMEM = FWD_NST * FWD_NB * RS + (int)sizeof(FwdSmem) + GSTAR_FWD_SMEM_PAD;  // (the pad: occupancy experiments)
 constexpr int FWD_UNITS = 4;  // P1 work units per group (strided chunks)
+#ifndef GSTAR_FWD_U
+#define GSTAR_FWD_U 3
+#endif
+constexpr int FWD_U = GSTAR_FWD_U;  // hits per P2 pass
 
 __device__ __forceinline__ void fwd_fetch(unsigned char* stage, uint64_t* bar, const unsigned char* tile_packed, int b, int n)
 {
@@ -270,7 +463,7 @@ __device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned cha
             if (lane >= d) incl += v;
         }
         const uint32_t ex = incl - c0 - c1;
-        *reinterpret_cast<uint2*>(&G.pref[2 * lane]) = make_uint2(ex, ex + c0);
+        *reinterpret_cast<uint4*>(&G.wp[2 * lane]) = make_uint4(ww.x, ex, ww.y, ex + c0);
     }
 }
 
@@ -282,7 +475,11 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
     FwdSmem& sm = *reinterpret_cast<FwdSmem*>(s_dyn + FWD_NST * FWD_NB * RS);
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
+#ifdef GSTAR_FWD_SKIP_TOP
+    const int n = blockIdx.x < GSTAR_FWD_SKIP_TOP ? 0 : (int)(re - rs);  // experiment: how long does the kernel take without its longest lists?
+#else
     const int n = (int)(re - rs);
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_ty = tile / p.gx;
     const int tile_x0 = (tile - tile_ty * p.gx) * GSTAR_TILE, tile_y0 = tile_ty * GSTAR_TILE;
@@ -296,8 +493,17 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         p.host_counts[4] = (uint32_t)need;
         p.host_counts[5] = (uint32_t)(need >> 32);
     }
+    // tile_sort marks the tiles whose footprints average more than 24 pixels: their pairs would not fit the alpha buffer
+    // anyway, and with footprints that large the pixel-parallel formulation is the dense one
+    if (n > 0 && p.tile_lanes && (p.tile_lanes[tile] & 0x80u)) return;  // k_blend_fwd_fat's
     float4 fin = make_float4(0.f, 0.f, 0.f, 1.0f);  // (C, T) of my pixel
     uint32_t fin_last = 0;
+#ifdef GSTAR_FWD_DEBUG_TIME
+    unsigned long long t_start = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    long long dbg_t[6] = {0, 0, 0, 0, 0, 0}, dbg_c = 0;
+    int dbg_n = 0, dbg_rounds = 0, dbg_hits = 0, dbg_items = 0;
+#endif
 
     if (n > 0) {
         const unsigned char* tile_packed = p.packed + (size_t)rs * RS;
@@ -307,7 +513,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         sm.last[tid] = 0u;
         if (tid < 17) sm.magic[tid] = tid ? (4096u + (uint32_t)tid - 1u) / (uint32_t)tid : 0u;
         if (tid < 64) (&sm.hist[0][0])[tid] = 0u;
-        if (tid < 2) { sm.tick_c[tid] = 0u; sm.hdone[tid] = 0u; sm.anyfat[tid] = 0u; }
+        if (tid < 2) { sm.tick_c[tid] = 0u; sm.anyfat[tid] = 0u; }
         {
             const unsigned out = __ballot_sync(FULL, !inside);
             if (lane == 0) sm.done[warp] = out;
@@ -315,6 +521,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         if (tid == 0) {
 #pragma unroll
             for (int s = 0; s < FWD_NST; s++) mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.hbar[0], FWD_NG);
+            mbar_init(&sm.hbar[1], FWD_NG);
             fence_mbar_init();
 #pragma unroll
             for (int s = 0; s < FWD_NST; s++)
@@ -322,6 +530,11 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         }
         int issued = min(nb, FWD_NST);  // batches whose copy has been issued (meaningful in thread 0)
         __syncthreads();
+        // Warp roles: warp w takes entries [32 w, 32 w + 32) of a batch's P2 work list (longest chains first, so warp 0 mostly
+        // runs the serial recurrences and draws little pair work); warps 4..7 build the group headers.  (Keeping the pair
+        // work off the schedulers of the long-chain warps was tried: no gain.)
+        const int p2_rank = warp;
+        const int hdr_grp = warp >= FWD_NG ? warp - FWD_NG : -1;
         const uint32_t kx = 0x4B000000u + (uint32_t)tile_x0, ky = 0x4B000000u + (uint32_t)tile_y0;
         const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
         int b = 0;
@@ -329,19 +542,27 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         for (; b < nb; b++) {
             const int st = b % FWD_NST, buf = b & 1;
             const unsigned char* stage = s_stage + st * FWD_NB * RS;
+#ifdef GSTAR_FWD_DEBUG_TIME
+            dbg_c = clock64();
+#endif
             mbar_wait(&sm.full[st], (uint32_t)(b / FWD_NST) & 1u);
+#ifdef GSTAR_FWD_DEBUG_TIME
+            dbg_t[5] += clock64() - dbg_c; dbg_c = clock64();
+#endif
             const int cnt = min(FWD_NB, n - b * FWD_NB);
             const uint32_t slot_b0 = *reinterpret_cast<const uint32_t*>(stage + 44);  // first pair of the batch
             // ================= P1: group headers (warps 4..7), then the batch's pairs in 16 work units drawn by ticket =================
             {
                 const uint32_t ng = (uint32_t)(cnt + 31) >> 5;
-                if (warp >= FWD_NG && (uint32_t)(warp - FWD_NG) < ng) {
-                    fwd_group_header(sm, stage, buf, warp - FWD_NG, cnt, slot_b0, lane);
+                if (hdr_grp >= 0) {
+                    if ((uint32_t)hdr_grp < ng) fwd_group_header(sm, stage, buf, hdr_grp, cnt, slot_b0, lane);
                     __syncwarp();
-                    if (lane == 0) { __threadfence_block(); atomicAdd(&sm.hdone[buf], 1u); }
+                    if (lane == 0) mbar_arrive(&sm.hbar[buf]);
                 }
-                while (lds_volatile(&sm.hdone[buf]) < ng) {}
-                __threadfence_block();
+                mbar_wait(&sm.hbar[buf], (uint32_t)(b >> 1) & 1u);
+#ifdef GSTAR_FWD_DEBUG_TIME
+                dbg_t[0] += clock64() - dbg_c; dbg_c = clock64();
+#endif
                 float* const abase = sm.alpha[buf];
 #pragma unroll 1
                 for (;;) {
@@ -355,23 +576,65 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                         float* const ab = abase + G.rel0;
                         uint32_t* const mk = sm.mask[buf][g];
                         const unsigned char* const gstage = stage + g * 32 * RS;
+                        // chunks j, j+4, j+8, ... of the group's pair space, two per iteration while two are left (their loads and
+                        // exponentials overlap), then the odd one
+                        const uint32_t nch = (total + 31u) >> 5;
+                        uint32_t c = j;
 #pragma unroll 1
-                        for (uint32_t q = j * 32u + (uint32_t)lane; q < total; q += FWD_UNITS * 32u) {
-                            const uint32_t c = q >> 5;
-                            const uint2 pr = G.prec[G.pref[c] + (uint32_t)__popc(G.words[c] & le_mask) - 1u];
-                            const uint32_t rl = pr.x >> 24;
-                            const uint32_t off = q - (pr.x & 0xffffu), fw = __byte_perm(pr.x, 0u, 0x4442);
-                            const uint32_t yy = (off * (pr.y & 0xffffu)) >> 12, xx = off - yy * fw;
-                            const uint32_t plx = __byte_perm(pr.y, 0u, 0x4442) + xx, ply = (pr.y >> 24) + yy;
-                            const unsigned char* rp = gstage + rl * RS;
-                            const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
-                            const float2 co = *reinterpret_cast<const float2*>(rp + 16);  // C o
-                            float dx, dy;
-                            const float power = eval_power(q0.x, q0.y, q0.z, q0.w, co.x, small_int_to_float(kx + plx), small_int_to_float(ky + ply), dx, dy);
-                            const float al = fminf(0.99f, __fmul_rn(co.y, expf(power)));
-                            if (!(power > 0.0f) && !(al < 1.0f / 255.0f)) {  // forward.cu:336-345
-                                ab[q] = al;
-                                atomicOr(&mk[ply * 16u + plx], 1u << rl);
+                        for (; c + FWD_UNITS < nch; c += 2u * FWD_UNITS) {
+                            uint2 pr[2];
+                            uint32_t qq[2];
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                qq[u] = (c + (uint32_t)u * FWD_UNITS) * 32u + (uint32_t)lane;
+                                const uint2 wp = G.wp[c + (uint32_t)u * FWD_UNITS];
+                                pr[u] = G.prec[wp.y + (uint32_t)__popc(wp.x & le_mask) - 1u];
+                            }
+                            float4 q0[2];
+                            float2 co[2];
+                            uint32_t plx[2], ply[2];
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                const unsigned char* rp = gstage + (pr[u].x >> 24) * RS;
+                                q0[u] = *reinterpret_cast<const float4*>(rp);       // x y A B
+                                co[u] = *reinterpret_cast<const float2*>(rp + 16);  // C o
+                                const uint32_t off = qq[u] - (pr[u].x & 0xffffu), fw = __byte_perm(pr[u].x, 0u, 0x4442);
+                                const uint32_t yy = (off * (pr[u].y & 0xffffu)) >> 12, xx = off - yy * fw;
+                                plx[u] = __byte_perm(pr[u].y, 0u, 0x4442) + xx;
+                                ply[u] = (pr[u].y >> 24) + yy;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                float dx, dy;
+                                const float power = eval_power(q0[u].x, q0[u].y, q0[u].z, q0[u].w, co[u].x, small_int_to_float(kx + plx[u]),
+                                                               small_int_to_float(ky + ply[u]), dx, dy);
+                                const float al = fminf(0.99f, __fmul_rn(co[u].y, expf(power)));
+                                // (the last chunk of a group may be partial: only the second of the two can be it)
+                                if ((u == 0 || qq[u] < total) && !(power > 0.0f) && !(al < 1.0f / 255.0f)) {  // forward.cu:336-345
+                                    ab[qq[u]] = al;
+                                    atomicOr(&mk[ply[u] * 16u + plx[u]], 1u << (pr[u].x >> 24));
+                                }
+                            }
+                        }
+                        if (c < nch) {
+                            const uint32_t q = c * 32u + (uint32_t)lane;
+                            if (q < total) {
+                                const uint2 wp = G.wp[c];
+                                const uint2 pr = G.prec[wp.y + (uint32_t)__popc(wp.x & le_mask) - 1u];
+                                const uint32_t rl = pr.x >> 24;
+                                const unsigned char* rp = gstage + rl * RS;
+                                const float4 q0 = *reinterpret_cast<const float4*>(rp);       // x y A B
+                                const float2 co = *reinterpret_cast<const float2*>(rp + 16);  // C o
+                                const uint32_t off = q - (pr.x & 0xffffu), fw = __byte_perm(pr.x, 0u, 0x4442);
+                                const uint32_t yy = (off * (pr.y & 0xffffu)) >> 12, xx = off - yy * fw;
+                                const uint32_t plx = __byte_perm(pr.y, 0u, 0x4442) + xx, ply = (pr.y >> 24) + yy;
+                                float dx, dy;
+                                const float power = eval_power(q0.x, q0.y, q0.z, q0.w, co.x, small_int_to_float(kx + plx), small_int_to_float(ky + ply), dx, dy);
+                                const float al = fminf(0.99f, __fmul_rn(co.y, expf(power)));
+                                if (!(power > 0.0f) && !(al < 1.0f / 255.0f)) {  // forward.cu:336-345
+                                    ab[q] = al;
+                                    atomicOr(&mk[ply * 16u + plx], 1u << rl);
+                                }
                             }
                         }
                     } else {
@@ -388,7 +651,13 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                     }
                 }
             }
+#ifdef GSTAR_FWD_DEBUG_TIME
+            dbg_t[1] += clock64() - dbg_c; dbg_c = clock64();
+#endif
             const int alive = __syncthreads_or(sm.done[lane & 7] != 0xffffffffu);  // barrier A: the batch's hit words are complete
+#ifdef GSTAR_FWD_DEBUG_TIME
+            dbg_t[2] += clock64() - dbg_c; dbg_c = clock64();
+#endif
             if (alive == 0) break;  // every pixel of the tile is finished (forward.cu:309-311)
             if (tid == 0 && b >= 1 && b - 1 + FWD_NST < nb) {
                 // every warp is past P2 of batch b-1: its stage can be refilled
@@ -404,10 +673,13 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
 #pragma unroll
                 for (int k = 0; k < FWD_NG; k++) {
                     w[k] = (k * 32 < cnt) ? sm.mask[buf][k][tid] : 0u;
-                    if (w[k]) sm.mask[buf][k][tid] = 0u;  // the buffer is clean again for batch b+2
                     any |= w[k];
                 }
                 const bool act = any != 0u && !((sm.done[warp] >> lane) & 1u);
+                if (any != 0u && !act) {  // hits of a finished pixel: dropped here (a listed pixel's words are cleared by its P2 lane)
+#pragma unroll
+                    for (int k = 0; k < FWD_NG; k++) sm.mask[buf][k][tid] = 0u;
+                }
                 int hits = 0;
 #pragma unroll
                 for (int k = 0; k < FWD_NG; k++) hits += __popc(w[k]);
@@ -415,7 +687,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                 uint32_t rank = 0;
                 if (act) rank = atomicAdd(&sm.hist[buf][cls], 1u);
                 if (tid < 32) sm.hist[buf ^ 1][tid] = 0u;  // every warp is past P2 of batch b-1; nobody is at batch b+1's list yet
-                if (tid == 32) { sm.tick_c[buf ^ 1] = 0u; sm.hdone[buf ^ 1] = 0u; sm.anyfat[buf ^ 1] = 0u; }  // batch b+1's P1 starts behind barrier B
+                if (tid == 32) { sm.tick_c[buf ^ 1] = 0u; sm.anyfat[buf ^ 1] = 0u; }  // batch b+1's P1 starts behind barrier B
                 __syncthreads();
                 uint32_t incl = sm.hist[buf][lane];
                 const uint32_t mine = incl;
@@ -426,10 +698,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                 }
                 const uint32_t base = __shfl_sync(FULL, incl - mine, cls);
                 if (act) {
-                    const uint32_t j = base + rank;
-                    sm.item[0][j] = (uint32_t)tid;
-#pragma unroll
-                    for (int k = 0; k < FWD_NG; k++) sm.item[1 + k][j] = w[k];
+                    sm.item[base + rank] = (uint32_t)tid;
                 }
                 __syncthreads();  // barrier B: the work list is complete
             }
@@ -440,14 +709,19 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                 tot = __reduce_add_sync(FULL, tot);
                 nact = (int)tot;
             }
-            if (warp * 32 < nact) {
-                const bool have = tid < nact;
-                const int pid = have ? (int)sm.item[0][tid] : 0;
+#ifdef GSTAR_FWD_DEBUG_TIME
+            dbg_t[3] += clock64() - dbg_c; dbg_c = clock64(); dbg_n += (warp * 32 < nact);
+#endif
+            if (p2_rank * 32 < nact) {
+                const int li = p2_rank * 32 + lane;  // my entry of the work list
+                const bool have = li < nact;
+                const int pid = have ? (int)sm.item[li] : 0;
                 unsigned w[FWD_NG];
                 int left = 0;
 #pragma unroll
                 for (int k = 0; k < FWD_NG; k++) {
-                    w[k] = have ? sm.item[1 + k][tid] : 0u;
+                    w[k] = (have && k * 32 < cnt) ? sm.mask[buf][k][pid] : 0u;
+                    if (w[k]) sm.mask[buf][k][pid] = 0u;  // the buffer is clean again for batch b+2
                     left += __popc(w[k]);
                 }
                 const uint32_t lx = (uint32_t)pid & 15u, ly = (uint32_t)pid >> 4;
@@ -458,39 +732,58 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                 const float* const abuf = sm.alpha[buf] - 256;
                 const FwdHdr* const hbuf = sm.hdr[buf];
                 GHit* const hl = hitlog + slot_b0 - 256;
+                char* const hlb = reinterpret_cast<char*>(hl);
                 int rounds = __reduce_max_sync(FULL, left);
+#ifdef GSTAR_FWD_DEBUG_TIME
+                dbg_rounds += rounds; dbg_hits += __reduce_add_sync(FULL, left); dbg_items += min(32, nact - p2_rank * 32);
+#endif
                 if (!fat) {
-#pragma unroll 1
-                    for (; rounds > 0; rounds--) {
-                        if (left > 0) {
-                            while (cw == 0u) {  // next non-empty word (left > 0 guarantees there is one)
-                                ck++;
-                                unsigned nx = 0u;
+                    // Word by word (32 records each) with a warp-uniform trip count per word, FWD_U hits per pass, and no
+                    // data-dependent branches in the body: a lane without a hit in this pass runs through predicated off.  The
+                    // record headers and alphas of a pass are fetched together; only the T recurrence is a dependent chain.
+                    bool live = have;
 #pragma unroll
-                                for (int k = 1; k < FWD_NG; k++) nx = (ck == k) ? w[k] : nx;
-                                cw = nx;
+                    for (int k = 0; k < FWD_NG; k++) {
+                        unsigned cw = live ? w[k] : 0u;
+                        int rk = __reduce_max_sync(FULL, __popc(cw));
+#pragma unroll 1
+                        for (; rk > 0; rk -= FWD_U) {
+                            uint32_t r[FWD_U], idx[FWD_U];
+                            float4 h[FWD_U];
+                            float al[FWD_U];
+                            bool v[FWD_U];
+#pragma unroll
+                            for (int u = 0; u < FWD_U; u++) {
+                                v[u] = cw != 0u;
+                                r[u] = (uint32_t)(k * 32) + (v[u] ? (uint32_t)(__ffs(cw) - 1) : 0u);
+                                cw &= cw - 1u;
+                                h[u] = *reinterpret_cast<const float4*>(&hbuf[r[u]]);
                             }
-                            const uint32_t r = (uint32_t)(ck * 32 + __ffs(cw) - 1);
-                            cw &= cw - 1u;
-                            left--;
-                            const float4 h = *reinterpret_cast<const float4*>(&hbuf[r]);
-                            const uint32_t pk = __float_as_uint(h.w);
-                            const uint32_t idx = (pk >> 6) + ly * (pk & 31u) + lx;  // 256 + the pair's index in the batch
-                            const float al = abuf[idx];
-                            const float test_T = __fmul_rn(S.w, __fsub_rn(1.0f, al));
-                            if (test_T < 0.0001f) {
-                                fin_flag = 1u;
-                                left = 0;  // a finished pixel drops the rest of its queue
-                            } else {
-                                S.x = __fmaf_rn(S.w, __fmul_rn(al, h.x), S.x);
-                                S.y = __fmaf_rn(S.w, __fmul_rn(al, h.y), S.y);
-                                S.z = __fmaf_rn(S.w, __fmul_rn(al, h.z), S.z);
-                                if (log_on) *reinterpret_cast<float4*>(hl + idx) = S;  // (C_i, T_i): colour including the pair, transmittance in front of it
-                                S.w = test_T;
-                                lastr = r;
+#pragma unroll
+                            for (int u = 0; u < FWD_U; u++) {
+                                const uint32_t pk = __float_as_uint(h[u].w);
+                                idx[u] = (pk >> 6) + ly * (pk & 31u) + lx;  // 256 + the pair's index in the batch
+                                al[u] = abuf[v[u] ? idx[u] : 256u];
                             }
+#pragma unroll
+                            for (int u = 0; u < FWD_U; u++) {
+                                const float test_T = __fmul_rn(S.w, __fsub_rn(1.0f, al[u]));
+                                const bool hit = v[u] && live;
+                                const bool fin = hit && test_T < 0.0001f;  // forward.cu:351-355: the pair is not blended, the pixel is finished
+                                const bool upd = hit && !fin;
+                                live = live && !fin;
+                                const float c0 = __fmaf_rn(S.w, __fmul_rn(al[u], h[u].x), S.x);
+                                const float c1 = __fmaf_rn(S.w, __fmul_rn(al[u], h[u].y), S.y);
+                                const float c2 = __fmaf_rn(S.w, __fmul_rn(al[u], h[u].z), S.z);
+                                S.x = upd ? c0 : S.x; S.y = upd ? c1 : S.y; S.z = upd ? c2 : S.z;
+                                if (upd && log_on) *reinterpret_cast<float4*>(hlb + (size_t)idx[u] * sizeof(GHit)) = S;  // (C_i, T_i): colour including the pair, transmittance in front of it
+                                S.w = upd ? test_T : S.w;
+                                lastr = upd ? r[u] : lastr;
+                            }
+                            if (!live) cw = 0u;
                         }
                     }
+                    fin_flag = (have && !live) ? 1u : 0u;
                 } else {
                     // a batch with fat groups: their pairs are evaluated here, by the pixel (the reference's own loop body)
 #pragma unroll 1
@@ -539,6 +832,9 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                         }
                     }
                 }
+#ifdef GSTAR_FWD_DEBUG_TIME
+                dbg_t[4] += clock64() - dbg_c;
+#endif
                 if (have) {
                     sm.state[pid] = S;
                     if (lastr != 0xffffffffu) sm.last[pid] = (uint32_t)(b * FWD_NB + 1) + lastr;
@@ -552,6 +848,18 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         __syncthreads();
         fin = sm.state[tid];
         fin_last = sm.last[tid];
+#ifdef GSTAR_FWD_DEBUG_TIME
+        if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 20 || blockIdx.x == 200 || blockIdx.x == 600 || blockIdx.x == 1000)) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            printf("blk %d n=%d batches=%d start=%llu dur=%llu ns\n", blockIdx.x, n, nb, t_start % 100000000ull, t_end - t_start);
+        }
+        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 600))
+            printf("  blk %d warp %d cycles: stagewait %lld hdr+wait %lld units %lld barA %lld build..B %lld P2 %lld (P2 batches %d)\n", blockIdx.x, warp, dbg_t[5], dbg_t[0], dbg_t[1], dbg_t[2],
+                   dbg_t[3], dbg_t[4], dbg_n);
+        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 600 || blockIdx.x == 300))
+            printf("  blk %d warp %d P2: batches %d rounds %d hits %d items %d\n", blockIdx.x, warp, dbg_n, dbg_rounds, dbg_hits, dbg_items);
+#endif
     }
     if (inside) {
         const int px = tile_x0 + (tid & 15), py = tile_y0 + (tid >> 4);
@@ -792,7 +1100,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
     // Lanes per instance, chosen per tile by the sort kernel from the mean footprint area and the list length: one for
     // the tiny splats of a dense surface, 2/4/8 when footprints are large or the tile has fewer instances than threads
     // (a single lane would walk a 50-pixel footprint through 50 dependent hit-log loads).
-    const int L = p.tile_lanes ? (int)p.tile_lanes[tile] : 1;
+    const int L = p.tile_lanes ? (int)(p.tile_lanes[tile] & 0x7fu) : 1;  // (bit 7: the forward's fat-tile mark)
     if (L <= 1) {
 #pragma unroll 1
     for (uint32_t i = tid; i < total; i += GATHER_THREADS) {
@@ -924,6 +1232,7 @@ __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src,
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && disable_log) hdr->log_overflow = 1u;  // inference re-blend: no hit log (the new binning buffer has none)
+    if (i == 0) hdr->pad0[2] = 0u;  // k_blend_fwd_fat's tile cursor (the header is a copy of the source call's)
     if (i == 0 && cam.src_view) {
         // the caller's "same camera" claim, verified where it costs nothing: a re-blend through another camera must not
         // produce a plausible image of the wrong view.  overflow = 2 makes the blend kernels skip this call; k_poison
@@ -962,8 +1271,24 @@ void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, 
                                                 hdr, disable_log, cam);
 }
 
-int blend_setup() { return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM); }
-void launch_blend_fwd(const BlendParams& p, cudaStream_t s) { k_blend_fwd<<<p.gx * p.gy, FWD_THREADS, FWD_DYN_SMEM, s>>>(p); }
+static int g_blend_sms = 0;
+int blend_setup()
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&g_blend_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_blend_fwd_fat, cudaFuncAttributeMaxDynamicSharedMemorySize, FAT_DYN_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM);
+}
+void launch_blend_fwd(const BlendParams& p, cudaStream_t s)
+{
+    k_blend_fwd<<<p.gx * p.gy, FWD_THREADS, FWD_DYN_SMEM, s>>>(p);
+    const int sms = g_blend_sms > 0 ? g_blend_sms : 148;
+    k_blend_fwd_fat<<<min(p.gx * p.gy, sms * FAT_CTAS_PER_SM), NCONS * 32, FAT_DYN_SMEM, s>>>(p);
+}
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
 void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s) { k_blend_bwd_gather<<<p.gx * p.gy, GATHER_THREADS, 0, s>>>(p); }
 

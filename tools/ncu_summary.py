@@ -67,10 +67,57 @@ def source(path, kernel, top=40):
         print(f"{100*ins/tot_i:5.1f}% inst {100*smp/tot_s:5.1f}% smp  L{ln:>4d}  {src[:120]}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] != "regions":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 1)
     elif sys.argv[1] == "source":
         source(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
     else:
         full(sys.argv[2])
+
+
+def regions(path, kernel, srcfile, markers):
+    """Instructions and stall samples per source region. markers: substrings of source lines that START a region (in file order)."""
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kernel],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
+    H = rows[hi]
+    idx = {h: i for i, h in enumerate(H)}
+    stalls = [h for h in H if h.startswith("stall_") and "Not Issued" not in h]
+    src = open(srcfile).read().split("\n")
+    starts = []
+    for m in markers:
+        ln = [i + 1 for i, l in enumerate(src) if m in l]
+        starts.append((ln[0] if ln else 10**9, m))
+    starts.sort()
+    agg = [collections.Counter() for _ in starts]
+    inst = [0] * len(starts)
+    tinst = [0] * len(starts)
+    for r in rows[hi + 1:]:
+        if len(r) < len(H) or not r[0].strip().isdigit():
+            continue
+        ln = int(r[0])
+        k = max([i for i, (s, _) in enumerate(starts) if s <= ln], default=None)
+        if k is None:
+            continue
+        try:
+            inst[k] += int(r[idx["Instructions Executed"]]); tinst[k] += int(r[idx["Thread Instructions Executed"]])
+        except ValueError:
+            pass
+        for s in stalls:
+            try:
+                agg[k][s] += int(r[idx[s]])
+            except ValueError:
+                pass
+    ti = sum(inst) or 1
+    ts = sum(sum(a.values()) for a in agg) or 1
+    for (s, m), n, tn, a in zip(starts, inst, tinst, agg):
+        tot = sum(a.values())
+        top = " ".join(f"{k.replace('stall_', '')}={100 * v / max(tot, 1):.0f}%" for k, v in a.most_common(5))
+        print(f"L{s:4d} {m[:38]:38s} inst {100 * n / ti:5.1f}% ({n / 1e6:6.2f}M, {tn / max(n, 1):4.1f} lanes)  samples {100 * tot / ts:5.1f}%  [{top}]")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "regions":
+    regions(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5:])
