@@ -272,14 +272,15 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bp.ranges = (uint32_t*)(img + IL.ranges);
     bp.tile_order = (uint32_t*)(img + IL.tile_order);
     bp.tile_lanes = (unsigned char*)(img + IL.tile_lanes);
-    bp.host_counts = ctx->host_counts_dev;
+    // a captured call must not touch the thread's pinned counters: its replays would race with un-captured calls reading them
+    bp.host_counts = capturing ? nullptr : ctx->host_counts_dev;
 
     BlendParams bl;
     bl.W = W; bl.H = H; bl.gx = gx; bl.gy = gy;
     bl.recs = (const GRec*)geom; bl.hdr = hdr; bl.ranges = bp.ranges; bl.tile_order = bp.tile_order; bl.bg = a->background;
     bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
     bl.dL_dpix = nullptr; bl.gacc = nullptr; bl.tile_lanes = bp.tile_lanes;
-    bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = ctx->host_counts_dev;
+    bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = capturing ? nullptr : ctx->host_counts_dev;
 
     // Hit-log provision: the slots the previous view needed (published by its blend_fwd; a hint, it may lag) with the
     // same grow-at-once / shrink-slowly / quantised policy as the instance count.  A view whose log does not fit simply
@@ -354,6 +355,9 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             STAGE_CHECK("blend_fwd");
         }
         if (capturing) {
+            // a replay whose view needs more instances than `cap` leaves the header's overflow flag set and blends nothing:
+            // the image is then filled with NaN instead of being returned uninitialised
+            if (cap > 0) launch_poison(hdr, a->out_color, (size_t)3 * W * H, stream, 1);
             R = (uint32_t)cap;
             break;
         }

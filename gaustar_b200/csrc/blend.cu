@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                 uint32_t lastr = 0xffffffffu, fin_flag = 0;
                 unsigned cw = w[0];
                 int ck = 0;
-                const float* const abuf = sm.alpha[buf] - 256;
+                const float* const abuf = sm.alpha[buf];  // (indices carry a +256 bias: see FwdHdr::pk)
                 const FwdHdr* const hbuf = sm.hdr[buf];
                 GHit* const hl = hitlog + slot_b0 - 256;
                 char* const hlb = reinterpret_cast<char*>(hl);
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                             for (int u = 0; u < FWD_U; u++) {
                                 const uint32_t pk = __float_as_uint(h[u].w);
                                 idx[u] = (pk >> 6) + ly * (pk & 31u) + lx;  // 256 + the pair's index in the batch
-                                al[u] = abuf[v[u] ? idx[u] : 256u];
+                                al[u] = abuf[v[u] ? idx[u] - 256u : 0u];
                             }
 #pragma unroll
                             for (int u = 0; u < FWD_U; u++) {
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                             float al;
                             bool ok = true;
                             if (!(pk & 32u)) {
-                                al = abuf[idx];
+                                al = abuf[idx - 256u];
                             } else {
                                 const unsigned char* rp = stage + r * RS;
                                 const float4 q0 = *reinterpret_cast<const float4*>(rp);
@@ -1060,7 +1060,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
 // cross-lane reduction and no per-pixel atomics at all.  A pair was blended iff it lies in front of the pixel's last
 // contributor and passes the reference's power / alpha tests, which are re-evaluated here with the forward's arithmetic.
 constexpr int GATHER_THREADS = 256;
-__global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams p)
+__global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendParams p)
 {
     __shared__ float4 s_pix[GSTAR_TILE * GSTAR_TILE];    // dL_dpix rgb, (C_fin . dpx + T_final bg . dpx)
     __shared__ uint32_t s_nc[GSTAR_TILE * GSTAR_TILE];  // n_contrib
@@ -1119,9 +1119,12 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f;
         bool any = false;
         int xx = 0, pl = f.y0 * GSTAR_TILE + f.x0;
+        GHit hn = hrow[0];  // the row of the next pixel is requested one step ahead of its use (the rows of a footprint are consecutive)
 #pragma unroll 1
         for (int s = 0; s < area; s++) {
-            const int cur_pl = pl, cur_s = s;
+            const int cur_pl = pl;
+            const GHit hcur = hn;
+            if (s + 1 < area) hn = hrow[s + 1];
             if (++xx == f.w) { xx = 0; pl += GSTAR_TILE - f.w + 1; } else pl++;
             if (i >= s_nc[cur_pl]) continue;  // behind this pixel's last contributor
             float dx, dy;
@@ -1130,7 +1133,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
             const float G = expf(power);
             const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
             if (alpha < 1.0f / 255.0f) continue;
-            const GHit h = hrow[cur_s];
+            const GHit h = hcur;
             const float4 pv = s_pix[cur_pl];
             const float w = alpha * h.T;
             const float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
@@ -1178,8 +1181,12 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
                 for (int off = q * 128; off < area * (int)sizeof(GHit); off += L * 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
                 int xx = q, yy = 0;
                 while (xx >= f.w) { xx -= f.w; yy++; }
+                GHit hn = {0.f, 0.f, 0.f, 0.f};
+                if (q < area) hn = hrow[q];  // the row of the lane's next pixel is requested one step ahead of its use
 #pragma unroll 1
                 for (int s = q; s < area; s += L) {
+                    const GHit h = hn;
+                    if (s + L < area) hn = hrow[s + L];
                     const int pl = (f.y0 + yy) * GSTAR_TILE + f.x0 + xx;
                     xx += L;
                     while (xx >= f.w) { xx -= f.w; yy++; }
@@ -1190,7 +1197,6 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_blend_bwd_gather(BlendParams
                     const float G = expf(power);
                     const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
                     if (alpha < 1.0f / 255.0f) continue;
-                    const GHit h = hrow[s];
                     const float4 pv = s_pix[pl];
                     const float w = alpha * h.T;
                     const float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
@@ -1255,13 +1261,16 @@ __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src,
     b.z = __ldg(col); b.w = __ldg(col + 1); c.z = __ldg(col + 2);
     dst[(size_t)i * 3] = a; dst[(size_t)i * 3 + 1] = b; dst[(size_t)i * 3 + 2] = c;
 }
-__global__ void __launch_bounds__(256) k_poison(const GHeader* __restrict__ hdr, float* __restrict__ out, size_t n)
+__global__ void __launch_bounds__(256) k_poison(const GHeader* __restrict__ hdr, float* __restrict__ out, size_t n, uint32_t any_overflow)
 {
-    if (hdr->overflow != 2u) return;  // the usual case: one load per thread
+    // overflow == 2: a refused re-blend; any_overflow: also 1 -- a replayed CUDA graph whose view needs more instances than
+    // the captured capacity (nothing was blended: the image must not look like a result)
+    const uint32_t ov = hdr->overflow;
+    if (!(ov == 2u || (any_overflow && ov != 0u))) return;  // the usual case: one load per thread
     const float nan = __uint_as_float(0x7fc00000u);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = nan;
 }
-void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s) { k_poison<<<296, 256, 0, s>>>(hdr, out, n); }
+void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s, int any_overflow) { k_poison<<<296, 256, 0, s>>>(hdr, out, n, (uint32_t)any_overflow); }
 
 void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
                     int disable_log, const CameraCheck& cam, cudaStream_t s)

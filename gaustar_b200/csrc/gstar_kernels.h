@@ -125,7 +125,8 @@ struct CameraCheck {
 };
 void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
                     int disable_log, const CameraCheck& cam, cudaStream_t s);
-// fills `out` with NaN if the header says the re-blend was refused on the device (overflow == 2)
-void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s);
+// fills `out` with NaN if the header says the re-blend was refused on the device (overflow == 2) or, with any_overflow, if
+// the call found its instance capacity too small (a replayed CUDA graph cannot grow the buffer)
+void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s, int any_overflow = 0);
 
 }  // namespace gstar

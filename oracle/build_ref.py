@@ -15,6 +15,10 @@ Outputs:
   oracle/_ref/libref_dgr.so   reference kernels + oracle/ref_shim.cu (C ABI, exposes intermediates)
   oracle/_ref/ref_dgr_C.so    the reference's own pybind module under the name ``ref_dgr_C``
                               (stock binding: used by bench.py --impl reference)
+  oracle/_ref/pyref/...       the reference's Python CALLERS of the operator, byte-compiled where they lie (sourceless
+                              byte-code files *.refpyc, the Python analogue of the .so above; imported through oracle/pyref.py): ``gaussian_renderer.render()``, the
+                              ``GaussianModel`` it renders, the stock operator wrapper, and the SuGaR model/camera modules.
+                              tests/test_zz_reference_callers_gpu.py runs them unchanged against this repository's op.
 """
 from __future__ import annotations
 
@@ -35,8 +39,47 @@ NVCC = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a
 KERNEL_SRCS = [os.path.join(DGR, "cuda_rasterizer", f) for f in ("rasterizer_impl.cu", "forward.cu", "backward.cu")]
 
 
+PYREF = os.path.join(OUT, "pyref")
+PYC_SUFFIX = ".refpyc"  # (not ".pyc": gpurun's snapshot drops *.pyc; oracle/pyref.py imports these)
+GS = os.path.join(REF_ROOT, "gaussian_splatting")
+# (source file, path below oracle/_ref/pyref/ without the .pyc suffix)
+PY_CALLERS = [
+    (os.path.join(GS, "gaussian_renderer", "__init__.py"), "gaussian_splatting/gaussian_renderer/__init__"),
+    (os.path.join(GS, "scene", "gaussian_model.py"), "gaussian_splatting/scene/gaussian_model"),
+    (os.path.join(GS, "utils", "general_utils.py"), "gaussian_splatting/utils/general_utils"),
+    (os.path.join(GS, "utils", "sh_utils.py"), "gaussian_splatting/utils/sh_utils"),
+    (os.path.join(GS, "utils", "graphics_utils.py"), "gaussian_splatting/utils/graphics_utils"),
+    (os.path.join(GS, "utils", "system_utils.py"), "gaussian_splatting/utils/system_utils"),
+    (os.path.join(DGR, "diff_gaussian_rasterization", "__init__.py"), "ref_operator/diff_gaussian_rasterization/__init__"),
+    (os.path.join(REF_ROOT, "gaustar_scene", "sugar_model.py"), "gaustar/gaustar_scene/sugar_model"),
+    (os.path.join(REF_ROOT, "gaustar_scene", "cameras.py"), "gaustar/gaustar_scene/cameras"),
+    (os.path.join(REF_ROOT, "gaustar_scene", "gs_model.py"), "gaustar/gaustar_scene/gs_model"),
+    (os.path.join(REF_ROOT, "gaustar_utils", "spherical_harmonics.py"), "gaustar/gaustar_utils/spherical_harmonics"),
+    (os.path.join(REF_ROOT, "gaustar_utils", "graphics_utils.py"), "gaustar/gaustar_utils/graphics_utils"),
+    (os.path.join(REF_ROOT, "gaustar_utils", "general_utils.py"), "gaustar/gaustar_utils/general_utils"),
+]
+
+
 def available() -> bool:
     return os.path.isdir(DGR)
+
+
+def build_py(force=False, verbose=False) -> bool:
+    """Byte-compile the reference's Python callers into oracle/_ref/pyref (sourceless .pyc; nothing is copied as source)."""
+    if not available():
+        return False
+    import py_compile
+    for src, rel in PY_CALLERS:
+        if not os.path.exists(src):
+            continue
+        dst = os.path.join(PYREF, rel + PYC_SUFFIX)
+        if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        py_compile.compile(src, cfile=dst, dfile=src, doraise=True)
+        if verbose:
+            print("byte-compiled", src, "->", dst, flush=True)
+    return True
 
 
 def _obj(src, tag=""):
@@ -76,6 +119,7 @@ def build(force=False, verbose=False, with_torch_ext=True):
         run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", EXT, o1, o2, *[_obj(s) for s in KERNEL_SRCS],
              "-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
              "-Xlinker", f"-rpath={tlib}"])
+    build_py(force, verbose)
     return True
 
 

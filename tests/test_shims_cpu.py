@@ -125,3 +125,41 @@ def test_uniform_laplacian_closed_forms():
     assert abs(float(mesh_laplacian_smoothing(Meshes([tv], [tf]), method="uniform")) - 4.0 / 3.0 * 3.0 ** 0.5) < 1e-9
     # scaling the mesh scales the loss; translating it does not change it
     assert abs(float(mesh_laplacian_smoothing(Meshes([2 * tv + 7.0], [tf]))) - 8.0 / 3.0 * 3.0 ** 0.5) < 1e-9
+
+
+def test_knn_points_matches_brute_force_and_normals_of_a_plane():
+    from pytorch3d.ops import estimate_pointcloud_normals, knn_points
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(2, 300, 3, generator=g)
+    q = torch.rand(2, 70, 3, generator=g)
+    out = knn_points(q, p, K=5, return_nn=True)
+    d = ((q[:, :, None] - p[:, None]) ** 2).sum(-1)
+    dk, ik = torch.topk(d, 5, dim=-1, largest=False)
+    assert torch.allclose(out.dists, dk, atol=1e-6) and torch.equal(out.idx, ik)
+    assert torch.allclose(out.knn, torch.stack([p[n][ik[n]] for n in range(2)]))
+    plane = torch.cat([torch.rand(1, 500, 2, generator=g), torch.zeros(1, 500, 1)], -1)
+    n = estimate_pointcloud_normals(plane, neighborhood_size=12)
+    assert torch.allclose(n.abs(), torch.tensor([0.0, 0.0, 1.0]).expand_as(n), atol=1e-4)
+
+
+def test_camera_container_and_calibration_matrix():
+    """What GauSTAR does with pytorch3d cameras (cameras.py:229-330,537-548; sugar_model.py:1113-1162): build from R/T/K, index,
+    ask for the centres.  Row-vector convention: X_cam = X_world R + T  =>  C R + T = 0."""
+    from pytorch3d.renderer import FoVPerspectiveCameras, RasterizationSettings, TexturesVertex
+    from pytorch3d.renderer.cameras import _get_sfm_calibration_matrix
+    from pytorch3d.transforms import quaternion_to_matrix
+    g = torch.Generator().manual_seed(1)
+    R = quaternion_to_matrix(torch.nn.functional.normalize(torch.randn(4, 4, generator=g), dim=-1))
+    T = torch.randn(4, 3, generator=g)
+    K = _get_sfm_calibration_matrix(4, "cpu", torch.tensor([[2.0, 3.0]]).expand(4, -1), torch.tensor([[0.1, -0.2]]).expand(4, -1))
+    assert torch.equal(K[0], torch.tensor([[2.0, 0, 0.1, 0], [0, 3.0, -0.2, 0], [0, 0, 0, 1], [0, 0, 1, 0]]))
+    cams = FoVPerspectiveCameras(R=R, T=T, K=K, znear=0.0001)
+    C = cams.get_camera_center()
+    assert torch.allclose(torch.einsum("ni,nij->nj", C, R) + T, torch.zeros(4, 3), atol=1e-5)
+    one = cams[2]
+    assert len(cams) == 4 and len(one) == 1 and torch.equal(one.R[0], R[2]) and torch.equal(one.K[0], K[2])
+    assert abs(one.znear.item() - 1e-4) < 1e-9 and one.zfar.item() == 100.0
+    assert torch.allclose(one.get_camera_center()[0], C[2])
+    assert RasterizationSettings(image_size=(4, 5)).image_size == (4, 5)
+    tv = TexturesVertex(verts_features=torch.rand(1, 7, 3))
+    assert tv.verts_features_packed().shape == (7, 3)

@@ -93,3 +93,44 @@ def test_operator_inference_and_reblend_replay_from_a_graph():
     _, eb2 = render()
     torch.cuda.synchronize()
     assert torch.equal(gb, eb2) and not torch.equal(eb2, eb)
+
+
+def test_captured_replay_that_outgrows_its_capacity_poisons_the_image():
+    """A replayed graph cannot grow its binning buffer: a view that needs more instances than the captured capacity sets the
+    header's overflow flag and blends nothing -- the image must then be NaN, not uninitialised memory.  (The capacity a capture
+    takes is per host thread; a fresh thread starts from the minimum, so the case is reachable here.)"""
+    import threading
+    result = {}
+
+    def body():
+        try:
+            torch.cuda.set_device(0)
+            g = scene.surface_gaussians(250000, 1, seed=2)
+            cam = scene.dome_cameras(4, 960, 540)[1]
+            kw = Hh.to_torch_kwargs(Hh.scene_dict(g, cam))
+            real = kw["means3D"].clone()
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                kw["means3D"].add_(1000.0)  # nothing on screen: the thread's capacity estimate stays at its minimum
+                f0 = capi.forward(**kw)
+                assert f0["num_rendered"] == 0
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=s):
+                    f = capi.forward(**kw)
+                kw["means3D"].copy_(real)
+                graph.replay()
+                torch.cuda.synchronize()
+                hdr = capi.debug_header(f)
+                result.update(overflow=hdr["overflow"], R=hdr["num_rendered"], cap=hdr["capacity"], nan=bool(torch.isnan(f["out_color"]).all()))
+                kw["means3D"].add_(1000.0)  # and a replay that fits again is a picture again (the background)
+                graph.replay()
+                torch.cuda.synchronize()
+                result["bg_again"] = bool(torch.equal(f["out_color"], f0["out_color"]))
+        except Exception as e:  # noqa: BLE001 (reported through the assert below)
+            result["error"] = repr(e)
+
+    t = threading.Thread(target=body)
+    t.start()
+    t.join()
+    assert "error" not in result, result
+    assert result["R"] > result["cap"] and result["overflow"] == 1 and result["nan"] and result["bg_again"], result

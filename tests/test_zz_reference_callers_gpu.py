@@ -1,0 +1,212 @@
+"""The reference's own CALLERS of the operator, run unchanged against this repository's drop-in (north_star: "drops in behind
+gaussian_renderer.render() and gaustar_scene/sugar_model so [they] run unchanged").
+
+What runs here is the reference's code, not a restatement: `oracle/build_ref.py` byte-compiles, where they lie under
+/root/reference, `gaussian_splatting/gaussian_renderer/__init__.py` (render(), :18-100), `scene/gaussian_model.py`, the `utils`
+they import, `gaustar_scene/{sugar_model,cameras,gs_model}.py` and the stock operator wrapper
+`diff_gaussian_rasterization/__init__.py` into sourceless byte-code files under oracle/_ref/pyref (git-ignored; they travel to
+the GPU box like the compiled reference kernels; oracle/pyref.py is the import hook).  Each caller module is imported TWICE,
+once with `diff_gaussian_rasterization` bound to this repository's package and once bound to the reference's wrapper over its own kernels (`ref_dgr_C.so`), and both are driven
+with the same objects.  Bar: images, radii and visibility identical; every parameter gradient within the bound the live
+reference comparison uses elsewhere (tests/test_parity_gpu.py).
+
+Dependencies the image lacks are taken from `shims/` (pytorch3d subset, import-only plyfile / plotly / open3d).
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from gaustar_b200 import scene
+
+import helpers as Hh
+from test_parity_gpu import LIVE_REF_TOL
+
+from oracle import pyref
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Hh.ROOT
+needs_pyref = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/pyref not built (oracle/build_ref.py needs /root/reference)")
+
+# modules a caller import pulls in and that bind the operator at import time: dropped between the two arms
+_CALLER_MODULES = ("gaussian_renderer", "scene", "scene.gaussian_model", "gaussian_splatting", "gaussian_splatting.gaussian_renderer",
+                   "gaussian_splatting.scene", "gaussian_splatting.scene.gaussian_model", "gaustar_scene", "gaustar_scene.sugar_model",
+                   "gaustar_scene.gs_model", "gaustar_scene.cameras")
+
+
+def _reference_operator():
+    """The reference's operator wrapper (DGR/diff_gaussian_rasterization/__init__.py, byte-compiled) over its own kernels."""
+    name = "ref_diff_gaussian_rasterization"
+    if name in sys.modules:
+        return sys.modules[name]
+    from oracle import refgpu
+    spec, mod = pyref.load_file(name, os.path.join("ref_operator", "diff_gaussian_rasterization", "__init__"),
+                                submodule_search_locations=[os.path.join(pyref.PYREF, "ref_operator", "diff_gaussian_rasterization")])
+    sys.modules[name + "._C"] = refgpu.stock_module()  # `from . import _C` (DGR/__init__.py:14)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _Arm:
+    """Import context of one arm: the byte-compiled callers importable under the reference's module names (oracle/pyref.py), the
+    repository root and shims/ on sys.path, and `diff_gaussian_rasterization` bound to the arm's operator."""
+
+    def __init__(self, operator_module):
+        self.op = operator_module
+
+    def __enter__(self):
+        self.saved_path = list(sys.path)
+        self.saved = {k: sys.modules.get(k) for k in _CALLER_MODULES + ("diff_gaussian_rasterization", "gaussian_splatting.scene.dataset_readers")}
+        for k in _CALLER_MODULES:
+            sys.modules.pop(k, None)
+        sys.modules["diff_gaussian_rasterization"] = self.op
+        stub = types.ModuleType("gaussian_splatting.scene.dataset_readers")  # gs_model.py:8 imports fetchPly (PLY loader; not used here)
+        stub.fetchPly = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("dataset_readers.fetchPly is stubbed in this test"))
+        sys.modules["gaussian_splatting.scene.dataset_readers"] = stub
+        for p in (os.path.join(ROOT, "shims"), ROOT):
+            if p in sys.path:
+                sys.path.remove(p)
+            sys.path.insert(0, p)
+        pyref.install()
+        importlib.invalidate_caches()
+        return self
+
+    def __exit__(self, *exc):
+        pyref.uninstall()
+        sys.path[:] = self.saved_path
+        for k in _CALLER_MODULES:
+            sys.modules.pop(k, None)
+        for k, v in self.saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)
+        return False
+
+
+def _arms():
+    import diff_gaussian_rasterization as ours
+    assert os.path.dirname(os.path.abspath(ours.__file__)) == os.path.join(ROOT, "diff_gaussian_rasterization")
+    return (("ours", ours), ("reference", _reference_operator()))
+
+
+def _check_param_grads(mine, ref):
+    """max |a - b| <= tol * max |b| per tensor (tests/test_parity_gpu.py's bound against the live reference).  A gradient that is
+    zero analytically -- SuGaR's in-plane rotation of splats whose two in-plane scales are equal -- is cancellation noise in both
+    arms (1e-9 against 1e-1 elsewhere): its scale is floored at 1e-4 of the largest gradient of the step."""
+    tol = max(LIVE_REF_TOL.values())
+    floor = 1e-4 * max(float(v.abs().max()) for v in ref.values())
+    for k in ref:
+        a, b = mine[k].double(), ref[k].double()
+        err = float((a - b).abs().max() / max(float(b.abs().max()), floor))
+        assert err <= tol, (k, err)
+
+
+@needs_pyref
+@pytest.mark.parametrize("variant", ["sh_in_rasterizer", "python_sh", "python_cov", "override_color_scaled"])
+def test_gaussian_renderer_render_runs_unchanged(variant):
+    """gaussian_renderer.render() (gaussian_renderer/__init__.py:18-100) on a reference GaussianModel built by its own
+    create_from_pcd (which calls simple_knn._C.distCUDA2: this repository's shim)."""
+    g = scene.surface_gaussians(30000, 3, seed=11)
+    cam = scene.dome_cameras(6, 480, 270)[2]
+    pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=variant == "python_cov", convert_SHs_python=variant == "python_sh")
+    scaling_modifier = 0.7 if variant == "override_color_scaled" else 1.0
+    vm = torch.from_numpy(cam.viewmatrix).cuda().view(4, 4)
+    view = types.SimpleNamespace(FoVx=2.0 * np.arctan(cam.tanfovx), FoVy=2.0 * np.arctan(cam.tanfovy), image_height=cam.image_height,
+                                 image_width=cam.image_width, world_view_transform=vm,
+                                 full_proj_transform=torch.from_numpy(cam.projmatrix).cuda().view(4, 4),
+                                 camera_center=torch.from_numpy(cam.campos).cuda().view(3))
+    bg = torch.tensor([0.0, 1.0, 0.0], device="cuda")
+    w = torch.randn(3, cam.image_height, cam.image_width, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    out = {}
+    for name, op in _arms():
+        with _Arm(op):
+            gr = importlib.import_module("gaussian_renderer")
+            gm = importlib.import_module("scene.gaussian_model")
+            from utils.graphics_utils import BasicPointCloud
+            assert gr.GaussianRasterizer is op.GaussianRasterizer
+            pc = gm.GaussianModel(3)
+            rng = np.random.default_rng(5)
+            pc.create_from_pcd(BasicPointCloud(points=g.means3D, colors=rng.uniform(0, 1, (g.P, 3)).astype(np.float32), normals=np.zeros((g.P, 3))), 1.0)
+            with torch.no_grad():  # a "trained" state: the generator's opacities / anisotropic scales / rotations / SH
+                pc._opacity.copy_(torch.logit(torch.from_numpy(g.opacities).cuda().clamp(1e-4, 1 - 1e-4)))
+                pc._scaling.copy_(torch.log(torch.from_numpy(g.scales).cuda()))
+                pc._rotation.copy_(torch.from_numpy(g.rotations).cuda())
+                sh = torch.from_numpy(g.shs).cuda()
+                pc._features_dc.copy_(sh[:, :1])
+                pc._features_rest.copy_(sh[:, 1:])
+            pc.active_sh_degree = 3
+            override = torch.rand(g.P, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(8)) if variant == "override_color_scaled" else None
+            res = gr.render(view, pc, pipe, bg, scaling_modifier=scaling_modifier, override_color=override)
+            (res["render"] * w).sum().backward()
+            torch.cuda.synchronize()
+            params = dict(xyz=pc._xyz, f_dc=pc._features_dc, f_rest=pc._features_rest, scaling=pc._scaling, rotation=pc._rotation, opacity=pc._opacity)
+            out[name] = dict(render=res["render"].detach(), radii=res["radii"], vis=res["visibility_filter"],
+                             vsp=res["viewspace_points"].grad.clone(),
+                             grads={k: (torch.zeros_like(v) if v.grad is None else v.grad.clone()) for k, v in params.items()})
+    a, b = out["ours"], out["reference"]
+    assert int(b["vis"].sum()) > 1000
+    assert torch.equal(a["radii"], b["radii"]) and torch.equal(a["vis"], b["vis"])
+    assert torch.equal(a["render"], b["render"])
+    _check_param_grads(dict(a["grads"], viewspace_points=a["vsp"]), dict(b["grads"], viewspace_points=b["vsp"]))
+
+
+def _sugar_inputs(n_faces=4000, n_cams=3, W=480, H=270):
+    verts, faces = scene.capsule_mesh(n_faces, seed=2)
+    cams = scene.dome_cameras(n_cams, W, H)
+    return verts, faces, cams
+
+
+@needs_pyref
+@pytest.mark.parametrize("color_in_rasterizer", [False, True])
+def test_sugar_render_image_gaussian_rasterizer_runs_unchanged(color_in_rasterizer):
+    """SuGaR bound to a surface mesh (sugar_model.py:90-405) rendering through render_image_gaussian_rasterizer (:1065-1311), with
+    the reference's own GSCamera / CamerasWrapper (cameras.py) providing the cameras; GauSTAR's training call uses
+    compute_color_in_rasterizer=False (refine.py:552-564), the detection render True."""
+    verts, faces, cams = _sugar_inputs()
+    rng = np.random.default_rng(4)
+    vcol = rng.uniform(0, 1, (len(verts), 3))
+    out = {}
+    for name, op in _arms():
+        with _Arm(op):
+            sm = importlib.import_module("gaustar_scene.sugar_model")
+            cm = importlib.import_module("gaustar_scene.cameras")
+            import open3d  # the shim: TriangleMeshLike
+            assert sm.GaussianRasterizer is op.GaussianRasterizer
+            gs_cams = []
+            for i, c in enumerate(cams):
+                # GSCamera takes the reference's (R, T) convention: world_view_transform = getWorld2View2(R, T).T, i.e. R = W2C[:3,:3].T
+                w2c = c.viewmatrix.reshape(4, 4).T.astype(np.float64)
+                gs_cams.append(cm.GSCamera(colmap_id=i, R=w2c[:3, :3].T.copy(), T=w2c[:3, 3].copy(), FoVx=2.0 * np.arctan(c.tanfovx),
+                                           FoVy=2.0 * np.arctan(c.tanfovy), image=None, gt_alpha_mask=None, image_name=f"img_{i:04d}", uid=i,
+                                           image_height=c.image_height, image_width=c.image_width))
+            wrapper = cm.CamerasWrapper(gs_cams)
+            nerf = types.SimpleNamespace(device=torch.device("cuda"), training_cameras=wrapper)
+            mesh = open3d.TriangleMeshLike(verts, faces, vcol)
+            torch.manual_seed(0)
+            sugar = sm.SuGaR(nerfmodel=nerf, points=None, colors=None, initialize=False, sh_levels=4, keep_track_of_knn=False,
+                             surface_mesh_to_bind=mesh, n_gaussians_per_surface_triangle=6, learn_surface_mesh_opacity=True)
+            with torch.no_grad():
+                sugar.all_densities.copy_(torch.logit(torch.full_like(sugar.all_densities, 0.9)))
+                sugar._sh_coordinates_rest.copy_(0.05 * torch.randn(sugar._sh_coordinates_rest.shape, device="cuda",
+                                                                    generator=torch.Generator("cuda").manual_seed(1)))
+            res = sugar.render_image_gaussian_rasterizer(camera_indices=1, bg_color=[0.0, 1.0, 0.0], sh_deg=3,
+                                                         compute_color_in_rasterizer=color_in_rasterizer, return_2d_radii=True)
+            img = res["image"]
+            wgt = torch.randn(img.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(6))
+            (img * wgt).sum().backward()
+            torch.cuda.synchronize()
+            params = {k: v for k, v in sugar.named_parameters() if v.requires_grad and v.grad is not None}
+            out[name] = dict(image=img.detach(), radii=res["radii"], vsp=res["viewspace_points"].grad.clone(),
+                             grads={k: v.grad.clone() for k, v in params.items()})
+    a, b = out["ours"], out["reference"]
+    assert int((b["radii"] > 0).sum()) > 5000 and set(a["grads"]) == set(b["grads"]) and "_points" in b["grads"]
+    assert torch.equal(a["radii"], b["radii"])
+    assert torch.equal(a["image"], b["image"])
+    _check_param_grads(dict(a["grads"], viewspace_points=a["vsp"]), dict(b["grads"], viewspace_points=b["vsp"]))

@@ -344,3 +344,32 @@ def test_forward_passes_one_node_matches_separate_calls():
     img, radii, extra = dgr.GaussianRasterizer(_settings(dgr, kw, kw["bg"], 0)).forward_passes(z3, z3, z1, colors_precomp=z3, scales=z3, rotations=z4,
                                                                                                  extra_passes=[(z3, bg2)])
     assert float(img.abs().max()) == 0.0 and float(extra[0].abs().max()) == 0.0 and radii.numel() == 0
+
+
+def test_forward_passes_after_many_forwards_still_finds_its_source():
+    """Regression (round 1, profiles/r1last_pytest_failure.txt): the host-side table of recent calls holds 16 entries; with FIFO
+    replacement a multi-pass call issued after more than 16 other forwards could evict its own source while re-blending.
+    More than 16 forwards, then one forward_passes call with three extra passes, then more forwards and another one."""
+    import diff_gaussian_rasterization as dgr
+    d = SCENES["surface_sh3"]()
+    kw = Hh.to_torch_kwargs(d)
+    P = kw["means3D"].shape[0]
+    gen = torch.Generator("cuda").manual_seed(5)
+    cols = [torch.rand(P, 3, device="cuda", generator=gen) for _ in range(3)]
+    bg2 = torch.full((3,), 2.0, device="cuda")
+    r = dgr.GaussianRasterizer(_settings(dgr, kw, kw["bg"], 3))
+    args = dict(means3D=kw["means3D"], means2D=torch.zeros(P, 3, device="cuda"), opacities=kw["opacities"], shs=kw["shs"], scales=kw["scales"],
+                rotations=kw["rotations"])
+    keep = []
+    for rounds in (19, 23):
+        with torch.no_grad():
+            for _ in range(rounds):
+                keep.append(r(**args)[0])  # (kept alive: every call owns fresh buffers, the table sees distinct addresses)
+            img, radii, extra = r.forward_passes(**args, extra_passes=[(c, bg2) for c in cols])
+            ref = [dgr.GaussianRasterizer(_settings(dgr, kw, bg2, 0))(means3D=kw["means3D"], means2D=args["means2D"], opacities=kw["opacities"],
+                                                                      colors_precomp=c, scales=kw["scales"], rotations=kw["rotations"])[0] for c in cols]
+        torch.cuda.synchronize()
+        assert torch.equal(img, keep[0])
+        for e, x in zip(extra, ref):
+            assert torch.equal(e, x)
+        del keep[4:]
