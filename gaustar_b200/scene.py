@@ -236,7 +236,9 @@ def _projection(znear, zfar, tan_half_x, tan_half_y):
     return P
 
 
-def look_at_camera(eye, target, W, H, fy_over_H=1.6667, znear=0.01, zfar=100.0) -> Camera:
+def look_at_camera(eye, target, W, H, fy_over_H=1.6667, znear=0.01, zfar=100.0, principal_ndc=(0.0, 0.0)) -> Camera:
+    """principal_ndc: off-centre principal point the way SuGaR hands it to the op -- sugar_model.py:1160-1161 writes
+    proj[2,0] = -K[0,0,2], proj[2,1] = -K[0,1,2] into the transposed projection (zero for GauSTAR's centred data)."""
     eye = np.asarray(eye, np.float64)
     target = np.asarray(target, np.float64)
     fwd = target - eye
@@ -259,6 +261,8 @@ def look_at_camera(eye, target, W, H, fy_over_H=1.6667, znear=0.01, zfar=100.0) 
     fx = fy
     tan_x, tan_y = W / (2.0 * fx), H / (2.0 * fy)
     proj = _projection(znear, zfar, tan_x, tan_y).astype(np.float32).T.astype(np.float64)
+    proj[2, 0] = -float(principal_ndc[0])
+    proj[2, 1] = -float(principal_ndc[1])
     full = (view.astype(np.float32) @ proj.astype(np.float32)).astype(np.float32)
     return Camera(W, H, float(tan_x), float(tan_y), np.ascontiguousarray(view, np.float32), np.ascontiguousarray(full, np.float32),
                   eye.astype(np.float32))

@@ -47,18 +47,33 @@ def cases():
     g = scene.random_gaussians(256, sh_degree=1, seed=13, scale_range=(0.01, 0.15))
     cam = scene.look_at_camera([0.0, 1.0, 2.0], [0, 1, 0], 33, 17, fy_over_H=1.3)
     yield "rand_sh1_deg0", g, cam, dict(use="sh", deg=0), [0.0, 0.0, 0.0]
+    # round 2: inputs the callers can reach that round 1's vectors did not cover -- render(..., scaling_modifier)
+    # (gaussian_renderer/__init__.py:18,44) and an off-centre principal point (sugar_model.py:1160-1161)
+    g = scene.surface_gaussians(300, sh_degree=3, seed=3)
+    g.scales[:, 1:] *= 6.0
+    cam = scene.look_at_camera([0.5, 1.1, 1.2], [0, 1.0, 0], 64, 48, fy_over_H=1.0)
+    yield "surf_sh3_mod05", g, cam, dict(use="sh", deg=3, scale_modifier=0.5), [0.0, 1.0, 0.0]
+    g = scene.random_gaussians(300, sh_degree=2, seed=17, scale_range=(0.02, 0.2))
+    cam = scene.look_at_camera([0.3, 1.4, 3.5], [0, 1, 0], 48, 48, fy_over_H=1.1)
+    yield "rand_sh2_mod2", g, cam, dict(use="sh", deg=2, scale_modifier=2.0), [0.2, 0.3, 0.4]
+    g = scene.surface_gaussians(300, sh_degree=3, seed=5)
+    g.scales[:, 1:] *= 6.0
+    cam = scene.look_at_camera([0.6, 1.2, 1.1], [0, 1.0, 0], 64, 48, fy_over_H=1.0, principal_ndc=(0.23, -0.17))
+    yield "surf_sh3_offcentre", g, cam, dict(use="sh", deg=3), [0.0, 1.0, 0.0]
 
 
-def main(out_dir):
+def main(out_dir, only=None):
     os.makedirs(out_dir, exist_ok=True)
     dev = "cuda"
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     for name, g, cam, mode, bg in cases():
+        if only and name not in only:
+            continue
         W, H = cam.image_width, cam.image_height
         rng = np.random.default_rng(5)
         inputs = dict(means3D=g.means3D, opacities=g.opacities, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, campos=cam.campos,
                       bg=np.asarray(bg, np.float32), tan_fovx=np.float32(cam.tanfovx), tan_fovy=np.float32(cam.tanfovy), W=W, H=H,
-                      scale_modifier=np.float32(1.0), sh_degree=0)
+                      scale_modifier=np.float32(mode.get("scale_modifier", 1.0)), sh_degree=0)
         if mode["use"] == "sh":
             inputs.update(shs=g.shs, scales=g.scales, rotations=g.rotations, sh_degree=mode["deg"])
         else:
@@ -87,4 +102,4 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"), only=sys.argv[2:] or None)

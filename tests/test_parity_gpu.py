@@ -6,8 +6,14 @@ Bars (SURVEY.md 8c / BASELINE.md 2.5):
               (tile|depth, gaussian) list, tile ranges, n_contrib            [vs reference & golden]
   fp32 tol. : out_color, final_T: rtol 1e-5 / atol 2e-6 vs the reference (same op order; observed 0);
               atol 2e-5 vs the CPU oracle (glibc expf vs the GPU's ex2.approx-based expf)
-  gradients : max-abs error <= 1e-3 of the tensor's max magnitude vs the fp64-accumulating oracle
-              and vs the reference (whose own fp32 atomics are order-nondeterministic)
+  gradients : vs the fp64-accumulating CPU oracle and vs the golden vectors: max-abs error <= 3e-4 of the tensor's
+              max magnitude, AND element-wise on every entry above 1 % of that max: the worst relative error must
+              stay below max(1e-3, 2 x the worst relative error of the UNMODIFIED REFERENCE against the same oracle
+              on the same entries) -- fp32 sums through 1/det^2 cannot meet a flat rtol 1e-3 entry by entry (the
+              reference itself shows 1e-2 on dL_dscales), so the bar is "no worse than the reference", measured.
+              vs the LIVE reference, whose fp32 atomics are order-nondeterministic: the reference is run TWICE and its
+              own run-to-run spread is measured per tensor; the bound is 3e-4 + 4 x that spread -- measured, not
+              argued (two runs of the unmodified reference differ by up to 1.4e-3 on dL_dcov3D: tools/grad_noise.py).
 """
 import numpy as np
 import pytest
@@ -21,13 +27,19 @@ import helpers as Hh
 
 pytestmark = pytest.mark.gpu
 
-GRAD_TOL = 1e-3
+GRAD_TOL = 3e-4        # max-abs error / max |ref|, vs oracle and golden (hit-log backward: a few adds per Gaussian)
+# The walk-back backward (no hit log) sums per-(Gaussian, warp) partials with unordered fp32 atomics like the reference does per
+# pixel -- thousands of adds for a fat splat -- and shows up to 3.9e-4 on dL_dscales of the fat-splat scene; it is the
+# fallback path, held to twice the bar.
+GRAD_TOL_WALK = 6e-4
+GRAD_RTOL_ELEM = 1e-3  # element-wise, on entries above GRAD_ELEM_FLOOR of the tensor's max
+GRAD_ELEM_FLOOR = 1e-2
 # The reference sums its blend gradients with order-nondeterministic fp32 atomics, and dL_dcov3D / dL_dscales /
-# dL_drotations amplify that noise through 1/det^2 (backward.cu:201-212): two runs of the UNMODIFIED reference on the same
-# inputs differ by up to 1.4e-3 / 5.6e-4 / 2.8e-4 of the tensor's max on the close-up scene (tools/grad_noise.py).  Against
-# the live reference those three tensors therefore get a bound above the reference's own run-to-run spread; against the
-# deterministic fp64-accumulating oracle and the golden files every tensor keeps GRAD_TOL.
+# dL_drotations amplify that noise through 1/det^2 (backward.cu:201-212).  Where a test can run the reference itself
+# (test_against_live_reference, the full-size tests) the bound comes from the reference's measured spread; the fixed table
+# below is only for comparisons that cannot (a CUDA-graph replay against eager calls, the reference callers' own modules).
 LIVE_REF_TOL = {"dL_dcov3D": 5e-3, "dL_dscales": 3e-3, "dL_drotations": 3e-3}
+LIVE_SPREAD_FACTOR = 4.0
 
 
 def bits(a):
@@ -86,15 +98,51 @@ def check_forward_against(fwd, kw, ref, exact_image, n_contrib_slack=0):
     return g, st
 
 
-def check_grads(mine, ref, tol=GRAD_TOL, per_key=None):
+def elementwise_worst(m, r):
+    """Worst relative error over the entries of r above GRAD_ELEM_FLOOR of its max (0.0 if there are none)."""
+    r64, m64 = np.asarray(r, np.float64), np.asarray(m, np.float64).reshape(np.shape(r))
+    big = np.abs(r64) > GRAD_ELEM_FLOOR * np.abs(r64).max()
+    return float((np.abs(m64 - r64)[big] / np.abs(r64)[big]).max()) if big.any() else 0.0
+
+
+def default_grad_tol():
+    return GRAD_TOL if capi.set_hit_log(-1) == 1 else GRAD_TOL_WALK
+
+
+def check_grads(mine, ref, tol=None, per_key=None, elementwise_against=None):
+    """max-norm bound per tensor (per_key raises it for single tensors).  elementwise_against: the unmodified reference's gradients
+    for the same inputs -- our worst element-wise relative error (entries above 1 % of the max) vs `ref` must stay below
+    max(GRAD_RTOL_ELEM, 2 x the reference's own)."""
     for k in Hh.GRAD_KEYS:
         r = np.asarray(ref[k])
         if r.size == 0:
             continue
         m = mine[k].cpu().numpy().reshape(r.shape)
         assert np.isfinite(m).all(), k
-        bound = max(tol, (per_key or {}).get(k, 0.0))
+        bound = max(default_grad_tol() if tol is None else tol, (per_key or {}).get(k, 0.0))
         assert Hh.rel_err(m, r) < bound, (k, Hh.rel_err(m, r), bound)
+        if elementwise_against is not None:
+            ours, theirs = elementwise_worst(m, r), elementwise_worst(np.asarray(elementwise_against[k]), r)
+            assert ours < max(GRAD_RTOL_ELEM, 2.0 * theirs), (k, "element-wise", ours, "reference:", theirs)
+
+
+def reference_spread(ref, dpix, bkw, runs=3):
+    """Per-tensor run-to-run spread of the UNMODIFIED reference's backward on identical inputs (max-abs difference between two
+    runs over the tensor's max): what its atomics' order costs.  Returns (gradients of the first run, {key: spread})."""
+    first = {k: v.cpu().numpy() for k, v in refgpu.backward(ref, dpix, **bkw).items()}
+    spread = {k: 0.0 for k in first}
+    for _ in range(runs - 1):
+        again = refgpu.backward(ref, dpix, **bkw)
+        for k, v in again.items():
+            if first[k].size:
+                spread[k] = max(spread[k], Hh.rel_err(v.cpu().numpy(), first[k]))
+    return first, spread
+
+
+def live_bound(spread):
+    """Per-tensor bound against ONE run of the live reference: our own fp32 error budget (GRAD_TOL, the bar against the
+    deterministic oracle) plus LIVE_SPREAD_FACTOR x the reference's measured run-to-run spread."""
+    return {k: default_grad_tol() + LIVE_SPREAD_FACTOR * v for k, v in spread.items()}
 
 
 SCENES = {
@@ -107,6 +155,15 @@ SCENES = {
                                                 bg=(0.3, 0.2, 0.1)),
     "sh_deg1_of_3": lambda: Hh.scene_dict(scene.random_gaussians(3000, 3, seed=8, scale_range=(0.01, 0.1)),
                                           scene.look_at_camera([0.0, 1.0, 3.0], [0, 1, 0], 160, 120), sh_degree=1),
+    # inputs the callers can reach (round 2): render(..., scaling_modifier) (gaussian_renderer/__init__.py:18,44), an off-centre
+    # principal point (sugar_model.py:1160-1161), campos of shape [1,3] on the SH path (sugar_model.py:1164: get_camera_center())
+    "surface_mod05": lambda: dict(Hh.scene_dict(scene.surface_gaussians(16000, 3, seed=3), scene.dome_cameras(6, 384, 216)[3]), scale_modifier=0.5),
+    "random_mod2": lambda: dict(Hh.scene_dict(scene.random_gaussians(4000, 2, seed=12, scale_range=(0.01, 0.15)),
+                                              scene.look_at_camera([0.4, 1.2, 3.6], [0, 1, 0], 320, 180, fy_over_H=1.2)), scale_modifier=2.0),
+    "surface_offcentre": lambda: Hh.scene_dict(scene.surface_gaussians(16000, 3, seed=6),
+                                               scene.look_at_camera([1.9, 1.6, 2.2], [0, 1, 0], 400, 225, principal_ndc=(0.31, -0.22))),
+    "surface_campos_1x3": lambda: (lambda d: dict(d, campos=d["campos"].reshape(1, 3)))(
+        Hh.scene_dict(scene.surface_gaussians(9000, 3, seed=7), scene.dome_cameras(6, 320, 180)[0])),
 }
 
 
@@ -129,7 +186,11 @@ def test_against_cpu_oracle(name):
     of.n_contrib = st["n_contrib"].astype(np.uint32)
     of.final_T = st["final_T"].copy()
     ob = O.backward(inp, of, dpix)
-    check_grads(mine, ob.__dict__)
+    ref_grads = None
+    if refgpu.available():  # the reference on the same inputs: the yardstick of the element-wise check
+        rf = refgpu.forward(**kw)
+        ref_grads = {k: v.cpu().numpy() for k, v in refgpu.backward(rf, torch.from_numpy(dpix).cuda(), **Hh.bwd_kwargs(kw)).items()}
+    check_grads(mine, ob.__dict__, elementwise_against=ref_grads)
 
 
 @pytest.mark.parametrize("path", Hh.golden_files() or [None])
@@ -142,6 +203,7 @@ def test_against_reference_golden(path):
     check_forward_against(fwd, kw, rf, exact_image=True)
     mine = capi.backward(fwd, torch.from_numpy(inp_d["dL_dpix"]).cuda(), **Hh.bwd_kwargs(kw))
     torch.cuda.synchronize()
+    # (the golden gradients are ONE run of the reference and carry its atomics' noise: max-norm bound only)
     check_grads(mine, rb)
 
 
@@ -155,8 +217,8 @@ def test_against_live_reference(name):
     check_forward_against(fwd, kw, rnp, exact_image=True)
     dpix = torch.randn(3, d["H"], d["W"], device="cuda", generator=torch.Generator("cuda").manual_seed(2))
     mine = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
-    rg = refgpu.backward(ref, dpix, **Hh.bwd_kwargs(kw))
-    check_grads(mine, {k: v.cpu().numpy() for k, v in rg.items()}, per_key=LIVE_REF_TOL)
+    rg, spread = reference_spread(ref, dpix, Hh.bwd_kwargs(kw))
+    check_grads(mine, rg, per_key=live_bound(spread))
 
 
 def test_operator_api_autograd_matches_cabi():
@@ -446,7 +508,7 @@ def test_hit_log_too_small_falls_back_on_device():
         torch.cuda.synchronize()
         of.n_contrib = st["n_contrib"].astype(np.uint32)
         of.final_T = st["final_T"].copy()
-        check_grads(mine, O.backward(inp, of, dpix).__dict__)
+        check_grads(mine, O.backward(inp, of, dpix).__dict__, tol=GRAD_TOL_WALK)  # (this view took the walk-back backward)
         fwd2 = capi.forward(**kw)
         torch.cuda.synchronize()
         assert capi.hit_log_state(fwd2)[2]  # re-provisioned from the need the first call published
@@ -495,5 +557,64 @@ def test_baseline_config_shapes_against_live_reference(shape):
     check_forward_against(fwd, kw, rnp, exact_image=True)
     dpix = torch.randn(3, d["H"], d["W"], device="cuda", generator=torch.Generator("cuda").manual_seed(6)) / (d["H"] * d["W"])
     mine = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
-    rg = refgpu.backward(ref, dpix, **Hh.bwd_kwargs(kw))
-    check_grads(mine, {k: v.cpu().numpy() for k, v in rg.items()}, per_key=LIVE_REF_TOL)
+    rg, spread = reference_spread(ref, dpix, Hh.bwd_kwargs(kw))
+    check_grads(mine, rg, per_key=live_bound(spread))
+
+
+def test_prefiltered_flag_changes_nothing_when_every_gaussian_is_in_front():
+    """prefiltered=True is a promise that no Gaussian is behind the near plane (auxiliary.h:154-160 traps on a culled point);
+    with every Gaussian in front the outputs equal the prefiltered=False call bit for bit."""
+    d = SCENES["surface_sh3"]()
+    kw = Hh.to_torch_kwargs(d)
+    a = capi.forward(prefiltered=False, **kw)
+    b = capi.forward(prefiltered=True, **kw)
+    torch.cuda.synchronize()
+    assert a["num_rendered"] == b["num_rendered"] and torch.equal(a["radii"], b["radii"]) and torch.equal(a["out_color"], b["out_color"])
+
+
+# BASELINE.json's configurations at FULL size against the live reference (SURVEY 8d "configs restated"): the headline
+# (1 M surface Gaussians, 1920x1080, SH3), #3 (1 M, 1352x1014, SH3), #4 (500 k, 1352x1014, GauSTAR's sh_levels = 3 -> M = 9),
+# #5 (4 M, 3840x2160: 32 400 tiles, 47 sort bits; RGB through SH, then a colors_precomp pass as its depth / normal renders do).
+FULL_CONFIGS = {
+    "headline_1M_1080p_sh3": dict(P=1_000_000, W=1920, H=1080, deg=3, cam=5, precomp=False),
+    "config3_1M_1352x1014_sh3": dict(P=1_000_000, W=1352, H=1014, deg=3, cam=2, precomp=False),
+    "config4_500k_1352x1014_sh2": dict(P=500_000, W=1352, H=1014, deg=2, cam=7, precomp=False),
+    "config5_4M_4k_sh3": dict(P=4_000_000, W=3840, H=2160, deg=3, cam=1, precomp=False),
+    "config5_4M_4k_precomp": dict(P=4_000_000, W=3840, H=2160, deg=3, cam=4, precomp=True),
+}
+
+
+@pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref not built (reference sources absent at build time)")
+@pytest.mark.parametrize("name", sorted(FULL_CONFIGS))
+def test_full_size_against_live_reference(name, backward_path):
+    """Every integer / key quantity and the image bit-identical to the unmodified reference at the full size of the configuration;
+    gradients within GRAD_TOL + LIVE_SPREAD_FACTOR x the reference's own measured run-to-run spread."""
+    c = FULL_CONFIGS[name]
+    if backward_path == "walk" and c["P"] > 1_000_000:
+        pytest.skip("the walk-back backward is covered at 1 M; 4 M runs once (memory and time)")
+    g = scene.surface_gaussians(c["P"], c["deg"], seed=0)
+    cam = scene.dome_cameras(8, c["W"], c["H"])[c["cam"]]
+    d = Hh.scene_dict(g, cam, use_sh=not c["precomp"], bg=(10.0, 10.0, 10.0) if c["precomp"] else (0.0, 1.0, 0.0))
+    del g
+    kw, fwd = run_mine(d)
+    ref = refgpu.forward(**kw)
+    P, W, H = kw["means3D"].shape[0], kw["W"], kw["H"]
+    geo = capi.unpack_geometry(fwd, P)
+    st = capi.image_state(fwd, W, H)
+    vis = ref["radii"] > 0
+    assert fwd["num_rendered"] == ref["num_rendered"] and ref["num_rendered"] > P
+    assert torch.equal(fwd["radii"], ref["radii"])
+    assert torch.equal(geo["tiles_touched"].int(), ref["tiles_touched"].int())
+    for k in ("depths", "means2D", "conic_opacity"):
+        assert torch.equal(geo[k].contiguous().view(torch.int32)[vis], ref[k].contiguous().view(torch.int32)[vis]), k
+    assert torch.equal(capi.point_list(fwd).int(), ref["point_list"].int())
+    assert torch.equal(st["ranges"].int().reshape(-1), ref["ranges"].int().reshape(-1))
+    assert torch.equal(st["n_contrib"].int().reshape(-1), ref["n_contrib"].int().reshape(-1))
+    assert torch.equal(fwd["out_color"], ref["out_color"])
+    assert torch.equal(st["final_T"].reshape(-1), ref["final_T"].reshape(-1))
+    del geo, st
+    dpix = torch.randn(3, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(2)) / (W * H)
+    mine = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
+    torch.cuda.synchronize()
+    rg, spread = reference_spread(ref, dpix, Hh.bwd_kwargs(kw))
+    check_grads(mine, rg, per_key=live_bound(spread))

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_zz_reference_callers_gpu.py -m gpu -q -x > gpurun_out/r2ag_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2ag_pytest.log; tail -40 gpurun_out/r2ag_pytest.log
+timeout 2400 python -m pytest tests -m gpu -q -x > gpurun_out/r2ak_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2ak_pytest.log; tail -30 gpurun_out/r2ak_pytest.log | cut -c1-250
