@@ -49,10 +49,34 @@ UNIT = "views/s"
 P_TARGET, W, H, SH_DEG = 1_000_000, 1920, 1080, 3
 VIEWS_PER_GPU = 20  # BASELINE.json config #3: 160 views / 8 GPUs per step
 CAM_POOL = 32
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-# (profiles/r1p_ncu_full_summary.txt); None where no capture is committed
-NCU_TRAFFIC = {"blend_fwd": 388686592, "blend_bwd": 548568832, "preprocess_bwd": 556546816, "preprocess_fwd": 258706176, "tile_sort": 112042240,
-               "emit": 16018176, "tile_scan": 61696}
+NUM_SMS_FALLBACK = 148
+
+
+def kernel_sources_sha():
+    """Identity of the kernels a capture belongs to: sha256 over gaustar_b200/csrc (sorted file names and contents)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "gaustar_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture():
+    """dram__bytes_read+write and smsp__inst_executed per launch of every kernel, from profiles/ncu_capture.json -- written by
+    tools/ncu_capture.py from an `ncu --set full` capture of this workload together with the sha of the kernel sources it was
+    taken from.  Returned only when that sha equals the sources' sha now: a capture of other code is not a measurement of this
+    code (round 1 printed a constant that predated two kernel rewrites)."""
+    path = os.path.join(ROOT, "profiles", "ncu_capture.json")
+    try:
+        cap = json.load(open(path))
+    except Exception:
+        return None, "no profiles/ncu_capture.json"
+    sha = kernel_sources_sha()
+    if cap.get("sources_sha") != sha:
+        return None, f"profiles/ncu_capture.json was taken from kernel sources {cap.get('sources_sha')}, these are {sha}: traffic withheld"
+    return cap, f"profiles/ncu_capture.json ({cap.get('capture')}, sources {sha})"
 
 
 def measured_peak():
@@ -136,7 +160,7 @@ def build_workload(device, rank, world):
 class OursCABI:
     """Device-resident arm: straight through the C ABI."""
     name = "gaustar_b200 (C ABI)"
-    launches_per_view = 8  # preprocess_fwd, tile_scan, emit, tile_sort, blend_fwd, blend_bwd_gather, blend_bwd (no-op), preprocess_bwd
+    launches_per_view = 9  # preprocess_fwd, tile_scan, emit, tile_sort, blend_fwd, blend_fwd_fat (no marked tile here), blend_bwd_gather, blend_bwd (no-op), preprocess_bwd
 
     def __init__(self):
         from gaustar_b200 import capi
@@ -348,9 +372,20 @@ def run_gpu(args, impl_name, rank, world, local):
                 ms = float(np.mean(ts))
                 per[name] = {"ms": round(ms, 4), "algorithmic_bytes": int(alg[name]), "gbs": round(alg[name] / (ms * 1e-3) / 1e9, 1),
                              "frac": round(alg[name] / (ms * 1e-3) / 1e9 / peak, 4), "samples": len(ts)}
+        # issue-slot ceiling next to the HBM one: warp instructions of the kernel (ncu capture of the same sources)
+        # over the issue slots its live duration offered -- SMs x 4 schedulers x SM clock under load
+        cap, cap_note = ncu_capture()
+        sm_mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
+        n_sms = torch.cuda.get_device_properties(device).multi_processor_count or NUM_SMS_FALLBACK
+        for name, st_ in per.items():
+            k = (cap or {}).get("kernels", {}).get(kernel_of[name])
+            st_["traffic"] = k["dram_bytes"] if k else None
+            st_["warp_instructions"] = k["warp_inst"] if k else None
+            st_["issue_frac"] = round(k["warp_inst"] / (st_["ms"] * 1e-3 * n_sms * 4 * sm_mhz * 1e6), 4) if k else None
         dom = max(per, key=lambda k: per[k]["ms"])
         roofline = {"kernel": kernel_of[dom], "stage": dom, "bound": "hbm", "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": per[dom]["frac"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": how, "algorithmic_bytes_per_launch": per[dom]["algorithmic_bytes"],
+                    "frac": per[dom]["frac"], "traffic": per[dom]["traffic"], "traffic_source": cap_note, "issue_frac": per[dom]["issue_frac"],
+                    "peak_source": how, "algorithmic_bytes_per_launch": per[dom]["algorithmic_bytes"],
                     "avg_launch_ms": per[dom]["ms"], "avg_num_rendered": int(R_avg),
                     "note": "dominant (longest) kernel of the step, timed live with CUDA events on its launching stream while the other "
                             "stream's view runs concurrently; blend kernels are SIMT-issue-bound by construction (DESIGN.md section 4)",
@@ -358,102 +393,176 @@ def run_gpu(args, impl_name, rank, world, local):
 
     # ---------------- public-API arm (e2e): host buffers, copies inside the timed region ----------------
     Settings, Rasterizer = make_autograd_rasterizer(impl_name)
-    if impl_name == "ours":
-        # gradient-accumulation fusion: the leaves' .grad (views of the flat all-reduce buffer) are updated inside the
-        # backward kernel instead of by autograd's AccumulateGrad (gaustar_b200/rasterizer.py)
-        import gaustar_b200
-        gaustar_b200.set_grad_accumulation_fusion(True)
     name_of = {"means3D": "dL_dmeans3D", "scales": "dL_dscales", "rotations": "dL_drotations", "opacities": "dL_dopacity", "shs": "dL_dsh"}
     base_leaves = {k: params[k].clone() for k in name_of}
-    # one set of autograd leaves per compute stream (same storage, separate .grad buffers = the per-stream flat buffers),
-    # so that each stream's AccumulateGrad nodes run on that stream and never touch the other stream's buffer
-    leaf_sets, m2d_sets = [], []
-    e2e_streams = side if side else [torch.cuda.current_stream(device)]
-    for si, st in enumerate(e2e_streams):
-        with torch.cuda.stream(st):
-            ls = {k: base_leaves[k].detach().requires_grad_(True) for k in name_of}
-            for k, p_ in ls.items():
-                p_.grad = flats[si].views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
-            leaf_sets.append(ls)
-            m2d_sets.append(torch.zeros(P, 3, device=device, requires_grad=True))
-    torch.cuda.synchronize()
     copy_stream = torch.cuda.Stream(device)
-    slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), tgt_f=torch.empty(3, H, W, device=device), vm=torch.empty(4, 4, device=device),
-                  pm=torch.empty(4, 4, device=device), cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event())
-             for _ in range(n_streams + 1)]
-    NSLOT = len(slots)
     h2d_per_view = H * W * 3 + (16 + 16 + 3) * 4
 
-    def prefetch(slot, v, i):
-        """H2D of the next view's 8-bit target + camera on the copy stream, and its uint8 -> float CHW conversion there too."""
-        s = slots[slot]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(s["free"])
-            s["tgt"].copy_(targets[i % len(targets)], non_blocking=True)
-            s["vm"].copy_(cam_host[v]["viewmatrix"], non_blocking=True)
-            s["pm"].copy_(cam_host[v]["projmatrix"], non_blocking=True)
-            s["cp"].copy_(cam_host[v]["campos"], non_blocking=True)
-            torch.mul(s["tgt"].permute(2, 0, 1), 1.0 / 255.0, out=s["tgt_f"])  # uint8 HWC -> float CHW in one kernel
-            s["ev"].record(copy_stream)
-
-    loss_acc = [torch.zeros((), device=device) for _ in e2e_streams]
-
-    def step_e2e(step):
-        main = torch.cuda.current_stream(device)
-        for fl in flats:
-            fl.zero_()
-        for la in loss_acc:
-            la.zero_()
-        views = my_views(step)
-        prefetch(0, views[0], 0)
-        if side:
-            fork.record(main)
-            for st in side:
-                st.wait_event(fork)
-        ns = len(e2e_streams)
-        for i, v in enumerate(views):
-            s = slots[i % NSLOT]
-            if i + 1 < len(views):
-                prefetch((i + 1) % NSLOT, views[i + 1], i + 1)
-            st, ls = e2e_streams[i % ns], leaf_sets[i % ns]
+    def measure_e2e(ns, fusion):
+        """views/s through the operator API with `ns` views in flight on `ns` CUDA streams; fusion: gradient accumulation inside the
+        backward kernel into the leaves' .grad (ours only; needs LEAF inputs -- GauSTAR's own call sites pass non-leaf tensors)."""
+        if impl_name == "ours":
+            import gaustar_b200
+            gaustar_b200.set_grad_accumulation_fusion(bool(fusion))
+        streams = [torch.cuda.Stream(device) for _ in range(ns)] if ns > 1 else [torch.cuda.current_stream(device)]
+        fl_set = flats[:ns] if len(flats) >= ns else flats + [gdist.FlatGrads(P, M, device) for _ in range(ns - len(flats))]
+        # one set of autograd leaves per compute stream (same storage, separate .grad buffers = the per-stream flat buffers),
+        # so that each stream's AccumulateGrad nodes run on that stream and never touch the other stream's buffer
+        leaf_sets, m2d_sets = [], []
+        for si, st in enumerate(streams):
             with torch.cuda.stream(st):
-                st.wait_event(s["ev"])
-                rs = Settings(image_height=H, image_width=W, tanfovx=cam_host[v]["tanfovx"], tanfovy=cam_host[v]["tanfovy"], bg=bg, scale_modifier=1.0,
-                              viewmatrix=s["vm"], projmatrix=s["pm"], sh_degree=SH_DEG, campos=s["cp"], prefiltered=False, debug=False)
-                img, _radii = Rasterizer(rs)(means3D=ls["means3D"], means2D=m2d_sets[i % ns], opacities=ls["opacities"], shs=ls["shs"],
-                                             scales=ls["scales"], rotations=ls["rotations"])
-                loss = _L1Mean.apply(img, s["tgt_f"])
-                loss.backward()
-                loss_acc[i % ns] += loss.detach()
-                s["free"].record(st)
-        if side:
-            for st, ev in zip(side, joins):
-                ev.record(st)
-                main.wait_event(ev)
-            for fl in flats[1:]:
-                flat.flat.add_(fl.flat)
-        flat.allreduce()
-        return float(sum(loss_acc).item())  # D2H read of the step's result
+                ls = {k: base_leaves[k].detach().requires_grad_(True) for k in name_of}
+                for k, p_ in ls.items():
+                    p_.grad = fl_set[si].views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
+                leaf_sets.append(ls)
+                m2d_sets.append(torch.zeros(P, 3, device=device, requires_grad=True))
+        torch.cuda.synchronize()
+        slots = [dict(tgt=torch.empty(H, W, 3, dtype=torch.uint8, device=device), tgt_f=torch.empty(3, H, W, device=device), vm=torch.empty(4, 4, device=device),
+                      pm=torch.empty(4, 4, device=device), cp=torch.empty(3, device=device), ev=torch.cuda.Event(), free=torch.cuda.Event())
+                 for _ in range(ns + 1)]
+        NSLOT = len(slots)
+        fork_e, joins_e = torch.cuda.Event(), [torch.cuda.Event() for _ in streams]
 
-    for e in slots:
-        e["free"].record(torch.cuda.current_stream(device))
-    e2e_steps = max(1, args.steps)
-    for s in range(min(args.warmup, 3)):
-        step_e2e(s)
-    gdist.barrier(); torch.cuda.synchronize()
-    e0.record()
-    for s in range(e2e_steps):
-        step_e2e(args.warmup + s)
-    e1.record()
-    gdist.barrier(); torch.cuda.synchronize()
-    ms_e2e = gdist.max_over_ranks(e0.elapsed_time(e1), device)
-    e2e_val = VIEWS_PER_GPU * world * e2e_steps / (ms_e2e / 1e3)
+        def prefetch(slot, v, i):
+            """H2D of the next view's 8-bit target + camera on the copy stream, and its uint8 -> float CHW conversion there too."""
+            sl = slots[slot]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(sl["free"])
+                sl["tgt"].copy_(targets[i % len(targets)], non_blocking=True)
+                sl["vm"].copy_(cam_host[v]["viewmatrix"], non_blocking=True)
+                sl["pm"].copy_(cam_host[v]["projmatrix"], non_blocking=True)
+                sl["cp"].copy_(cam_host[v]["campos"], non_blocking=True)
+                torch.mul(sl["tgt"].permute(2, 0, 1), 1.0 / 255.0, out=sl["tgt_f"])  # uint8 HWC -> float CHW in one kernel
+                sl["ev"].record(copy_stream)
+
+        loss_acc = [torch.zeros((), device=device) for _ in streams]
+
+        def step_e2e(step):
+            main = torch.cuda.current_stream(device)
+            for fl in fl_set:
+                fl.zero_()
+            for la in loss_acc:
+                la.zero_()
+            views = my_views(step)
+            prefetch(0, views[0], 0)
+            if ns > 1:
+                fork_e.record(main)
+                for st in streams:
+                    st.wait_event(fork_e)
+            for i, v in enumerate(views):
+                sl = slots[i % NSLOT]
+                if i + 1 < len(views):
+                    prefetch((i + 1) % NSLOT, views[i + 1], i + 1)
+                st, ls = streams[i % ns], leaf_sets[i % ns]
+                with torch.cuda.stream(st):
+                    st.wait_event(sl["ev"])
+                    rs = Settings(image_height=H, image_width=W, tanfovx=cam_host[v]["tanfovx"], tanfovy=cam_host[v]["tanfovy"], bg=bg, scale_modifier=1.0,
+                                  viewmatrix=sl["vm"], projmatrix=sl["pm"], sh_degree=SH_DEG, campos=sl["cp"], prefiltered=False, debug=False)
+                    img, _radii = Rasterizer(rs)(means3D=ls["means3D"], means2D=m2d_sets[i % ns], opacities=ls["opacities"], shs=ls["shs"],
+                                                 scales=ls["scales"], rotations=ls["rotations"])
+                    loss = _L1Mean.apply(img, sl["tgt_f"])
+                    loss.backward()
+                    loss_acc[i % ns] += loss.detach()
+                    sl["free"].record(st)
+            if ns > 1:
+                for st, ev in zip(streams, joins_e):
+                    ev.record(st)
+                    main.wait_event(ev)
+                for fl in fl_set[1:]:
+                    fl_set[0].flat.add_(fl.flat)
+            fl_set[0].allreduce()
+            return float(sum(loss_acc).item())  # D2H read of the step's result
+
+        for e in slots:
+            e["free"].record(torch.cuda.current_stream(device))
+        e2e_steps = max(1, args.steps)
+        for s_ in range(min(args.warmup, 3)):
+            step_e2e(s_)
+        gdist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for s_ in range(e2e_steps):
+            step_e2e(args.warmup + s_)
+        e1.record()
+        gdist.barrier(); torch.cuda.synchronize()
+        ms = gdist.max_over_ranks(e0.elapsed_time(e1), device)
+        del leaf_sets, m2d_sets, slots
+        return VIEWS_PER_GPU * world * e2e_steps / (ms / 1e3)
+
+    ours = impl_name == "ours"
+    ns_main = n_streams if ours else 1
+    e2e_val = measure_e2e(ns_main, fusion=ours)
     e2e = {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_per_view * VIEWS_PER_GPU, "d2h_bytes_per_step": 4,
            "api": "diff_gaussian_rasterization.GaussianRasterizer + autograd; target image (uint8) and camera copied from pinned host memory per view "
-                  "(prefetched on a copy stream), loss scalar read back per step; compute streams: " + str(len(e2e_streams))
-                  + ("; gradient-accumulation fusion into the leaves' .grad (set_grad_accumulation_fusion)" if impl_name == "ours" else "")}
+                  "(prefetched on a copy stream), loss scalar read back per step; compute streams: " + str(ns_main)
+                  + ("; gradient-accumulation fusion into the leaves' .grad (set_grad_accumulation_fusion)" if ours else "")}
+    if ours and not args.quick:
+        # the same measurement under the conditions an UNMODIFIED GauSTAR call site has: its rasterizer inputs are non-leaf tensors,
+        # so the fusion cannot apply, and it renders one view at a time on one stream -- the reference arm's own conditions
+        e2e["value_unfused"] = round(measure_e2e(ns_main, fusion=False), 2)
+        e2e["value_like_for_like"] = round(measure_e2e(1, fusion=False), 2)
+        e2e["like_for_like"] = "1 view in flight on 1 stream, ordinary AccumulateGrad: the conditions of the reference arm and of unmodified GauSTAR call sites"
+        import gaustar_b200
+        gaustar_b200.set_grad_accumulation_fusion(True)
+
+    # ---------------- GauSTAR's own training step (refine.py:552-616): RGB, then depth, through colors_precomp ----------------
+    refine = None
+    if not args.quick:
+        refine = measure_refine_step(args, impl_name, Settings, Rasterizer, params, bg, cam_host, targets, device, P)
     return dict(value=value, ms_per_step=ms_value / args.steps, roofline=roofline, e2e=e2e, clocks=clk, P=P, M=M, device_name=torch.cuda.get_device_name(device),
-                launches=impl.launches_per_view * VIEWS_PER_GPU * args.steps, impl_desc=impl.name, allreduce_bytes=flat.nbytes)
+                launches=impl.launches_per_view * VIEWS_PER_GPU * args.steps, impl_desc=impl.name, allreduce_bytes=flat.nbytes, refine_step=refine)
+
+
+def measure_refine_step(args, impl_name, Settings, Rasterizer, params, bg, cam_host, targets, device, P, iters=60):
+    """iterations/s of the step gaustar_trainers/refine.py runs (:529-841, one view per iteration, single stream): the camera goes
+    host -> device, the Gaussians are rendered TWICE from it -- RGB with colours precomputed outside the rasterizer
+    (compute_color_in_rasterizer=False: colors_precomp, no SH in the op; :552-564) on bg [0,1,0], then view depth as three equal
+    colour channels on bg [10,10,10] (:602-616) -- an L1 loss on both, one backward, and the host reads the loss (the trainer
+    logs it).  Rasterizer inputs are NON-LEAF tensors as in SuGaR (points/scaling/quaternions are computed per call)."""
+    leaves = {k: params[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities")}
+    rgb_leaf = torch.rand(P, 3, device=device).requires_grad_(True)
+    bg_depth = torch.full((3,), 10.0, device=device)
+    tgt = (targets[0].to(device).permute(2, 0, 1).float() / 255.0).contiguous()
+    tgt_depth = torch.full((3, H, W), 3.0, device=device)
+    vm_d, pm_d, cp_d = torch.empty(4, 4, device=device), torch.empty(4, 4, device=device), torch.empty(3, device=device)
+    import contextlib
+    variants = [("unchanged", contextlib.nullcontext)]
+    if impl_name == "ours":
+        import diff_gaussian_rasterization as dgr
+        variants.append(("shared_geometry", dgr.shared_geometry))  # the one-line edit: `with shared_geometry():` around the two calls
+    out = {}
+    for vname, ctx in variants:
+        def one_iter(it):
+            v = it % len(cam_host)
+            vm_d.copy_(cam_host[v]["viewmatrix"], non_blocking=True)
+            pm_d.copy_(cam_host[v]["projmatrix"], non_blocking=True)
+            cp_d.copy_(cam_host[v]["campos"], non_blocking=True)
+            m, sc, rot, op = (leaves[k] * 1.0 for k in ("means3D", "scales", "rotations", "opacities"))  # non-leaf, like SuGaR's properties
+            col = rgb_leaf * 1.0
+            m2d = torch.zeros(P, 3, device=device, requires_grad=True)
+            mk = lambda b: Settings(image_height=H, image_width=W, tanfovx=cam_host[v]["tanfovx"], tanfovy=cam_host[v]["tanfovy"], bg=b, scale_modifier=1.0,
+                                    viewmatrix=vm_d, projmatrix=pm_d, sh_degree=0, campos=cp_d, prefiltered=False, debug=False)
+            with ctx():
+                img, _ = Rasterizer(mk(bg))(means3D=m, means2D=m2d, opacities=op, colors_precomp=col, scales=sc, rotations=rot)
+                depth = (m @ vm_d[:3, 2] + vm_d[3, 2])[:, None].expand(-1, 3)
+                dimg, _ = Rasterizer(mk(bg_depth))(means3D=m, means2D=m2d, opacities=op, colors_precomp=depth, scales=sc, rotations=rot)
+            loss = (img - tgt).abs().mean() + (dimg - tgt_depth).abs().mean()
+            loss.backward()
+            for t_ in list(leaves.values()) + [rgb_leaf]:
+                t_.grad = None
+            return float(loss.item())
+
+        for it in range(5):
+            one_iter(it)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for it in range(iters):
+            one_iter(5 + it)
+        torch.cuda.synchronize()
+        out[vname] = round(iters / (time.time() - t0), 2)
+    return {"workload": f"GauSTAR refine step: 1 view/iteration, colors_precomp RGB pass + depth pass (2 fwd + 2 bwd) at {P} Gaussians {W}x{H}, "
+                        "non-leaf inputs, single stream, loss read back every iteration (refine.py:552-616)",
+            "unit": "iterations/s", "value": out["unchanged"], "value_with_shared_geometry": out.get("shared_geometry"), "iterations": iters,
+            "timing": "host wall clock around the loop (the step includes host work by design)"}
 
 
 def cpu_oracle_views_per_sec(n_views=1, small=False):
@@ -486,12 +595,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (CUDA streams) in our arm")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (skip the unfused / like-for-like e2e variants, the refine step, the CPU baselines)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "config3"],
+                    help="headline: 1 M Gaussians at 1920x1080 (BASELINE.json's metric); config3: the same Gaussians at 1352x1014 (ActorsHQ shape)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global W, H
+    if args.workload == "config3":
+        W, H = 1352, 1014
     os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     rank, world, local = gdist.init_from_env()
     have_gpu = torch.cuda.is_available()
-    config = {"workload": f"surface-1M-1080p-sh3 ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
+    wl_name = "surface-1M-1080p-sh3" if args.workload == "headline" else "config3: surface-1M-1352x1014-sh3 (160 views / 8 GPUs)"
+    config = {"workload": f"{wl_name} ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
               "gaussians": None, "resolution": [W, H], "sh_degree": SH_DEG, "views_per_step": VIEWS_PER_GPU * world,
               "parallelism": f"view-sharded dp{world} + 1 allreduce/step; ours: {args.streams} views in flight on {args.streams} CUDA streams per GPU", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
 
@@ -520,6 +636,8 @@ def main():
             "ms_per_step": round(res["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"],
             "device": res["device_name"], "allreduce_bytes_per_step": res["allreduce_bytes"] if world > 1 else 0}
+    if res.get("refine_step"):
+        line["refine_step"] = res["refine_step"]
     if args.impl == "reference":
         line["impl"] = "reference"
         line["implementation"] = res["impl_desc"]
@@ -528,10 +646,18 @@ def main():
         line["gpu_launches"] = 0
     else:
         line["roofline"] = res["roofline"]
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             v, dt, sample = cpu_oracle_views_per_sec(3)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
                                     "seconds": round(dt, 1)}
+            # the CPU baseline north_star / BASELINE.md 2.2 name: a naive PyTorch point-splat with autograd, at its two stated sizes
+            from oracle import naive_splat
+            naive = []
+            for Pn, wn, hn, nv in ((30000, 128, 128, 4), (200000, 480, 270, 2)):
+                v2, dt2, Pgot = naive_splat.time_fwd_bwd(Pn, wn, hn, sh_degree=SH_DEG, views=nv)
+                naive.append({"value": round(v2, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "naive PyTorch point-splat (oracle/naive_splat.py)",
+                              "sample": f"{nv} views fwd+bwd (autograd) of P={Pgot} {wn}x{hn} SH{SH_DEG}", "seconds": round(dt2, 1)})
+            line["cpu_baseline_naive"] = naive
     print(json.dumps(line), flush=True)
 
 
