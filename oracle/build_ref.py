@@ -54,6 +54,8 @@ PY_CALLERS = [
     (os.path.join(REF_ROOT, "gaustar_scene", "sugar_model.py"), "gaustar/gaustar_scene/sugar_model"),
     (os.path.join(REF_ROOT, "gaustar_scene", "cameras.py"), "gaustar/gaustar_scene/cameras"),
     (os.path.join(REF_ROOT, "gaustar_scene", "gs_model.py"), "gaustar/gaustar_scene/gs_model"),
+    (os.path.join(REF_ROOT, "gaustar_scene", "sugar_optimizer.py"), "gaustar/gaustar_scene/sugar_optimizer"),
+    (os.path.join(REF_ROOT, "gaustar_utils", "loss_utils.py"), "gaustar/gaustar_utils/loss_utils"),
     (os.path.join(REF_ROOT, "gaustar_utils", "spherical_harmonics.py"), "gaustar/gaustar_utils/spherical_harmonics"),
     (os.path.join(REF_ROOT, "gaustar_utils", "graphics_utils.py"), "gaustar/gaustar_utils/graphics_utils"),
     (os.path.join(REF_ROOT, "gaustar_utils", "general_utils.py"), "gaustar/gaustar_utils/general_utils"),

@@ -45,6 +45,24 @@ def _batched(x, n, device, dtype=torch.float32):
     return t
 
 
+class _RowVectorTransform:
+    """The small part of pytorch3d.transforms.Transform3d GauSTAR touches: a batch of 4x4 row-vector matrices."""
+
+    def __init__(self, matrix):
+        self._matrix = matrix
+
+    def get_matrix(self):
+        return self._matrix
+
+    def inverse(self):
+        return _RowVectorTransform(torch.linalg.inv(self._matrix))
+
+    def transform_points(self, points):
+        p = points if points.dim() == 3 else points[None]
+        out = p @ self._matrix[:, :3, :3] + self._matrix[:, 3:4, :3]
+        return out if points.dim() == 3 else out[0]
+
+
 class FoVPerspectiveCameras:
     def __init__(self, znear=1.0, zfar=100.0, aspect_ratio=1.0, fov=60.0, degrees: bool = True, R=None, T=None, K=None, device="cpu"):
         R = torch.eye(3)[None] if R is None else R
@@ -87,13 +105,17 @@ class FoVPerspectiveCameras:
     def cuda(self):
         return self.to("cuda")
 
-    def get_camera_center(self):
+    def get_world_to_view_transform(self):
+        """X_view = X_world @ R + T (refine.py:604-605 takes the z column of it as the per-Gaussian depth)."""
         n = len(self)
         M = torch.zeros(n, 4, 4, device=self.device, dtype=self.R.dtype)
         M[:, :3, :3] = self.R
         M[:, 3, :3] = self.T
         M[:, 3, 3] = 1.0
-        return torch.linalg.inv(M)[:, 3, :3]
+        return _RowVectorTransform(M)
+
+    def get_camera_center(self):
+        return self.get_world_to_view_transform().inverse().get_matrix()[:, 3, :3]
 
     def get_projection_transform(self):
         raise NotImplementedError("shims/pytorch3d: the FoV projection transform is not needed by GauSTAR's calls (K is always given)")

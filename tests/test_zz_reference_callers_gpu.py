@@ -210,3 +210,90 @@ def test_sugar_render_image_gaussian_rasterizer_runs_unchanged(color_in_rasteriz
     assert torch.equal(a["radii"], b["radii"])
     assert torch.equal(a["image"], b["image"])
     _check_param_grads(dict(a["grads"], viewspace_points=a["vsp"]), dict(b["grads"], viewspace_points=b["vsp"]))
+
+
+@needs_pyref
+def test_refine_loop_with_the_references_model_optimizer_and_losses():
+    """The training step of gaustar_trainers/refine.py (:529-841) driven with the reference's own modules -- SuGaR bound to a mesh,
+    GSCamera / CamerasWrapper, SuGaROptimizer + OptimizationParams (sugar_optimizer.py), l1_loss / ssim (loss_utils.py) and the
+    mesh regulariser -- for 40 iterations per operator from identical seeds.  The loop body restates refine.py's path with GauSTAR's
+    settings: RGB pass (compute_color_in_rasterizer=False, :552-564), l1+dssim loss (:451-453), depth pass with the view depth as
+    point_colors on bg = max_depth (:602-616), depth L1 on the foreground and mask loss on the background (:630-659), normal
+    consistency (:686-688), opacity regulariser (:744-748), backward, optimizer.step (:794-795).  Bar: same loss curve -- the first
+    iterations to 1e-4 relative (same images, gradients within the atomics' noise), the last one within 2 % (two Adam trajectories
+    fed gradients that differ by that noise drift apart slowly) -- and the loss decreases."""
+    verts, faces, cams = _sugar_inputs(n_faces=3000, n_cams=6, W=384, H=216)
+    vcol = np.random.default_rng(4).uniform(0, 1, (len(verts), 3))
+    max_depth = 10.0
+    curves = {}
+    gt = {}
+    for name, op in (list(_arms())[::-1]):  # the reference arm first: it renders the ground truth both arms train against
+        with _Arm(op):
+            sm = importlib.import_module("gaustar_scene.sugar_model")
+            cm = importlib.import_module("gaustar_scene.cameras")
+            so = importlib.import_module("gaustar_scene.sugar_optimizer")
+            lu = importlib.import_module("gaustar_utils.loss_utils")
+            from pytorch3d.loss import mesh_normal_consistency
+            import open3d
+            gs_cams = []
+            for i, c in enumerate(cams):
+                w2c = c.viewmatrix.reshape(4, 4).T.astype(np.float64)
+                gs_cams.append(cm.GSCamera(colmap_id=i, R=w2c[:3, :3].T.copy(), T=w2c[:3, 3].copy(), FoVx=2.0 * np.arctan(c.tanfovx),
+                                           FoVy=2.0 * np.arctan(c.tanfovy), image=None, gt_alpha_mask=None, image_name=f"img_{i:04d}", uid=i,
+                                           image_height=c.image_height, image_width=c.image_width))
+            wrapper = cm.CamerasWrapper(gs_cams)
+            nerf = types.SimpleNamespace(device=torch.device("cuda"), training_cameras=wrapper)
+
+            def make(vertices, colours):
+                torch.manual_seed(0)
+                return sm.SuGaR(nerfmodel=nerf, points=None, colors=None, initialize=False, sh_levels=3, keep_track_of_knn=False,
+                                surface_mesh_to_bind=open3d.TriangleMeshLike(vertices, faces, colours), n_gaussians_per_surface_triangle=6,
+                                learn_surface_mesh_opacity=True)
+
+            def two_passes(model, ci):
+                rgb = model.render_image_gaussian_rasterizer(camera_indices=ci, bg_color=[0.0, 1.0, 0.0], sh_deg=2, compute_color_in_rasterizer=False,
+                                                             compute_covariance_in_rasterizer=True, return_2d_radii=False)
+                depth_pts = wrapper.p3d_cameras[ci].get_world_to_view_transform().transform_points(model.points)[..., 2:].expand(-1, 3)
+                depth = model.render_image_gaussian_rasterizer(camera_indices=ci, bg_color=max_depth + torch.zeros(3, dtype=torch.float, device="cuda"),
+                                                               sh_deg=0, compute_color_in_rasterizer=False, compute_covariance_in_rasterizer=True,
+                                                               return_2d_radii=False, point_colors=depth_pts)[..., 0]
+                return rgb, depth
+
+            if not gt:  # ground truth: the same mesh, moved and recoloured, rendered once (by the reference arm)
+                with torch.no_grad():
+                    target = make(verts * np.array([1.03, 0.98, 1.02]) + np.array([0.01, -0.015, 0.0]), np.clip(vcol * 0.6 + 0.3, 0, 1))
+                    target.all_densities.copy_(torch.logit(torch.full_like(target.all_densities, 0.95)))
+                    for ci in range(len(cams)):
+                        gt[ci] = tuple(t.clone() for t in two_passes(target, ci))
+                    del target
+            sugar = make(verts, vcol)
+            with torch.no_grad():
+                sugar.all_densities.copy_(torch.logit(torch.full_like(sugar.all_densities, 0.9)))
+            optimizer = so.SuGaROptimizer(sugar, so.OptimizationParams(iterations=40, position_lr_max_steps=40), spatial_lr_scale=wrapper.get_spatial_extent())
+            order = torch.randperm(40, generator=torch.Generator().manual_seed(3)) % len(cams)
+            losses = []
+            for it in range(40):
+                optimizer.update_learning_rate(it + 1)
+                ci = int(order[it])
+                pred_rgb, pred_depth = two_passes(sugar, ci)
+                pr = pred_rgb.permute(2, 0, 1)[None]
+                gr_ = gt[ci][0].permute(2, 0, 1)[None]
+                loss = 0.8 * lu.l1_loss(pr, gr_) + 0.2 * (1.0 - lu.ssim(pr, gr_))
+                gt_depth = gt[ci][1]
+                fg = gt_depth < max_depth
+                loss = loss + 1.0 * (pred_depth[fg] - gt_depth[fg]).abs().mean() + 1.0 * (pred_depth[~fg] - max_depth).abs().mean()
+                loss = loss + 0.1 * mesh_normal_consistency(sugar.surface_mesh)
+                loss = loss + torch.relu(0.8 - sugar.strengths.view(-1, 1)).mean()
+                loss.backward()
+                optimizer.step()
+                optimizer.zero_grad(set_to_none=True)
+                losses.append(float(loss.item()))
+            curves[name] = np.array(losses)
+    a, b = curves["ours"], curves["reference"]
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    assert np.abs(a[:5] - b[:5]).max() / b[:5].max() < 1e-4, (a[:5], b[:5])
+    assert abs(a[-1] - b[-1]) / b[-1] < 2e-2, (a[-5:], b[-5:])
+    assert a[-8:].mean() < 0.9 * a[:8].mean(), a  # it trains
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        np.savetxt(os.path.join(out, "refine_loop_loss_curves.txt"), np.stack([a, b], 1), header="loss per iteration: gaustar_b200 | reference rasterizer", fmt="%.6f")
