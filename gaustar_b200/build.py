@@ -21,7 +21,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgstar_raster.so")
 EXT = os.path.join(HERE, "_C.so")
 
-CU_SOURCES = ["preprocess.cu", "binning.cu", "blend.cu", "api.cu", "knn.cu"]
+CU_SOURCES = ["preprocess.cu", "binning.cu", "blend.cu", "api.cu", "knn.cu", "sugar_prologue.cu"]
 CU_HEADERS = ["gstar_common.cuh", "gstar_kernels.h", "recent_calls.h", os.path.join(ROOT, "include", "gstar_raster.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "--extended-lambda"]

@@ -23,7 +23,7 @@ EXPORTED = [
     "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
     "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
     "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state", "gstar_debug_header", "gstar_knn3_mean_dist2",
-    "gstar_raster_reblend",
+    "gstar_raster_reblend", "gstar_sugar_prologue_forward", "gstar_sugar_prologue_backward",
 ]
 STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
@@ -67,6 +67,19 @@ class ReblendArgs(C.Structure):
     ]
 
 
+class SugarArgs(C.Structure):
+    """gstar_sugar_args (include/gstar_raster.h)."""
+    _fields_ = [
+        ("P", C.c_int), ("K", C.c_int),
+        ("verts", C.c_void_p), ("faces32", C.c_void_p), ("faces64", C.c_void_p), ("bary", C.c_void_p),
+        ("scales", C.c_void_p), ("cplx", C.c_void_p), ("dens", C.c_void_p),
+        ("thickness", C.c_float), ("min_scale", C.c_float), ("max_scale", C.c_float), ("has_min", C.c_int), ("has_max", C.c_int),
+        ("points", C.c_void_p), ("scaling", C.c_void_p), ("quats", C.c_void_p), ("opac", C.c_void_p),
+        ("g_points", C.c_void_p), ("g_scaling", C.c_void_p), ("g_quats", C.c_void_p), ("g_opac", C.c_void_p),
+        ("d_verts", C.c_void_p), ("d_scales", C.c_void_p), ("d_cplx", C.c_void_p), ("d_dens", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -96,6 +109,8 @@ def lib():
         L.gstar_set_hit_log.argtypes = [C.c_int]
         L.gstar_knn3_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_void_p, C.c_void_p]
+        L.gstar_sugar_prologue_forward.argtypes = [C.POINTER(SugarArgs), C.c_void_p]
+        L.gstar_sugar_prologue_backward.argtypes = [C.POINTER(SugarArgs), C.c_void_p]
         L.gstar_debug_header.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.gstar_hit_log_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         _lib = L

@@ -543,6 +543,29 @@ int gstar_mark_visible(int P, const float* means3D, const float* viewmatrix, con
     return 0;
 }
 
+static int sugar_call(const gstar_sugar_args* a, void* stream, bool backward)
+{
+    if (!a) return fail(GSTAR_ERR_INVALID, "null argument");
+    if (a->P <= 0) return 0;
+    if (a->K <= 0 || a->P % a->K != 0) return fail(GSTAR_ERR_INVALID, "P must be a multiple of the Gaussians per face");
+    if (!a->verts || !a->bary || !a->scales || !a->cplx || !a->dens || (!a->faces32 == !a->faces64))
+        return fail(GSTAR_ERR_INVALID, "sugar prologue: missing input (exactly one of faces32 / faces64)");
+    if (!backward && (!a->points || !a->scaling || !a->quats || !a->opac)) return fail(GSTAR_ERR_INVALID, "sugar prologue: missing output");
+    gstar::SugarParams s;
+    s.P = a->P; s.K = a->K; s.verts = a->verts; s.faces32 = a->faces32; s.faces64 = a->faces64; s.bary = a->bary; s.scales = a->scales;
+    s.cplx = a->cplx; s.dens = a->dens; s.thickness = a->thickness; s.min_scale = a->min_scale; s.max_scale = a->max_scale;
+    s.has_min = a->has_min; s.has_max = a->has_max; s.points = a->points; s.scaling = a->scaling; s.quats = a->quats; s.opac = a->opac;
+    s.g_points = a->g_points; s.g_scaling = a->g_scaling; s.g_quats = a->g_quats; s.g_opac = a->g_opac;
+    s.d_verts = a->d_verts; s.d_scales = a->d_scales; s.d_cplx = a->d_cplx; s.d_dens = a->d_dens;
+    if (backward) gstar::launch_sugar_prologue_bwd(s, (cudaStream_t)stream);
+    else gstar::launch_sugar_prologue_fwd(s, (cudaStream_t)stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+int gstar_sugar_prologue_forward(const gstar_sugar_args* a, void* stream) { return sugar_call(a, stream, false); }
+int gstar_sugar_prologue_backward(const gstar_sugar_args* a, void* stream) { return sugar_call(a, stream, true); }
+
 int gstar_geom_unpack(const char* geom_buffer, int P, float* depths, float* means2D, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
                       unsigned char* clamped, void* stream)
 {

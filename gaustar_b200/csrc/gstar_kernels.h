@@ -129,4 +129,24 @@ void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, 
 // the call found its instance capacity too small (a replayed CUDA graph cannot grow the buffer)
 void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s, int any_overflow = 0);
 
+// mesh-bound SuGaR prologue (sugar_prologue.cu).  Forward fills points / scaling / quats / opac; backward reads the
+// g_* upstream gradients (NULL: zero) and fills d_scales / d_cplx / d_dens and ACCUMULATES into d_verts (zeroed by the caller).
+struct SugarParams {
+    int P, K;                   // Gaussians, Gaussians per face
+    const float* verts;         // [Nv,3]
+    const int* faces32;         // [F,3] (one of the two is non-NULL)
+    const long long* faces64;
+    const float* bary;          // [K,3]
+    const float* scales;        // [P,2]  log of the in-plane scales
+    const float* cplx;          // [P,2]  in-plane rotation as a complex number (normalised in-kernel)
+    const float* dens;          // [P]    logit of the opacity
+    float thickness, min_scale, max_scale;
+    int has_min, has_max;
+    float *points, *scaling, *quats, *opac;                       // forward outputs [P,3] [P,3] [P,4] [P]
+    const float *g_points, *g_scaling, *g_quats, *g_opac;         // backward inputs
+    float *d_verts, *d_scales, *d_cplx, *d_dens;                  // backward outputs
+};
+void launch_sugar_prologue_fwd(const SugarParams& s, cudaStream_t st);
+void launch_sugar_prologue_bwd(const SugarParams& s, cudaStream_t st);
+
 }  // namespace gstar

@@ -236,6 +236,30 @@ GSTAR_API int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, ui
 GSTAR_API int gstar_knn3_mean_dist2(int P, const float* points, const int* order, const int* cell_start, int nx, int ny, int nz,
                                     float ox, float oy, float oz, float cell, float* out, void* stream);
 
+/* ---- SURVEY 8f-4 (beyond the reference's operator boundary): the caller-side prologue of a mesh-bound SuGaR model --------
+ * What gaustar_scene/sugar_model.py computes per render call with a few dozen torch kernels: `points` (:417-435), `scaling`
+ * (:457-476), `quaternions` (:478-508) and `strengths` (:443-447) of P = F*K Gaussians bound K per face to a triangle mesh.
+ * All pointers are device pointers; faces32 / faces64: exactly one non-NULL ([F,3] int32 or int64).  Backward: g_* are the
+ * upstream gradients (NULL = zero); d_scales / d_cplx / d_dens are written, d_verts [Nv,3] is ACCUMULATED into (zero it first);
+ * any d_* may be NULL.  gaustar_b200/sugar.py is the host side (autograd function + a patch for SuGaR instances). */
+typedef struct gstar_sugar_args {
+    int P, K;
+    const float* verts;
+    const int* faces32;
+    const long long* faces64;
+    const float* bary;      /* [K,3] barycentric coordinates of the K Gaussians of a face (sugar_model.py:176-226) */
+    const float* scales;    /* [P,2] */
+    const float* cplx;      /* [P,2] */
+    const float* dens;      /* [P]   */
+    float thickness, min_scale, max_scale;
+    int has_min, has_max;
+    float *points, *scaling, *quats, *opac;
+    const float *g_points, *g_scaling, *g_quats, *g_opac;
+    float *d_verts, *d_scales, *d_cplx, *d_dens;
+} gstar_sugar_args;
+GSTAR_API int gstar_sugar_prologue_forward(const gstar_sugar_args* a, void* stream);
+GSTAR_API int gstar_sugar_prologue_backward(const gstar_sugar_args* a, void* stream);
+
 /* ---- measurement hook: record `start`/`stop` (cudaEvent_t) around kernel stage `stage` of every
  * subsequent call on this thread (stage < 0 disables).  Stages: see gstar_stage_name(). ---- */
 GSTAR_API int gstar_profile_stage(int stage, void* start_event, void* stop_event);

@@ -38,7 +38,7 @@ def matrix_to_quaternion(matrix: torch.Tensor) -> torch.Tensor:
     floor = torch.tensor(0.1, dtype=q_abs.dtype, device=q_abs.device)
     candidates = quat_by_rijk / (2.0 * q_abs[..., None].max(floor))
     out = candidates[F.one_hot(q_abs.argmax(dim=-1), num_classes=4) > 0.5, :].reshape(batch_dim + (4,))
-    return standardize_quaternion(out)
+    return out  # (0.7.4, the version GauSTAR pins, does not standardise the sign here; later releases do)
 
 
 def quaternion_to_matrix(quaternions: torch.Tensor) -> torch.Tensor:

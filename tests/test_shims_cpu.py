@@ -24,8 +24,9 @@ def test_quaternion_matrix_round_trip_and_sign():
     assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3, dtype=torch.float64).expand_as(R), atol=1e-12)
     assert torch.allclose(torch.linalg.det(R), torch.ones(500, dtype=torch.float64), atol=1e-12)
     q2 = T.matrix_to_quaternion(R)
-    assert (q2[:, 0] >= 0).all()
-    assert torch.allclose(q2, T.standardize_quaternion(q), atol=1e-10)
+    # pytorch3d 0.7.4 (the version GauSTAR pins) returns the best-conditioned candidate WITHOUT standardising its sign
+    assert torch.allclose(T.standardize_quaternion(q2), T.standardize_quaternion(q), atol=1e-10)
+    assert torch.allclose(T.quaternion_to_matrix(q2), R, atol=1e-10)
     # non-unit quaternions give the same rotation (sugar_model.py normalises lazily)
     assert torch.allclose(T.quaternion_to_matrix(3.7 * q), R, atol=1e-12)
     # batched leading dimensions

@@ -297,3 +297,77 @@ def test_refine_loop_with_the_references_model_optimizer_and_losses():
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
         np.savetxt(os.path.join(out, "refine_loop_loss_curves.txt"), np.stack([a, b], 1), header="loss per iteration: gaustar_b200 | reference rasterizer", fmt="%.6f")
+
+
+@needs_pyref
+def test_fused_sugar_prologue_matches_the_references_properties():
+    """gaustar_b200.sugar.fused_gaussian_params / patch_sugar against the reference's SuGaR properties
+    (sugar_model.py:417-508: points, scaling, quaternions, strengths) evaluated by the reference's own byte-compiled module with
+    torch autograd -- forward values to fp32 round-off, the gradients of a random linear functional of all four outputs w.r.t. the
+    mesh vertices, the scale / rotation parameters and the densities to 1e-4 of their max -- and a patched model renders the same
+    image with the same parameter gradients as the un-patched one."""
+    import diff_gaussian_rasterization as ours
+    from gaustar_b200 import sugar as gsugar
+    verts, faces, cams = _sugar_inputs(n_faces=6000, n_cams=3, W=320, H=180)
+    vcol = np.random.default_rng(4).uniform(0, 1, (len(verts), 3))
+    with _Arm(ours):
+        sm = importlib.import_module("gaustar_scene.sugar_model")
+        cm = importlib.import_module("gaustar_scene.cameras")
+        import open3d
+        gs_cams = []
+        for i, c in enumerate(cams):
+            w2c = c.viewmatrix.reshape(4, 4).T.astype(np.float64)
+            gs_cams.append(cm.GSCamera(colmap_id=i, R=w2c[:3, :3].T.copy(), T=w2c[:3, 3].copy(), FoVx=2.0 * np.arctan(c.tanfovx), FoVy=2.0 * np.arctan(c.tanfovy),
+                                       image=None, gt_alpha_mask=None, image_name=f"img_{i:04d}", uid=i, image_height=c.image_height, image_width=c.image_width))
+        nerf = types.SimpleNamespace(device=torch.device("cuda"), training_cameras=cm.CamerasWrapper(gs_cams))
+        torch.manual_seed(0)
+        model = sm.SuGaR(nerfmodel=nerf, points=None, colors=None, initialize=False, sh_levels=3, keep_track_of_knn=False,
+                         surface_mesh_to_bind=open3d.TriangleMeshLike(verts, faces, vcol), n_gaussians_per_surface_triangle=6,
+                         learn_surface_mesh_opacity=True, max_gaussian_scale=0.02, min_gaussian_scale=1e-5)
+        gen = torch.Generator("cuda").manual_seed(9)
+        with torch.no_grad():  # away from the initial state: anisotropic scales, arbitrary in-plane rotations, mixed opacities
+            model._scales.add_(0.4 * torch.randn(model._scales.shape, device="cuda", generator=gen))
+            model._quaternions.copy_(torch.randn(model._quaternions.shape, device="cuda", generator=gen))
+            model.all_densities.copy_(2.0 * torch.randn(model.all_densities.shape, device="cuda", generator=gen))
+        P = model.n_points
+        ws = [torch.randn(P, k, device="cuda", generator=gen) for k in (3, 3, 4, 1)]
+        leaves = (model._points, model._scales, model._quaternions, model.all_densities)
+
+        def functional(outs):
+            return sum((o * w).sum() for o, w in zip(outs, ws))
+
+        ref_out = (model.points, model.scaling, model.quaternions, model.strengths)
+        ref_grads = torch.autograd.grad(functional(ref_out), leaves)
+        mine_out = gsugar.fused_gaussian_params(model._points, model._surface_mesh_faces, model._scales, model._quaternions, model.all_densities,
+                                                model.surface_triangle_bary_coords, float(model.surface_mesh_thickness.item()),
+                                                model.min_gaussian_scale, model.max_gaussian_scale)
+        mine_grads = torch.autograd.grad(functional(mine_out), leaves)
+        for name, a, b in zip(("points", "scaling", "quaternions", "strengths"), mine_out, ref_out):
+            assert a.shape == b.shape, name
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (name, float((a - b).abs().max()))
+        for name, a, b in zip(("_points", "_scales", "_quaternions", "all_densities"), mine_grads, ref_grads):
+            assert a.shape == b.shape, name
+            assert Hh.rel_err(a.cpu(), b.cpu()) < 1e-4, (name, Hh.rel_err(a.cpu(), b.cpu()))
+
+        def render_and_grads():
+            for t in leaves:
+                t.grad = None
+            res = model.render_image_gaussian_rasterizer(camera_indices=1, bg_color=[0.0, 1.0, 0.0], sh_deg=2, compute_color_in_rasterizer=True,
+                                                         return_2d_radii=True)
+            depth_pts = (model.points @ torch.tensor([0.3, -0.2, 0.9], device="cuda"))[:, None].expand(-1, 3)
+            img2 = model.render_image_gaussian_rasterizer(camera_indices=1, bg_color=[10.0, 10.0, 10.0], sh_deg=0, point_colors=depth_pts)
+            (res["image"].square().sum() + img2.sum()).backward()
+            torch.cuda.synchronize()
+            return res["image"].detach().clone(), img2.detach().clone(), [t.grad.clone() for t in leaves]
+
+        img_a, dep_a, g_a = render_and_grads()
+        gsugar.patch_sugar(model)
+        assert isinstance(model, sm.SuGaR)
+        img_b, dep_b, g_b = render_and_grads()
+        gsugar.unpatch_sugar(model)
+        assert type(model) is sm.SuGaR
+        # quaternions / points agree to round-off, not bit for bit: images to 1e-4, radii-level identity is not claimed here
+        assert float((img_a - img_b).abs().max()) < 2e-3 and float((dep_a - dep_b).abs().max()) < 2e-2
+        assert float((img_a - img_b).abs().mean()) < 1e-5
+        for name, a, b in zip(("_points", "_scales", "_quaternions", "all_densities"), g_b, g_a):
+            assert Hh.rel_err(a.cpu(), b.cpu()) < 5e-3, (name, Hh.rel_err(a.cpu(), b.cpu()))
