@@ -13,5 +13,6 @@ from gaustar_b200.rasterizer import (  # noqa: F401
     rasterize_gaussians,
     set_geometry_cache,
     shared_geometry,
+    release_shared_geometry,
     _C,
 )

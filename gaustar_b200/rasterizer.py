@@ -60,7 +60,10 @@ def _fusable(t, needs):
 # and whose geometry inputs and camera are those of the previous full forward starts from that call's sorted record
 # stream (gstar_raster_reblend): only the blend runs again.  Two ways to say "same geometry":
 #   set_geometry_cache(True)   automatic and strict: the geometry tensors and camera matrices must be the very same
-#                              tensor objects' memory, unmodified (data_ptr + _version), same stream, same thread;
+#                              tensor objects' memory, unmodified (data_ptr + _version), same stream, same thread.
+#                              CAVEAT: writes through `param.data` (some optimizers / densifiers) do not bump `_version`;
+#                              code that edits parameters that way must use shared_geometry() blocks instead (or call
+#                              release_shared_geometry() after the edit);
 #   with shared_geometry():    asserted by the caller for the calls inside the block (GauSTAR's properties rebuild
 #                              `points`/`scaling`/`quaternions` and the camera matrices on every call, so the tensors are
 #                              equal in value but not in identity); shared_geometry(check=True) verifies the values
@@ -73,7 +76,7 @@ _tls = threading.local()
 
 class _GeomSource:
     """What a later re-blend needs of a full forward call."""
-    __slots__ = ("key", "tensors", "geom", "binning", "image", "radii", "num_rendered")
+    __slots__ = ("key", "tensors", "geom", "binning", "image", "radii", "num_rendered", "cam")
 
 
 def set_geometry_cache(enabled: bool) -> bool:
@@ -83,6 +86,12 @@ def set_geometry_cache(enabled: bool) -> bool:
     if not enabled:
         _tls.src = None
     return old
+
+
+def release_shared_geometry() -> None:
+    """Forget the remembered source call of this thread (its geometry / binning incl. hit log / image buffers -- up to a few GB --
+    are otherwise kept alive until the next full forward replaces them)."""
+    _tls.src = None
 
 
 @contextlib.contextmanager
@@ -105,7 +114,11 @@ def shared_geometry(check: bool = False):
 def _tkey(t):
     if not isinstance(t, torch.Tensor) or t.numel() == 0:
         return None
-    return (t.data_ptr(), t._version, tuple(t.shape), str(t.device), t.dtype)
+    try:
+        version = t._version
+    except RuntimeError:  # inference tensors do not track versions: never equal to a remembered key -> a full forward
+        version = object()
+    return (t.data_ptr(), version, tuple(t.shape), str(t.device), t.dtype)
 
 
 def _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs):
@@ -137,6 +150,10 @@ def _remember_source(means3D, opacities, scales, rotations, cov3Ds_precomp, rs, 
     src.tensors = _geom_inputs(means3D, opacities, scales, rotations, cov3Ds_precomp, rs)  # kept alive: their addresses cannot be recycled
     src.key = _geom_key(src.tensors, rs, means3D.device)
     src.geom, src.binning, src.image, src.radii, src.num_rendered = geom, binning, image, radii, num_rendered
+    # the camera AS IT WAS when this call ran (2 x 16 floats, copied on the call's stream): the device-side guard of a re-blend
+    # compares against this snapshot -- a matrix overwritten in place between the two calls compares equal to itself
+    src.cam = (rs.viewmatrix.detach().to(device=means3D.device, dtype=torch.float32).reshape(-1).clone(),
+               rs.projmatrix.detach().to(device=means3D.device, dtype=torch.float32).reshape(-1).clone())
     _tls.src = src
 
 
@@ -257,7 +274,7 @@ class _ReblendGaussians(torch.autograd.Function):
             # the camera of this call is compared with the source call's on the device: a mismatch (a shared_geometry() block
             # put around a loop over cameras) gives a NaN image, not a plausible picture of the wrong view
             num_rendered, color, binningBuffer, imgBuffer = _C.rasterize_gaussians_reblend(
-                rs.bg, colors_precomp, rs.image_height, rs.image_width, src.binning, src.image, rs.debug, src.tensors[5], src.tensors[6],
+                rs.bg, colors_precomp, rs.image_height, rs.image_width, src.binning, src.image, rs.debug, src.cam[0], src.cam[1],
                 rs.viewmatrix, rs.projmatrix)
         finally:
             if fwd_only:

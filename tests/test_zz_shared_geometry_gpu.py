@@ -373,3 +373,35 @@ def test_forward_passes_after_many_forwards_still_finds_its_source():
         for e, x in zip(extra, ref):
             assert torch.equal(e, x)
         del keep[4:]
+
+
+def test_camera_overwritten_in_place_between_the_calls_is_refused():
+    """The device-side camera guard compares the re-blend's camera with a SNAPSHOT of the source call's matrices: overwriting the
+    same tensors in place (a loop over cameras that reuses its buffers) must not pass as "same camera" -- the re-blend is refused
+    (NaN image), and after release_shared_geometry() / a new block the next call is a full forward again."""
+    import diff_gaussian_rasterization as dgr
+    from gaustar_b200 import scene
+    g = scene.surface_gaussians(8000, 3, seed=3)
+    cams = scene.dome_cameras(6, 256, 144)
+    kwA, kwB = Hh.to_torch_kwargs(Hh.scene_dict(g, cams[1])), Hh.to_torch_kwargs(Hh.scene_dict(g, cams[4]))
+    vm, pm = kwA["viewmatrix"].view(4, 4).clone(), kwA["projmatrix"].view(4, 4).clone()
+    P = kwA["means3D"].shape[0]
+    col = torch.rand(P, 3, device="cuda")
+    args = dict(means3D=kwA["means3D"], means2D=torch.zeros(P, 3, device="cuda"), opacities=kwA["opacities"], scales=kwA["scales"], rotations=kwA["rotations"])
+
+    def rs(bg, deg):
+        return dgr.GaussianRasterizationSettings(kwA["H"], kwA["W"], kwA["tan_fovx"], kwA["tan_fovy"], bg, 1.0, vm, pm, deg, kwA["campos"], False, False)
+
+    with torch.no_grad():
+        with dgr.shared_geometry():
+            a, _ = dgr.GaussianRasterizer(rs(kwA["bg"], 3))(shs=kwA["shs"], **args)
+            vm.copy_(kwB["viewmatrix"].view(4, 4)); pm.copy_(kwB["projmatrix"].view(4, 4))  # the SAME tensors now hold another camera
+            b, _ = dgr.GaussianRasterizer(rs(kwA["bg"], 0))(colors_precomp=col, **args)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a).all() and torch.isnan(b).all()
+        dgr.release_shared_geometry()
+        c, _ = dgr.GaussianRasterizer(rs(kwA["bg"], 0))(colors_precomp=col, **args)  # a full forward through the new camera
+        vm, pm = kwB["viewmatrix"].view(4, 4).clone(), kwB["projmatrix"].view(4, 4).clone()
+        ref, _ = dgr.GaussianRasterizer(rs(kwA["bg"], 0))(colors_precomp=col, **args)  # the same camera from other memory, outside any block
+        torch.cuda.synchronize()
+    assert torch.isfinite(c).all() and torch.equal(c, ref)
