@@ -15,6 +15,8 @@ Outputs:
   oracle/_ref/libref_dgr.so   reference kernels + oracle/ref_shim.cu (C ABI, exposes intermediates)
   oracle/_ref/ref_dgr_C.so    the reference's own pybind module under the name ``ref_dgr_C``
                               (stock binding: used by bench.py --impl reference)
+  oracle/_ref/libref_knn.so   the reference simple_knn (gaussian_splatting/submodules/simple-knn/simple_knn.cu, unmodified) +
+                              oracle/ref_knn_shim.cu: pins the simple_knn._C.distCUDA2 shim (tests/test_simple_knn.py)
   oracle/_ref/pyref/...       the reference's Python CALLERS of the operator, byte-compiled where they lie (sourceless
                               byte-code files *.refpyc, the Python analogue of the .so above; imported through oracle/pyref.py): ``gaussian_renderer.render()``, the
                               ``GaussianModel`` it renders, the stock operator wrapper, and the SuGaR model/camera modules.
@@ -33,6 +35,8 @@ DGR = os.path.join(REF_ROOT, "gaussian_splatting", "submodules", "diff-gaussian-
 OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libref_dgr.so")
 EXT = os.path.join(OUT, "ref_dgr_C.so")
+SKNN = os.path.join(REF_ROOT, "gaussian_splatting", "submodules", "simple-knn")
+KNN_LIB = os.path.join(OUT, "libref_knn.so")
 
 NVCC = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-include", "cstdint",
         "-I", os.path.join(DGR, "third_party", "glm"), "-I", os.path.join(DGR, "cuda_rasterizer"), "-I", DGR, "-w"]
@@ -121,6 +125,12 @@ def build(force=False, verbose=False, with_torch_ext=True):
         run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", EXT, o1, o2, *[_obj(s) for s in KERNEL_SRCS],
              "-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
              "-Xlinker", f"-rpath={tlib}"])
+    knn_shim = os.path.join(HERE, "ref_knn_shim.cu")
+    if os.path.isdir(SKNN) and (force or not os.path.exists(KNN_LIB) or os.path.getmtime(KNN_LIB) < os.path.getmtime(knn_shim)):
+        # -include cfloat: simple_knn.cu uses FLT_MAX without including <cfloat> (the reference's setup.py builds it on older toolchains
+        # where another header brought it in); no source edits
+        run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-include", "cfloat", "-w",
+             "-I", SKNN, "-shared", "-o", KNN_LIB, os.path.join(SKNN, "simple_knn.cu"), knn_shim])
     build_py(force, verbose)
     return True
 

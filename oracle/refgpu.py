@@ -104,3 +104,28 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
     if rc < 0:
         raise RuntimeError(f"reference backward failed ({rc})")
     return g
+
+
+# ---- the reference simple_knn (oracle/_ref/libref_knn.so; oracle/ref_knn_shim.cu) ----
+KNN_LIB_PATH = os.path.join(REF_DIR, "libref_knn.so")
+_knn_lib = None
+
+
+def knn_available() -> bool:
+    return os.path.exists(KNN_LIB_PATH)
+
+
+def knn_mean_dist2(points: torch.Tensor) -> torch.Tensor:
+    """SimpleKNN::knn of the unmodified reference on a [P,3] fp32 CUDA tensor: mean squared distance to the 3 nearest other points."""
+    global _knn_lib
+    if _knn_lib is None:
+        _knn_lib = C.CDLL(KNN_LIB_PATH)
+        _knn_lib.ref_knn_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _knn_lib.ref_knn_mean_dist2.restype = C.c_int
+    pts = points.detach().to(dtype=torch.float32).contiguous()
+    out = torch.zeros(pts.shape[0], device=pts.device)
+    torch.cuda.synchronize(pts.device)
+    rc = _knn_lib.ref_knn_mean_dist2(pts.shape[0], C.c_void_p(pts.data_ptr()), C.c_void_p(out.data_ptr()))
+    if rc != 0:
+        raise RuntimeError(f"reference simple_knn failed: CUDA error {rc}")
+    return out
