@@ -74,3 +74,97 @@ def test_two_rank_allreduce_equals_single_rank_sum(tmp_path):
         ref.accumulate(_view_grads(v, P, M))
     assert torch.allclose(got["flat"], ref.flat, rtol=1e-6, atol=1e-6)
     assert got["max"] == 2.0 and got["sum"] == 2.0
+
+
+# ---- TrainerSharding: the hooks that shard an UNMODIFIED one-view-per-iteration loop (refine.py:529-548, :794-795) ----
+def test_rank_view_sequences_are_disjoint_per_iteration_and_cover_the_permutation():
+    for n in (2, 5, 8, 21, 160):
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(n))
+        for world in (1, 2, 4, 8):
+            if world > n:
+                continue
+            seqs = [gdist.rank_view_sequence(perm, r, world) for r in range(world)]
+            assert all(s.numel() == n for s in seqs)
+            for i in range(n):
+                held = [int(s[i]) for s in seqs]
+                assert len(set(held)) == world  # different views on the ranks at every iteration
+                assert held == [int(perm[(i * world + r) % n]) for r in range(world)]  # = the next `world` entries of the shared order
+
+
+def _toy_targets(n):
+    g = torch.Generator().manual_seed(7)
+    return torch.randn(n, 5, 3, generator=g), torch.randn(n, 5, generator=g)
+
+
+def _toy_loss(a, b, c, cam, ta, tb):
+    loss = ((a - ta[cam]) ** 2).mean() + (torch.tanh(b) - tb[cam]).abs().mean()
+    if cam % 3 == 0:  # a parameter only some views touch: its grad is None otherwise (set_to_none=True)
+        loss = loss + (c * float(cam + 1)).sum()
+    return loss
+
+
+def _unmodified_loop(n_cams, passes, lr=0.05):
+    """Shaped like refine.py: randperm per pass, ONE view per iteration, optimizer.step(); zero_grad(set_to_none=True).  Knows nothing of ranks."""
+    ta, tb = _toy_targets(n_cams)
+    a, b, c = [torch.nn.Parameter(torch.zeros(s)) for s in ((5, 3), (5,), (2,))]
+    opt = torch.optim.Adam([{"params": [a], "lr": lr}, {"params": [b, c], "lr": lr / 2}])
+    seen = []
+    for _ in range(passes):
+        shuffled_idx = torch.randperm(n_cams)
+        for i in range(0, len(shuffled_idx), 1):
+            cmr_i = shuffled_idx[i:i + 1].item()
+            seen.append(cmr_i)
+            _toy_loss(a, b, c, cmr_i, ta, tb).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+    return [p.detach().clone() for p in (a, b, c)], seen
+
+
+def _sharded_worker(rank, world, port, n_cams, passes, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    gdist.init_from_env(backend="gloo")
+    torch.manual_seed(1234 + rank)  # the trainer's global RNG differs per rank; the shared permutation must not depend on it
+    with gdist.TrainerSharding(shared_seed=3) as ts:
+        params, seen = _unmodified_loop(n_cams, passes)
+    assert ts.steps == n_cams * passes and ts.bytes_last == 4 * (15 + 5 + 2 + 3)
+    assert torch.randperm.__module__ != gdist.__name__  # restored on exit
+    torch.save({"params": params, "seen": seen}, out + f".{rank}")
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_unmodified_loop_sharded_over_two_ranks_equals_one_rank_stepping_on_both_views(tmp_path):
+    n_cams, passes, world = 7, 2, 2
+    out = str(tmp_path / "r")
+    mp.spawn(_sharded_worker, args=(world, _free_port(), n_cams, passes, out), nprocs=world, join=True)
+    got = [torch.load(out + f".{r}") for r in range(world)]
+    # what one process does with the SAME shared order, two views per step, gradients summed
+    gen = torch.Generator().manual_seed(3)
+    ta, tb = _toy_targets(n_cams)
+    a, b, c = [torch.nn.Parameter(torch.zeros(s)) for s in ((5, 3), (5,), (2,))]
+    opt = torch.optim.Adam([{"params": [a], "lr": 0.05}, {"params": [b, c], "lr": 0.025}])
+    want_seen = [[], []]
+    for _ in range(passes):
+        perm = torch.randperm(n_cams, generator=gen)
+        for i in range(n_cams):
+            for r in range(world):
+                cam = int(perm[(i * world + r) % n_cams])
+                want_seen[r].append(cam)
+                _toy_loss(a, b, c, cam, ta, tb).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+    for r in range(world):
+        assert got[r]["seen"] == want_seen[r]
+        for p_got, p_want in zip(got[r]["params"], (a, b, c)):
+            assert torch.allclose(p_got, p_want.detach(), rtol=1e-5, atol=1e-6)
+    for p0, p1 in zip(got[0]["params"], got[1]["params"]):
+        assert torch.equal(p0, p1)  # the replicas never drift apart: identical reduced gradients, identical Adam state
+
+
+def test_trainer_sharding_is_a_no_op_in_a_single_process():
+    before = torch.randperm
+    with gdist.TrainerSharding() as ts:
+        assert torch.randperm is before and ts.world == 1
+        params, seen = _unmodified_loop(4, 1)
+    assert sorted(seen) == [0, 1, 2, 3] and ts.steps == 0
