@@ -14,5 +14,6 @@ from gaustar_b200.rasterizer import (  # noqa: F401
     set_geometry_cache,
     shared_geometry,
     release_shared_geometry,
+    set_deterministic_backward,
     _C,
 )

@@ -22,7 +22,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 EXPORTED = [
     "gstar_raster_forward", "gstar_raster_backward", "gstar_mark_visible", "gstar_last_error", "gstar_abi_version",
     "gstar_geom_bytes", "gstar_image_bytes", "gstar_binning_bytes", "gstar_geom_unpack", "gstar_image_views",
-    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_hit_log_state", "gstar_debug_header", "gstar_knn3_mean_dist2",
+    "gstar_binning_views", "gstar_profile_stage", "gstar_stage_name", "gstar_set_hit_log", "gstar_set_deterministic", "gstar_hit_log_state", "gstar_debug_header", "gstar_knn3_mean_dist2",
     "gstar_raster_reblend", "gstar_sugar_prologue_forward", "gstar_sugar_prologue_backward",
 ]
 STAGES = ["preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"]
@@ -107,6 +107,7 @@ def lib():
         L.gstar_binning_views.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.gstar_profile_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.gstar_set_hit_log.argtypes = [C.c_int]
+        L.gstar_set_deterministic.argtypes = [C.c_int]
         L.gstar_knn3_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_void_p, C.c_void_p]
         L.gstar_sugar_prologue_forward.argtypes = [C.POINTER(SugarArgs), C.c_void_p]
@@ -324,6 +325,12 @@ def profile_stage(stage: int, start: Optional[torch.cuda.Event] = None, stop: Op
 def set_hit_log(mode: int) -> int:
     """gstar_set_hit_log: 0 = walk-back backward only, 1 = hit log when it fits (default).  Returns the previous mode."""
     return int(lib().gstar_set_hit_log(int(mode)))
+
+
+def set_deterministic(on) -> bool:
+    """gstar_set_deterministic: fixed-order gradient sums in the blend backward (bit-identical gradients run to run; test mode,
+    needs the hit log).  Returns the previous mode; pass -1 to query."""
+    return bool(lib().gstar_set_deterministic(int(on)))
 
 
 def hit_log_state(fwd):

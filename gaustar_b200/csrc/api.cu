@@ -14,6 +14,7 @@
 // record stream), gstar_bwd_args.blend_only (K7 alone, moments left in the caller's scratch), and a forward that stays
 // on the device while its stream is being captured into a CUDA graph.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: the ranges below cost a pointer test when no tool is attached
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -84,18 +85,40 @@ struct Profile {
 };
 thread_local Profile t_prof;
 
+// NVTX ranges (SURVEY section 5 "tracing"): one per entry point ("gstar_raster_forward", ...) and, nested inside it, one per pipeline
+// stage ("gstar::blend_fwd", ...), so that a timeline groups the kernels of a view and `ncu --nvtx --nvtx-include "gstar::blend_fwd/"`
+// selects one stage's kernels.  The reference has no ranges.
+const char* const STAGE_RANGE[GSTAR_NUM_STAGES] = {"gstar::preprocess_fwd", "gstar::tile_scan", "gstar::emit", "gstar::tile_sort", "gstar::blend_fwd",
+                                                   "gstar::blend_bwd", "gstar::preprocess_bwd"};
+struct CallRange {
+    explicit CallRange(const char* name) { nvtxRangePushA(name); }
+    ~CallRange() { nvtxRangePop(); }
+};
+
 struct StageScope {
     int stage;
     cudaStream_t s;
     StageScope(int st, cudaStream_t stream) : stage(st), s(stream)
     {
+        nvtxRangePushA(STAGE_RANGE[stage]);
         if (t_prof.stage == stage && t_prof.start) cudaEventRecord(t_prof.start, s);
     }
     ~StageScope()
     {
         if (t_prof.stage == stage && t_prof.stop) cudaEventRecord(t_prof.stop, s);
+        nvtxRangePop();
     }
 };
+
+int g_deterministic = -1;  // -1: read GSTAR_DETERMINISTIC on first use
+bool deterministic_mode()
+{
+    if (g_deterministic < 0) {
+        const char* e = getenv("GSTAR_DETERMINISTIC");
+        g_deterministic = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_deterministic != 0;
+}
 
 int get_ctx(DevCtx** out, bool capturing = false)
 {
@@ -192,6 +215,13 @@ int gstar_set_hit_log(int mode)
     return old;
 }
 
+int gstar_set_deterministic(int on)
+{
+    const int old = deterministic_mode() ? 1 : 0;
+    if (on == 0 || on == 1) g_deterministic = on;
+    return old;
+}
+
 const char* gstar_stage_name(int stage)
 {
     static const char* names[GSTAR_NUM_STAGES] = {"preprocess_fwd", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "preprocess_bwd"};
@@ -212,6 +242,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
                          void* binning_user, gstar_alloc_fn image_alloc, void* image_user, void* stream_)
 {
     using namespace gstar;
+    CallRange call_range("gstar_raster_forward");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!a || !geom_alloc || !binning_alloc || !image_alloc) return fail(GSTAR_ERR_INVALID, "null argument");
     if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(GSTAR_ERR_INVALID, "bad sizes");
@@ -475,6 +506,7 @@ int gstar_raster_reblend(const gstar_reblend_args* a, gstar_alloc_fn binning_all
 int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
 {
     using namespace gstar;
+    CallRange call_range("gstar_raster_backward");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!a) return fail(GSTAR_ERR_INVALID, "null argument");
     if (a->P == 0) return 0;
@@ -499,7 +531,24 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
         bl.dL_dpix = a->dL_dpix; bl.gacc = a->blend_grad_scratch;
         bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = nullptr;
-        {
+        if (deterministic_mode()) {
+            // test mode: one row of moments per record, then a fixed-order sum per Gaussian (k_det_reduce); needs the hit log
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            CU_OK(cudaStreamIsCapturing(stream, &cs));
+            if (cs != cudaStreamCaptureStatusNone)
+                return fail(GSTAR_ERR_INVALID, "the deterministic backward allocates scratch: not available while capturing a CUDA graph");
+            float* rows = nullptr;
+            const size_t bytes = (size_t)a->R * GSTAR_GACC * sizeof(float);
+            CU_OK(cudaMallocAsync((void**)&rows, bytes, stream));
+            CU_OK(cudaMemsetAsync(rows, 0, bytes, stream));
+            bl.det_partial = rows; bl.aux = (const GAux*)(geom + geom_aux_offset(a->P)); bl.P = a->P;
+            {
+                StageScope sc(GSTAR_STAGE_BLEND_BWD, stream);
+                launch_blend_bwd_gather(bl, stream);
+                launch_det_reduce(bl, stream);
+            }
+            CU_OK(cudaFreeAsync(rows, stream));
+        } else {
             // exactly one of the two does the work, decided on the device by the forward's log_overflow flag
             StageScope sc(GSTAR_STAGE_BLEND_BWD, stream);
             launch_blend_bwd_gather(bl, stream);

@@ -1147,10 +1147,15 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
             any = true;
         }
         if (any) {
-            float* dst = p.gacc + (size_t)__float_as_uint(q2.y) * GSTAR_GACC;
-            red_add_v4(dst, m0, m1, m2, m3);
-            red_add_v4(dst + 4, m4, m5, m6, m7);
-            atomicAdd(dst + 8, m8);
+            if (p.det_partial) {  // deterministic test mode: this record's own row, summed per Gaussian by k_det_reduce
+                float4* row = reinterpret_cast<float4*>(p.det_partial + (size_t)(rs + i) * GSTAR_GACC);
+                row[0] = make_float4(m0, m1, m2, m3); row[1] = make_float4(m4, m5, m6, m7); row[2] = make_float4(m8, 0.f, 0.f, 0.f);
+            } else {
+                float* dst = p.gacc + (size_t)__float_as_uint(q2.y) * GSTAR_GACC;
+                red_add_v4(dst, m0, m1, m2, m3);
+                red_add_v4(dst + 4, m4, m5, m6, m7);
+                atomicAdd(dst + 8, m8);
+            }
         }
     }
     return;
@@ -1219,12 +1224,68 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
         }
         const unsigned grp = (anyb >> ((tid & 31) & ~(L - 1))) & ((1u << L) - 1u);
         if (grp != 0u && q == 0) {
-            float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
-            red_add_v4(dst, m[0], m[1], m[2], m[3]);
-            red_add_v4(dst + 4, m[4], m[5], m[6], m[7]);
-            atomicAdd(dst + 8, m[8]);
+            if (p.det_partial) {
+                float4* row = reinterpret_cast<float4*>(p.det_partial + (size_t)(rs + i) * GSTAR_GACC);
+                row[0] = make_float4(m[0], m[1], m[2], m[3]); row[1] = make_float4(m[4], m[5], m[6], m[7]); row[2] = make_float4(m[8], 0.f, 0.f, 0.f);
+            } else {
+                float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
+                red_add_v4(dst, m[0], m[1], m[2], m[3]);
+                red_add_v4(dst + 4, m[4], m[5], m[6], m[7]);
+                atomicAdd(dst + 8, m[8]);
+            }
         }
     }
+}
+
+// ---- deterministic test mode: per-Gaussian sum of the per-record rows in a FIXED order ----------------------------------------
+// The only run-to-run freedom of the backward is the order in which the records of one Gaussian (one per tile of its rect) reach
+// its gacc row through fp32 reductions (the reference has the same freedom per (Gaussian, pixel): backward.cu:523-554).  With
+// gstar_set_deterministic(1) k_blend_bwd_gather leaves every record's moments in its own row and one thread per Gaussian adds the
+// rows up tile by tile in row-major order of its rect.  The record of Gaussian g in a tile is found by binary search: the tile's
+// list is sorted by (depth bits, id), both known per Gaussian.  A view without a usable hit log has no rows: its moments become
+// NaN (never a silently non-deterministic gradient).  Test mode: R x 48 bytes of scratch and a search per (Gaussian, tile).
+__global__ void __launch_bounds__(256) k_det_reduce(BlendParams p)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.P || p.hdr->overflow) return;
+    const uint4 a = *reinterpret_cast<const uint4*>(p.aux + g);  // depth, rect_min, rect_max, radius
+    if ((int)a.w <= 0) return;
+    float* dst = p.gacc + (size_t)g * GSTAR_GACC;
+    if (p.hdr->log_overflow) {
+        const float nan = __int_as_float(0x7fc00000);
+        for (int c = 0; c < 9; c++) dst[c] = nan;
+        return;
+    }
+    const uint64_t key = ((uint64_t)a.x << 32) | (uint32_t)g;
+    const int x0 = (int)(a.y & 0xffffu), y0 = (int)(a.y >> 16), x1 = (int)(a.z & 0xffffu), y1 = (int)(a.z >> 16);
+    float acc[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) acc[c] = 0.f;
+    for (int ty = y0; ty < y1; ty++)
+        for (int tx = x0; tx < x1; tx++) {
+            const int tile = ty * p.gx + tx;
+            const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
+            uint32_t lo = rs, hi = re;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                const uint32_t gm = __float_as_uint(reinterpret_cast<const float4*>(p.packed + (size_t)mid * RS)[2].y);
+                const uint64_t km = ((uint64_t)__float_as_uint(p.aux[gm].depth) << 32) | gm;
+                if (km < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= re) continue;
+            if (__float_as_uint(reinterpret_cast<const float4*>(p.packed + (size_t)lo * RS)[2].y) != (uint32_t)g) continue;
+            const float4* row = reinterpret_cast<const float4*>(p.det_partial + (size_t)lo * GSTAR_GACC);
+            const float4 r0 = row[0], r1 = row[1], r2 = row[2];
+            acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
+            acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w; acc[8] += r2.x;
+        }
+#pragma unroll
+    for (int c = 0; c < 9; c++) dst[c] += acc[c];  // += : a scratch pre-loaded by an earlier pass over this geometry is added to (blend_only)
+}
+
+void launch_det_reduce(const BlendParams& p, cudaStream_t s)
+{
+    if (p.P > 0) k_det_reduce<<<(p.P + 255) / 256, 256, 0, s>>>(p);
 }
 
 // ---- shared-geometry re-blend: a second pass over the SAME Gaussians and camera with other per-Gaussian

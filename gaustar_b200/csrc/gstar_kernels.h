@@ -96,6 +96,11 @@ struct BlendParams {
     // backward
     const float* dL_dpix;
     float* gacc;
+    // deterministic test mode (gstar_set_deterministic): [R][12] one row of raw moments per record, written with plain stores by
+    // k_blend_bwd_gather instead of its reductions into gacc; launch_det_reduce then sums every Gaussian's rows in a fixed order
+    float* det_partial = nullptr;
+    const GAux* aux = nullptr;
+    int P = 0;
 };
 
 void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s);
@@ -114,6 +119,7 @@ int  blend_setup();
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s);
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s);         // walk-back path (no hit log)
 void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s);  // instance-parallel path over the hit log
+void launch_det_reduce(const BlendParams& p, cudaStream_t s);        // deterministic mode: gacc[g] += sum of g's rows of det_partial, tile by tile
 // re-blend (shared geometry): copy the packed stream with the colour fields replaced by colors[gid] and rebuild the sorted
 // value list from the records' ids; optionally switch the new header's hit log off
 // the cameras of the source call and of the re-blend (device pointers to 16 floats each; src_view == NULL: not checked)

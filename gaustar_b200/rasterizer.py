@@ -42,6 +42,26 @@ def set_grad_accumulation_fusion(enabled: bool) -> bool:
     return old
 
 
+_DET = {"explicit": False, "current": False}
+
+
+def set_deterministic_backward(enabled: bool) -> bool:
+    """Fixed-order gradient sums in the blend backward: gradients BIT-IDENTICAL from run to run (include/gstar_raster.h,
+    gstar_set_deterministic; the reference sums with fp32 atomics in scheduling order, backward.cu:523-554, and has no such mode).
+    Also taken whenever ``torch.use_deterministic_algorithms(True)`` is in force.  A test mode: roughly twice the blend-backward
+    time, R x 48 bytes of scratch per backward, needs the hit log (default).  Returns the previous explicit setting."""
+    old, _DET["explicit"] = _DET["explicit"], bool(enabled)
+    return old
+
+
+def _sync_deterministic():
+    want = _DET["explicit"] or torch.are_deterministic_algorithms_enabled()
+    if want != _DET["current"]:
+        from . import capi  # same libgstar_raster.so as _C links: one process-wide switch
+        capi.set_deterministic(want)
+        _DET["current"] = want
+
+
 def _fusable(t, needs):
     """t: an input of the autograd function.  Empty (absent) inputs are trivially fine."""
     if t.numel() == 0:
@@ -230,6 +250,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out_color, _):
+        _sync_deterministic()
         rs = ctx.raster_settings
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
         args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix,
@@ -288,6 +309,7 @@ class _ReblendGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out_color, _):
+        _sync_deterministic()
         rs = ctx.raster_settings
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
         out = _C.rasterize_gaussians_backward(rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
@@ -341,6 +363,7 @@ class _RasterizePasses(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii, *grad_extras):
+        _sync_deterministic()
         rs = ctx.raster_settings
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, *bufs = ctx.saved_tensors
         P = means3D.shape[0]

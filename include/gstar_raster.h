@@ -225,6 +225,15 @@ GSTAR_API int gstar_binning_views(char* binning_buffer, char* image_buffer, uint
  * (default 8192).  gstar_set_hit_log(0|1) overrides the environment (returns the previous mode; other values only
  * query).  gstar_hit_log_state() is a synchronous test helper reading one forward call's header. */
 GSTAR_API int gstar_set_hit_log(int mode);
+/* ---- deterministic backward (test mode) ----
+ * The reference's backward is not reproducible run to run: every (Gaussian, pixel) pair adds into the Gaussian's gradients with
+ * fp32 atomics in whatever order the hardware schedules them (backward.cu:523-554), and so does this library's blend backward per
+ * (Gaussian, tile).  gstar_set_deterministic(1) -- or GSTAR_DETERMINISTIC=1 in the environment -- makes gstar_raster_backward
+ * leave one row of moments per record in a scratch of R x 48 bytes (cudaMallocAsync on the call's stream) and add every
+ * Gaussian's rows up in a fixed order: all gradients are then BIT-IDENTICAL from run to run (the forward always is), at roughly
+ * twice the blend-backward time.  Needs the forward's hit log (a view whose log did not fit gets NaN gradients, not silently
+ * unordered ones) and cannot be captured into a CUDA graph.  Returns the previous mode; other values only query. */
+GSTAR_API int gstar_set_deterministic(int on);
 /* Raw copy of one forward call's device header (24 32-bit words; private layout, gstar_common.cuh) -- diagnostics. */
 GSTAR_API int gstar_debug_header(char* image_buffer, uint32_t* words24);
 GSTAR_API int gstar_hit_log_state(char* image_buffer, uint64_t* slots_needed, uint64_t* slots_capacity, int* in_use);

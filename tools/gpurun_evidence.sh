@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_refine.py > gpurun_out/r2aw_sharded_refine.log 2>&1; echo "rc=$?" >> gpurun_out/r2aw_sharded_refine.log; tail -25 gpurun_out/r2aw_sharded_refine.log | cut -c1-400
+timeout 1500 python -m pytest tests/test_zz_deterministic_gpu.py -m gpu -q -x > gpurun_out/r2ax_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2ax_pytest.log; tail -40 gpurun_out/r2ax_pytest.log | cut -c1-220
