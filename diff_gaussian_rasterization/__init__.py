@@ -15,5 +15,6 @@ from gaustar_b200.rasterizer import (  # noqa: F401
     shared_geometry,
     release_shared_geometry,
     set_deterministic_backward,
+    set_pass_fusion,
     _C,
 )

@@ -37,6 +37,7 @@ class FwdArgs(C.Structure):
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("cam_pos", C.c_void_p),
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int),
         ("out_color", C.c_void_p), ("radii", C.c_void_p), ("debug", C.c_int), ("forward_only", C.c_int),
+        ("colors2", C.c_void_p), ("background2", C.c_void_p), ("out_color2", C.c_void_p),
     ]
 
 
@@ -54,6 +55,7 @@ class BwdArgs(C.Structure):
         ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p), ("blend_grad_scratch", C.c_void_p), ("debug", C.c_int), ("accumulate_param_grads", C.c_int),
         ("blend_only", C.c_int),
+        ("dL_dpix2", C.c_void_p), ("background2", C.c_void_p), ("colors2", C.c_void_p),
     ]
 
 
@@ -157,9 +159,11 @@ def _resizable(dev):
 
 def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, W, H, shs=None, colors_precomp=None,
             scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, prefiltered=False, debug=False,
-            forward_only=False):
+            forward_only=False, colors2=None, bg2=None):
     """gstar_raster_forward.  Returns dict(num_rendered, out_color, radii, geom, binning, image).
-    forward_only: no backward will follow (the forward then skips the hit log)."""
+    forward_only: no backward will follow (the forward then skips the hit log).
+    colors2 [P,3], bg2 [3]: a second feature pass blended in the same kernel (gstar_fwd_args::colors2); the dict then also holds
+    out_color2 (what a call with colors_precomp=colors2, bg=bg2 renders, bit for bit)."""
     L = lib()
     dev = means3D.device
     assert dev.type == "cuda", "gaustar_b200 has no CPU path"
@@ -172,12 +176,22 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
     (geom, geom_cb), (binning, binning_cb), (image, image_cb) = _resizable(dev), _resizable(dev), _resizable(dev)
     a = FwdArgs(P, sh_degree, M, _ptr(bgc), W, H, _ptr(m3), _ptr(sh), _ptr(col), _ptr(op), _ptr(sc), scale_modifier, _ptr(rot), _ptr(cov),
                 _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, int(prefiltered), _ptr(out_color), _ptr(radii), int(debug), int(forward_only))
+    out_color2 = None
+    if colors2 is not None:
+        keep += [_f32(colors2, dev), _f32(bg2, dev)]
+        out_color2 = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+        a.colors2, a.background2, a.out_color2 = _ptr(keep[-2]), _ptr(keep[-1]), _ptr(out_color2)
     with torch.cuda.device(dev):
         R = _check(L.gstar_raster_forward(C.byref(a), geom_cb, None, binning_cb, None, image_cb, None, _stream(dev)))
     if P == 0:
         out_color.zero_()
-    return dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom[0], binning=binning[0], image=image[0], viewmatrix=vm, projmatrix=pm,
-                _keep=keep)
+        if out_color2 is not None:
+            out_color2.zero_()
+    out = dict(num_rendered=R, out_color=out_color, radii=radii, geom=geom[0], binning=binning[0], image=image[0], viewmatrix=vm, projmatrix=pm,
+               _keep=keep)
+    if out_color2 is not None:
+        out["out_color2"] = out_color2
+    return out
 
 
 def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False, viewmatrix=None, projmatrix=None):
@@ -205,14 +219,16 @@ def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False, view
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,
              scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None, lean=False,
-             scratch=None):
+             scratch=None, dL_dout_color2=None, colors2=None, bg2=None):
     """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts).
     scratch: optional [P,12] moment buffer pre-loaded by blend_moments() calls of other passes over the same geometry (the
     per-Gaussian stage then serves all of them at once); default: a fresh zero-filled one.
     lean: do not materialise the intermediates dL_dconic and -- for inputs that were not given -- dL_dcolors / dL_dcov3D
     (NULL in the C ABI; the dict then holds empty tensors for them).
     accumulate_into: optional dict with dL_dmeans3D/dL_dscales/dL_drotations/dL_dopacity/dL_dsh tensors; the
-    parameter gradients are then ADDED to them inside the kernel (accumulate_param_grads=1)."""
+    parameter gradients are then ADDED to them inside the kernel (accumulate_param_grads=1).
+    dL_dout_color2, colors2, bg2: backward of a two-pass forward (forward(colors2=..., bg2=...)); the dict then also holds
+    dL_dcolors2 [P,3] (floats 9..11 of the moment scratch)."""
     L = lib()
     dev = means3D.device
     keep = [_f32(x, dev) for x in (means3D, viewmatrix, projmatrix, campos, bg, shs, colors_precomp, scales, rotations, cov3D_precomp, dL_dout_color)]
@@ -242,8 +258,13 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
                 _ptr(fwd["image"]), _ptr(dpix), _ptr(g["dL_dmeans2D"]), _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolors"]),
                 _ptr(g["dL_dmeans3D"]), _ptr(g["dL_dcov3D"]), _ptr(g["dL_dsh"]), _ptr(g["dL_dscales"]), _ptr(g["dL_drotations"]),
                 _ptr(scratch), int(debug), int(accumulate_into is not None))
+    if dL_dout_color2 is not None:
+        keep += [_f32(dL_dout_color2, dev), _f32(bg2, dev), _f32(colors2, dev)]
+        a.dL_dpix2, a.background2, a.colors2 = _ptr(keep[-3]), _ptr(keep[-2]), _ptr(keep[-1])
     with torch.cuda.device(dev):
         _check(L.gstar_raster_backward(C.byref(a), _stream(dev)))
+    if dL_dout_color2 is not None:
+        g["dL_dcolors2"] = scratch[:, 9:12].clone()
     g["_keep"] = keep + [scratch]
     return g
 

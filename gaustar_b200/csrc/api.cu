@@ -165,16 +165,18 @@ ImgLayout img_layout(int W, int H)
     return L;
 }
 struct BinLayout {
-    size_t packed, point_list, entries, log, total;
+    size_t packed, point_list, entries, log, pixstate2, total;
 };
-BinLayout bin_layout(size_t cap, size_t log_slots)
+// row_bytes: 16, or 32 for a two-pass forward, which also keeps the second pass's final colour per pixel (npix2 pixels) behind the log
+BinLayout bin_layout(size_t cap, size_t log_slots, size_t row_bytes = sizeof(GHit), size_t npix2 = 0)
 {
     BinLayout L;
     L.packed = 0;  // first, so that backward needs no capacity to find it (the other offsets travel in the header)
     L.point_list = align_up(cap * GSTAR_REC_SMEM, 128);
     L.entries = align_up(L.point_list + cap * 4, 128);
     L.log = align_up(L.entries + cap * 8, 128);
-    L.total = align_up(L.log + log_slots * sizeof(GHit), 128);
+    L.pixstate2 = align_up(L.log + log_slots * row_bytes, 128);
+    L.total = align_up(L.pixstate2 + npix2 * 16, 128);
     return L;
 }
 
@@ -251,6 +253,11 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     if (!a->cov3D_precomp && (!a->scales || !a->rotations))
         return fail(GSTAR_ERR_INVALID, "provide scales+rotations or cov3D_precomp");
     if (a->width > 32767 || a->height > 32767) return fail(GSTAR_ERR_INVALID, "image larger than 32767 pixels");
+    const bool dual = a->colors2 != nullptr;
+    if (dual != (a->background2 != nullptr) || dual != (a->out_color2 != nullptr))
+        return fail(GSTAR_ERR_INVALID, "two-pass forward: colors2, background2 and out_color2 go together");
+    if (dual && !a->forward_only && !hit_log_enabled())
+        return fail(GSTAR_ERR_NOLOG, "two-pass forward: the hit log is switched off (gstar_set_hit_log / GSTAR_HIT_LOG); re-blend the second pass instead");
     // CUDA-graph capture: while `stream` is being captured the forward stays entirely on the device -- no
     // event wait, no read of the instance count.  The binning buffer then has the size the earlier un-captured calls of
     // this thread provisioned, the return value is that capacity (an upper bound of num_rendered, good for the matching
@@ -260,6 +267,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     CU_OK(cudaStreamIsCapturing(stream, &cap_status));
     const bool capturing = cap_status != cudaStreamCaptureStatusNone;
     if (capturing && a->debug) return fail(GSTAR_ERR_INVALID, "debug mode synchronizes the device: not available while capturing a CUDA graph");
+    if (capturing && dual) return fail(GSTAR_ERR_INVALID, "a two-pass forward reads the hit-log need back on the host: not available while capturing a CUDA graph");
     DevCtx* ctx;
     int rc = get_ctx(&ctx, capturing);
     if (rc < 0) return rc;
@@ -312,6 +320,11 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
     bl.dL_dpix = nullptr; bl.gacc = nullptr; bl.tile_lanes = bp.tile_lanes;
     bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = capturing ? nullptr : ctx->host_counts_dev;
+    bl.colors2 = a->colors2; bl.bg2 = a->background2; bl.out_color2 = a->out_color2;
+    const size_t row_bytes = dual ? 2 * sizeof(GHit) : sizeof(GHit);
+    hit_log_enabled();  // (reads the environment on first use: g_hit_log_max_slots)
+    const double max_slots = g_hit_log_max_slots * (double)sizeof(GHit) / (double)row_bytes;
+    const size_t npix2 = dual ? (size_t)W * H : 0;
 
     // Hit-log provision: the slots the previous view needed (published by its blend_fwd; a hint, it may lag) with the
     // same grow-at-once / shrink-slowly / quantised policy as the instance count.  A view whose log does not fit simply
@@ -320,8 +333,8 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     if (use_log) {
         const double need = (double)(((unsigned long long)ctx->host_counts[5] << 32) | ctx->host_counts[4]);
         if (need > 0.0) {
-            const double want = need * 1.25 > g_hit_log_max_slots ? 0.0 : std::ceil((need * 1.25 + 65536.0) / LOG_QUANTUM) * LOG_QUANTUM;
-            if (!ctx->log_have || want > ctx->log_estimate || (want == 0.0 && need > g_hit_log_max_slots)) {
+            const double want = need * 1.25 > max_slots ? 0.0 : std::ceil((need * 1.25 + 65536.0) / LOG_QUANTUM) * LOG_QUANTUM;
+            if (!ctx->log_have || want > ctx->log_estimate || (want == 0.0 && need > max_slots)) {
                 ctx->log_estimate = want;
                 ctx->log_small_streak = 0;
             } else if (want * 2.0 < ctx->log_estimate) {
@@ -339,20 +352,28 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     size_t cap = ctx->have_estimate ? (size_t)ctx->estimate : 0;
     uint32_t R = 0;
     size_t used_cap = 0, used_log_slots = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    // A two-pass forward that a backward will follow MUST end with a hit log (there is no walk-back kernel over two passes): it
+    // waits for the sort's slot count and, if the provision was too small, grows it and goes round once more.
+    const bool need_log = dual && use_log;
+    double log_force = 0.0;  // slots the next attempt must provide
+    for (int attempt = 0; attempt < 3; attempt++) {
         char* bin = nullptr;
         if (cap > 0) {
             if (cap > 0xfffffff0ull) return fail(GSTAR_ERR_INVALID, "more than 2^32 instances");
         }
         size_t log_slots = 0;
         if (use_log && cap > 0) {
-            const double guess = ctx->log_have ? ctx->log_estimate : std::ceil((double)cap * 24.0 / LOG_QUANTUM) * LOG_QUANTUM;
-            log_slots = (guess <= g_hit_log_max_slots && guess < 4.0e9) ? (size_t)guess : 0;
+            double guess = ctx->log_have ? ctx->log_estimate : std::ceil((double)cap * 24.0 / LOG_QUANTUM) * LOG_QUANTUM;
+            if (log_force > guess) guess = log_force;
+            log_slots = (guess <= max_slots && guess < 4.0e9) ? (size_t)guess : 0;
+            if (need_log && log_slots == 0)
+                return fail(GSTAR_ERR_NOLOG, "two-pass forward: this view's hit log exceeds GSTAR_HIT_LOG_MAX_MB; re-blend the second pass instead");
         }
-        const BinLayout BL = bin_layout(cap, log_slots);
+        const BinLayout BL = bin_layout(cap, log_slots, row_bytes, npix2);
         used_cap = cap; used_log_slots = log_slots;
         bp.capacity = (uint32_t)cap;
         bp.log_capacity = log_slots; bp.off_point_list = BL.point_list; bp.off_log = BL.log;
+        bp.off_pixstate2 = dual ? BL.pixstate2 : 0; bp.log_row_bytes = (uint32_t)row_bytes;
         if (cap > 0) {
             bin = binning_alloc(binning_user, BL.total + 128);
             if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
@@ -377,6 +398,10 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             {
                 StageScope sc(GSTAR_STAGE_TILE_SORT, stream);
                 launch_tile_sort(bp, stream);
+                if (need_log) {  // the slots this view needs, to the host, before the blend starts
+                    launch_publish_log(hdr, ctx->host_counts_dev, stream);
+                    CU_OK(cudaEventRecord(ctx->scan_done, stream));
+                }
             }
             STAGE_CHECK("tile_sort");
             {
@@ -415,8 +440,21 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             }
             ctx->have_estimate = true;
         }
-        if (!overflow) break;
-        if (attempt == 1) return fail(GSTAR_ERR_INVALID, "instance count changed between attempts");
+        if (!overflow) {
+            if (need_log && cap > 0) {  // (the event waited for above was recorded behind the sort)
+                const double need = (double)(((unsigned long long)ctx->host_counts[5] << 32) | ctx->host_counts[4]);
+                if (need > (double)log_slots) {
+                    if (attempt == 2) return fail(GSTAR_ERR_INVALID, "hit-log need changed between attempts");
+                    log_force = std::ceil((need * 1.25 + 65536.0) / LOG_QUANTUM) * LOG_QUANTUM;
+                    if (log_force > max_slots) log_force = std::ceil(need / 65536.0) * 65536.0;  // without headroom, if that still fits under the cap
+                    ctx->log_estimate = std::max(ctx->log_estimate, log_force);
+                    ctx->log_have = true;
+                    continue;  // everything behind the scan no-op'd its log writes; binning + blend are re-enqueued with a log that fits
+                }
+            }
+            break;
+        }
+        if (attempt == 2) return fail(GSTAR_ERR_INVALID, "instance count changed between attempts");
         cap = (size_t)R;  // exact size; tile_scan reruns to reset cursors and the device flag
     }
     if (R == 0) {
@@ -426,7 +464,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
             char* bin = binning_alloc(binning_user, gstar_binning_bytes(1));
             if (!bin) return fail(GSTAR_ERR_ALLOC, "binning buffer callback returned NULL");
             bl.packed = (unsigned char*)aligned128(bin);
-            bp.capacity = 1; bp.log_capacity = 0; bp.off_point_list = 0; bp.off_log = 0;
+            bp.capacity = 1; bp.log_capacity = 0; bp.off_point_list = 0; bp.off_log = 0; bp.off_pixstate2 = 0;
             launch_tile_scan(bp, stream);
             launch_blend_fwd(bl, stream);
             STAGE_CHECK("blend_fwd(empty)");
@@ -531,6 +569,10 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         bl.out_color = nullptr; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
         bl.dL_dpix = a->dL_dpix; bl.gacc = a->blend_grad_scratch;
         bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = nullptr;
+        const bool dual = a->dL_dpix2 != nullptr;
+        if (dual != (a->background2 != nullptr) || dual != (a->colors2 != nullptr))
+            return fail(GSTAR_ERR_INVALID, "two-pass backward: dL_dpix2, background2 and colors2 go together");
+        bl.dL_dpix2 = a->dL_dpix2; bl.bg2 = a->background2; bl.colors2 = a->colors2;
         if (deterministic_mode()) {
             // test mode: one row of moments per record, then a fixed-order sum per Gaussian (k_det_reduce); needs the hit log
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -550,9 +592,10 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
             CU_OK(cudaFreeAsync(rows, stream));
         } else {
             // exactly one of the two does the work, decided on the device by the forward's log_overflow flag
+            // (a two-pass forward always ends with a log: there is no walk-back kernel over two passes)
             StageScope sc(GSTAR_STAGE_BLEND_BWD, stream);
             launch_blend_bwd_gather(bl, stream);
-            launch_blend_bwd(bl, stream);
+            if (!dual) launch_blend_bwd(bl, stream);
         }
         STAGE_CHECK("blend_bwd");
     }
@@ -653,7 +696,7 @@ int gstar_binning_views(char* binning_buffer, char* image_buffer, uint32_t** poi
 int gstar_debug_header(char* image_buffer, uint32_t* words24)
 {
     if (!image_buffer || !words24) return fail(GSTAR_ERR_INVALID, "null argument");
-    cudaError_t e = cudaMemcpy(words24, aligned128(image_buffer), sizeof(GHeader), cudaMemcpyDeviceToHost);  // test helper: synchronous
+    cudaError_t e = cudaMemcpy(words24, aligned128(image_buffer), 24 * sizeof(uint32_t), cudaMemcpyDeviceToHost);  // test helper: synchronous
     if (e != cudaSuccess) return fail(GSTAR_ERR_CUDA, cudaGetErrorString(e));
     return 0;
 }

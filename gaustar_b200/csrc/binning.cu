@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(BinParams p)
         p.hdr->log_capacity = p.log_capacity;
         p.hdr->off_point_list = p.off_point_list;
         p.hdr->off_log = p.off_log;
+        p.hdr->off_pixstate2 = p.off_pixstate2;
+        p.hdr->log_row_bytes = p.log_row_bytes;
+        p.hdr->pad1 = 0u;
         if (p.host_counts) {  // zero-copy write of R to pinned host memory: no separate D2H memcpy
             p.host_counts[1] = ovf;
             p.host_counts[2] = s_max;
@@ -737,6 +740,15 @@ int tile_sort_setup()
 
 void launch_tile_scan(const BinParams& p, cudaStream_t s) { k_tile_scan<<<1, SCAN_THREADS, 0, s>>>(p); }
 void launch_emit(const BinParams& p, cudaStream_t s) { k_emit<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
+__global__ void k_publish_log(const GHeader* hdr, volatile uint32_t* host_counts)
+{
+    const unsigned long long need = hdr->log_cursor;
+    host_counts[4] = (uint32_t)need;
+    host_counts[5] = (uint32_t)(need >> 32);
+    __threadfence_system();
+}
+void launch_publish_log(const GHeader* hdr, volatile uint32_t* host_counts, cudaStream_t s) { k_publish_log<<<1, 1, 0, s>>>(hdr, host_counts); }
+
 void launch_tile_sort(const BinParams& p, cudaStream_t s)
 {
     const int sms = g_num_sms > 0 ? g_num_sms : 148;  // persistent: one CTA per SM (148 on B200)

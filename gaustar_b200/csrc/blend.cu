@@ -130,6 +130,15 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
     __syncwarp();
 }
 
+// Two feature passes in one blend (NP == 2; SURVEY 8f-1 "generalise the blend to more channels"): the passes share alpha and T, so
+// the second one costs three more multiply-adds per blended pair instead of a whole K6 + K7.  Its per-Gaussian colours are
+// gathered from BlendParams::colors2 by id, its image goes to out_color2 with background bg2, a hit-log row grows from 16 to 32
+// bytes (C_rgb, T | C2_rgb, -), and the second pass's final colour per pixel lives behind the log (GHeader::off_pixstate2).
+__device__ __forceinline__ float4* pixstate2_of(const BlendParams& p)
+{
+    return reinterpret_cast<float4*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_pixstate2);
+}
+
 // ---- K6, fat tiles ---------------------------------------------------------------------------------------------------
 #ifndef GSTAR_FAT_SB
 #define GSTAR_FAT_SB 64
@@ -149,6 +158,7 @@ __device__ __forceinline__ void fat_fetch(unsigned char* stage, uint64_t* bar, c
 
 // (round 1's forward blend, kept for the tiles whose splats are fat: footprints that cover a large part of the tile make
 // lanes = pixels dense, and every warp streams the list on its own -- no CTA-wide phases)
+template <int NP>
 __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const int tile, unsigned char* s_dyn)
 {
     __shared__ __align__(8) uint64_t s_full[NCONS][FAT_NST];
@@ -160,11 +170,12 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
     // hit log (see k_blend_bwd_gather): every blended (instance, pixel) pair records the transmittance in front of it
     // and the colour accumulated up to and including it in the instance's slot for this pixel
     const bool log_on = p.hdr->log_overflow == 0u;
-    GHit* const hitlog = reinterpret_cast<GHit*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
+    char* const hitlog = reinterpret_cast<char*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);  // rows of NP x 16 bytes
     const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
     const int lx = g.px - tile_x0, ly = g.py - tile_y0;
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float D0 = 0.f, D1 = 0.f, D2 = 0.f;  // NP == 2: the second pass's colour (same alpha, same T)
     uint32_t last = 0;
     bool done = !g.inside;
 
@@ -210,6 +221,7 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                 int sl[4];
                 bool ok[4];
                 float al[4], cr_[4], cg[4], cbv[4];
+                float e0[4], e1[4], e2[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const bool have = left > 0;
@@ -232,6 +244,10 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                     const float4 q1 = *reinterpret_cast<const float4*>(rp + 16);  // C o r g
                     cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
                     cr_[u] = q1.z; cg[u] = q1.w;
+                    if constexpr (NP == 2) {
+                        const float* c2 = p.colors2 + (size_t)(*reinterpret_cast<const uint32_t*>(rp + 36)) * 3;  // gid
+                        e0[u] = __ldg(c2); e1[u] = __ldg(c2 + 1); e2[u] = __ldg(c2 + 2);
+                    }
                     float dx, dy;
                     const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
                     al[u] = fminf(0.99f, __fmul_rn(q1.y, expf(power)));
@@ -247,12 +263,23 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                             C0 = __fmaf_rn(T, __fmul_rn(al[u], cr_[u]), C0);
                             C1 = __fmaf_rn(T, __fmul_rn(al[u], cg[u]), C1);
                             C2 = __fmaf_rn(T, __fmul_rn(al[u], cbv[u]), C2);
+                            if constexpr (NP == 2) {
+                                D0 = __fmaf_rn(T, __fmul_rn(al[u], e0[u]), D0);
+                                D1 = __fmaf_rn(T, __fmul_rn(al[u], e1[u]), D1);
+                                D2 = __fmaf_rn(T, __fmul_rn(al[u], e2[u]), D2);
+                            }
                             if (log_on) {
                                 const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // foot gid b slot
                                 const Foot f = unpack_foot(tail.x);
-                                GHit h;
-                                h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
-                                hitlog[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
+                                if constexpr (NP == 1) {
+                                    GHit h;
+                                    h.T = T; h.c0 = C0; h.c1 = C1; h.c2 = C2;
+                                    reinterpret_cast<GHit*>(hitlog)[(size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))] = h;
+                                } else {
+                                    float4* row = reinterpret_cast<float4*>(hitlog + ((size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))) * (NP * sizeof(GHit)));
+                                    row[0] = make_float4(C0, C1, C2, T);
+                                    row[1] = make_float4(D0, D1, D2, 0.f);
+                                }
                             }
                             T = test_T;
                             last = (uint32_t)(b * FAT_SB + sl[u] + 1);
@@ -285,6 +312,12 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
         p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), T, C0);  // forward.cu:372
         p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), T, C1);
         p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), T, C2);
+        if constexpr (NP == 2) {
+            if (n > 0 && log_on) pixstate2_of(p)[pid] = make_float4(D0, D1, D2, 0.f);
+            p.out_color2[pid] = __fmaf_rn(__ldg(p.bg2 + 0), T, D0);
+            p.out_color2[HW + pid] = __fmaf_rn(__ldg(p.bg2 + 1), T, D1);
+            p.out_color2[2 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 2), T, D2);
+        }
     }
 }
 
@@ -292,9 +325,9 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
 // Persistent: a few CTAs per SM stride over the non-empty tiles and take the marked ones (none on a surface scene: the
 // kernel then costs a launch).
 constexpr int FAT_CTAS_PER_SM = 4;
-__global__ void __launch_bounds__(NCONS * 32, FAT_CTAS_PER_SM) k_blend_fwd_fat(BlendParams p)
+template <int NP>
+__device__ __forceinline__ void blend_fwd_fat_body(const BlendParams& p, unsigned char* s_dyn)
 {
-    extern __shared__ __align__(128) unsigned char s_dyn[];
     if (p.hdr->overflow || !p.tile_lanes) return;
     const uint32_t ntiles = p.hdr->cls_end[3];  // the non-empty tiles lead tile_order, longest list first
     __shared__ uint32_t s_item;
@@ -306,8 +339,18 @@ __global__ void __launch_bounds__(NCONS * 32, FAT_CTAS_PER_SM) k_blend_fwd_fat(B
         __syncthreads();  // (everyone has read the ticket before the next one overwrites it; also fences the previous tile's rings)
         if (i >= ntiles) break;
         const int tile = (int)p.tile_order[i];
-        if (p.tile_lanes[tile] & 0x80u) blend_fwd_fat_tile(p, tile, s_dyn);
+        if (p.tile_lanes[tile] & 0x80u) blend_fwd_fat_tile<NP>(p, tile, s_dyn);
     }
+}
+__global__ void __launch_bounds__(NCONS * 32, FAT_CTAS_PER_SM) k_blend_fwd_fat(BlendParams p)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    blend_fwd_fat_body<1>(p, s_dyn);
+}
+__global__ void __launch_bounds__(NCONS * 32, 3) k_blend_fwd_fat2(BlendParams p)  // two feature passes in one (BlendParams::colors2)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    blend_fwd_fat_body<2>(p, s_dyn);
 }
 
 // ---- K6: forward blend ---------------------------------------------------------------------------------------------
@@ -382,6 +425,16 @@ struct FwdSmem {
 #define GSTAR_FWD_SMEM_PAD 0
 #endif
 constexpr int FWD_DYN_SMEM = FWD_NST * FWD_NB * RS + (int)sizeof(FwdSmem) + GSTAR_FWD_SMEM_PAD;  // (the pad: occupancy experiments)
+struct FwdSmem2 {                    // NP == 2: what the second feature pass adds, behind FwdSmem
+    float4 hdr2[2][FWD_NB];          // the records' second colour (gathered by id in the group header)
+    float4 state2[256];              // per pixel (C3, C4, C5, -)
+};
+#ifndef GSTAR_FWD2_NST
+#define GSTAR_FWD2_NST 2
+#define GSTAR_FWD2_CTAS 3
+#endif
+constexpr int FWD2_NST = GSTAR_FWD2_NST;  // two stages leave room for three CTAs per SM (233 us at the headline; three stages and two CTAs: 286)
+constexpr int FWD_DYN_SMEM2 = FWD2_NST * FWD_NB * RS + (int)sizeof(FwdSmem) + GSTAR_FWD_SMEM_PAD + (int)sizeof(FwdSmem2);
 constexpr int FWD_UNITS = 4;  // P1 work units per group (strided chunks)
 #ifndef GSTAR_FWD_U
 #define GSTAR_FWD_U 3
@@ -417,7 +470,9 @@ __device__ __forceinline__ uint32_t warp_ticket(uint32_t* ctr, int lane)
 }
 
 // P1, group header: record starts, rank table, and what P2 needs of every record of the group
-__device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned char* stage, int buf, int grp, int cnt, uint32_t slot_b0, int lane)
+template <int NP>
+__device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned char* stage, int buf, int grp, int cnt, uint32_t slot_b0, int lane,
+                                                 FwdSmem2* sm2, const float* __restrict__ colors2)
 {
     FwdGroup& G = sm.grp[grp];
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -439,6 +494,10 @@ __device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned cha
         h.r = q1.z; h.g = q1.w; h.b = q2.z;
         h.pk = (uint32_t)f.w | (light ? 0u : 32u) | ((256u + (slot - slot_b0) - (uint32_t)(f.y0 * f.w + f.x0)) << 6);
         sm.hdr[buf][ri] = h;
+        if constexpr (NP == 2) {
+            const float* c2 = colors2 + (size_t)__float_as_uint(q2.y) * 3;  // by Gaussian id
+            sm2->hdr2[buf][ri] = make_float4(__ldg(c2), __ldg(c2 + 1), __ldg(c2 + 2), 0.f);
+        }
     }
     if (lane == 0) {
         G.total = total; G.light = light ? 1u : 0u; G.rel0 = rel0;
@@ -467,12 +526,15 @@ __device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned cha
     }
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(BlendParams p)
+template <int NP>
+__device__ __forceinline__ void blend_fwd_body(const BlendParams& p, unsigned char* const s_dyn)
 {
-    extern __shared__ __align__(128) unsigned char s_dyn[];  // (no pointer arithmetic through integers: it would demote every access to generic LD/ST/ATOM)
     if (p.hdr->overflow) return;
-    unsigned char* const s_stage = s_dyn;  // [FWD_NST][FWD_NB * RS]
-    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(s_dyn + FWD_NST * FWD_NB * RS);
+    constexpr int NST = NP == 2 ? FWD2_NST : FWD_NST;
+    unsigned char* const s_stage = s_dyn;  // [NST][FWD_NB * RS]
+    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(s_dyn + NST * FWD_NB * RS);
+    FwdSmem2* const sm2 = reinterpret_cast<FwdSmem2*>(s_dyn + NST * FWD_NB * RS + sizeof(FwdSmem) + GSTAR_FWD_SMEM_PAD);  // NP == 2 only
+    constexpr size_t ROW = NP * sizeof(GHit);  // bytes of a hit-log row
     const int tile = (int)p.tile_order[blockIdx.x];  // longest lists first
     const uint32_t rs = p.ranges[2 * tile], re = p.ranges[2 * tile + 1];
 #ifdef GSTAR_FWD_SKIP_TOP
@@ -487,7 +549,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
     // hit log (see k_blend_bwd_gather): every blended (instance, pixel) pair records the transmittance in front of it
     // and the colour accumulated up to and including it in the instance's slot for this pixel
     const bool log_on = p.hdr->log_overflow == 0u;
-    GHit* const hitlog = reinterpret_cast<GHit*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
+    char* const hitlog = reinterpret_cast<char*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_log);
     if (blockIdx.x == 0 && tid == 0 && p.host_counts) {  // size the next call's log: slots this view needed
         const unsigned long long need = p.hdr->log_cursor;
         p.host_counts[4] = (uint32_t)need;
@@ -497,6 +559,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
     // anyway, and with footprints that large the pixel-parallel formulation is the dense one
     if (n > 0 && p.tile_lanes && (p.tile_lanes[tile] & 0x80u)) return;  // k_blend_fwd_fat's
     float4 fin = make_float4(0.f, 0.f, 0.f, 1.0f);  // (C, T) of my pixel
+    float4 fin2 = make_float4(0.f, 0.f, 0.f, 0.f);  // NP == 2: the second pass's colour
     uint32_t fin_last = 0;
 #ifdef GSTAR_FWD_DEBUG_TIME
     unsigned long long t_start = 0;
@@ -510,6 +573,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         const int nb = (n + FWD_NB - 1) / FWD_NB;
         for (int i = tid; i < 2 * FWD_NG * 256; i += FWD_THREADS) (&sm.mask[0][0][0])[i] = 0u;
         sm.state[tid] = fin;
+        if constexpr (NP == 2) sm2->state2[tid] = fin2;
         sm.last[tid] = 0u;
         if (tid < 17) sm.magic[tid] = tid ? (4096u + (uint32_t)tid - 1u) / (uint32_t)tid : 0u;
         if (tid < 64) (&sm.hist[0][0])[tid] = 0u;
@@ -520,15 +584,15 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         }
         if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < FWD_NST; s++) mbar_init(&sm.full[s], 1);
+            for (int s = 0; s < NST; s++) mbar_init(&sm.full[s], 1);
             mbar_init(&sm.hbar[0], FWD_NG);
             mbar_init(&sm.hbar[1], FWD_NG);
             fence_mbar_init();
 #pragma unroll
-            for (int s = 0; s < FWD_NST; s++)
+            for (int s = 0; s < NST; s++)
                 if (s < nb) fwd_fetch(s_stage + s * FWD_NB * RS, &sm.full[s], tile_packed, s, n);
         }
-        int issued = min(nb, FWD_NST);  // batches whose copy has been issued (meaningful in thread 0)
+        int issued = min(nb, NST);  // batches whose copy has been issued (meaningful in thread 0)
         __syncthreads();
         // Warp roles: warp w takes entries [32 w, 32 w + 32) of a batch's P2 work list (longest chains first, so warp 0 mostly
         // runs the serial recurrences and draws little pair work); warps 4..7 build the group headers.  (Keeping the pair
@@ -540,12 +604,12 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         int b = 0;
 #pragma unroll 1
         for (; b < nb; b++) {
-            const int st = b % FWD_NST, buf = b & 1;
+            const int st = b % NST, buf = b & 1;
             const unsigned char* stage = s_stage + st * FWD_NB * RS;
 #ifdef GSTAR_FWD_DEBUG_TIME
             dbg_c = clock64();
 #endif
-            mbar_wait(&sm.full[st], (uint32_t)(b / FWD_NST) & 1u);
+            mbar_wait(&sm.full[st], (uint32_t)(b / NST) & 1u);
 #ifdef GSTAR_FWD_DEBUG_TIME
             dbg_t[5] += clock64() - dbg_c; dbg_c = clock64();
 #endif
@@ -555,7 +619,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
             {
                 const uint32_t ng = (uint32_t)(cnt + 31) >> 5;
                 if (hdr_grp >= 0) {
-                    if ((uint32_t)hdr_grp < ng) fwd_group_header(sm, stage, buf, hdr_grp, cnt, slot_b0, lane);
+                    if ((uint32_t)hdr_grp < ng) fwd_group_header<NP>(sm, stage, buf, hdr_grp, cnt, slot_b0, lane, sm2, p.colors2);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.hbar[buf]);
                 }
@@ -659,11 +723,11 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
             dbg_t[2] += clock64() - dbg_c; dbg_c = clock64();
 #endif
             if (alive == 0) break;  // every pixel of the tile is finished (forward.cu:309-311)
-            if (tid == 0 && b >= 1 && b - 1 + FWD_NST < nb) {
+            if (tid == 0 && b >= 1 && b - 1 + NST < nb) {
                 // every warp is past P2 of batch b-1: its stage can be refilled
                 fence_proxy_async();
-                fwd_fetch(s_stage + ((b - 1) % FWD_NST) * FWD_NB * RS, &sm.full[(b - 1) % FWD_NST], tile_packed, b - 1 + FWD_NST, n);
-                issued = b + FWD_NST;
+                fwd_fetch(s_stage + ((b - 1) % NST) * FWD_NB * RS, &sm.full[(b - 1) % NST], tile_packed, b - 1 + NST, n);
+                issued = b + NST;
             }
             // ---- work list of the pixels that have hits in this batch, longest chains first (counting sort): a P2 warp then
             // holds 32 chains of about the same length ----
@@ -726,13 +790,14 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                 }
                 const uint32_t lx = (uint32_t)pid & 15u, ly = (uint32_t)pid >> 4;
                 float4 S = sm.state[pid];  // C0 C1 C2 T
+                float4 S2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (NP == 2) S2 = sm2->state2[pid];
                 uint32_t lastr = 0xffffffffu, fin_flag = 0;
                 unsigned cw = w[0];
                 int ck = 0;
                 const float* const abuf = sm.alpha[buf];  // (indices carry a +256 bias: see FwdHdr::pk)
                 const FwdHdr* const hbuf = sm.hdr[buf];
-                GHit* const hl = hitlog + slot_b0 - 256;
-                char* const hlb = reinterpret_cast<char*>(hl);
+                char* const hlb = NP == 1 ? reinterpret_cast<char*>(reinterpret_cast<GHit*>(hitlog) + slot_b0 - 256) : hitlog + (size_t)slot_b0 * ROW - 256 * ROW;
                 int rounds = __reduce_max_sync(FULL, left);
 #ifdef GSTAR_FWD_DEBUG_TIME
                 dbg_rounds += rounds; dbg_hits += __reduce_add_sync(FULL, left); dbg_items += min(32, nact - p2_rank * 32);
@@ -749,7 +814,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
 #pragma unroll 1
                         for (; rk > 0; rk -= FWD_U) {
                             uint32_t r[FWD_U], idx[FWD_U];
-                            float4 h[FWD_U];
+                            float4 h[FWD_U], h2[FWD_U];
                             float al[FWD_U];
                             bool v[FWD_U];
 #pragma unroll
@@ -758,6 +823,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                                 r[u] = (uint32_t)(k * 32) + (v[u] ? (uint32_t)(__ffs(cw) - 1) : 0u);
                                 cw &= cw - 1u;
                                 h[u] = *reinterpret_cast<const float4*>(&hbuf[r[u]]);
+                                if constexpr (NP == 2) h2[u] = sm2->hdr2[buf][r[u]];
                             }
 #pragma unroll
                             for (int u = 0; u < FWD_U; u++) {
@@ -776,7 +842,22 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                                 const float c1 = __fmaf_rn(S.w, __fmul_rn(al[u], h[u].y), S.y);
                                 const float c2 = __fmaf_rn(S.w, __fmul_rn(al[u], h[u].z), S.z);
                                 S.x = upd ? c0 : S.x; S.y = upd ? c1 : S.y; S.z = upd ? c2 : S.z;
-                                if (upd && log_on) *reinterpret_cast<float4*>(hlb + (size_t)idx[u] * sizeof(GHit)) = S;  // (C_i, T_i): colour including the pair, transmittance in front of it
+                                if constexpr (NP == 2) {
+                                    const float c3 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].x), S2.x);
+                                    const float c4 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].y), S2.y);
+                                    const float c5 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].z), S2.z);
+                                    S2.x = upd ? c3 : S2.x; S2.y = upd ? c4 : S2.y; S2.z = upd ? c5 : S2.z;
+                                }
+                                // (C_i, T_i): colour including the pair, transmittance in front of it
+                                if constexpr (NP == 1) {
+                                    if (upd && log_on) *reinterpret_cast<float4*>(hlb + (size_t)idx[u] * sizeof(GHit)) = S;
+                                } else {
+                                    if (upd && log_on) {
+                                        float4* row = reinterpret_cast<float4*>(hlb + (size_t)idx[u] * ROW);
+                                        row[0] = S;
+                                        row[1] = S2;
+                                    }
+                                }
                                 S.w = upd ? test_T : S.w;
                                 lastr = upd ? r[u] : lastr;
                             }
@@ -824,7 +905,21 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
                                     S.x = __fmaf_rn(S.w, __fmul_rn(al, h.x), S.x);
                                     S.y = __fmaf_rn(S.w, __fmul_rn(al, h.y), S.y);
                                     S.z = __fmaf_rn(S.w, __fmul_rn(al, h.z), S.z);
-                                    if (log_on) *reinterpret_cast<float4*>(hl + idx) = S;
+                                    if constexpr (NP == 2) {
+                                        const float4 h2 = sm2->hdr2[buf][r];
+                                        S2.x = __fmaf_rn(S.w, __fmul_rn(al, h2.x), S2.x);
+                                        S2.y = __fmaf_rn(S.w, __fmul_rn(al, h2.y), S2.y);
+                                        S2.z = __fmaf_rn(S.w, __fmul_rn(al, h2.z), S2.z);
+                                    }
+                                    if constexpr (NP == 1) {
+                                        if (log_on) *reinterpret_cast<float4*>(reinterpret_cast<GHit*>(hlb) + idx) = S;
+                                    } else {
+                                        if (log_on) {
+                                            float4* row = reinterpret_cast<float4*>(hlb + (size_t)idx * ROW);
+                                            row[0] = S;
+                                            row[1] = S2;
+                                        }
+                                    }
                                     S.w = test_T;
                                     lastr = r;
                                 }
@@ -837,6 +932,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
 #endif
                 if (have) {
                     sm.state[pid] = S;
+                    if constexpr (NP == 2) sm2->state2[pid] = S2;
                     if (lastr != 0xffffffffu) sm.last[pid] = (uint32_t)(b * FWD_NB + 1) + lastr;
                     if (fin_flag) atomicOr(&sm.done[pid >> 5], 1u << (pid & 31));
                 }
@@ -844,9 +940,10 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         }
         // leaving early: the copies already issued must have landed before the CTA can retire
         if (b < nb && tid == 0)
-            for (int pb = b + 1; pb < issued; pb++) mbar_wait(&sm.full[pb % FWD_NST], (uint32_t)(pb / FWD_NST) & 1u);
+            for (int pb = b + 1; pb < issued; pb++) mbar_wait(&sm.full[pb % NST], (uint32_t)(pb / NST) & 1u);
         __syncthreads();
         fin = sm.state[tid];
+        if constexpr (NP == 2) fin2 = sm2->state2[tid];
         fin_last = sm.last[tid];
 #ifdef GSTAR_FWD_DEBUG_TIME
         if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 20 || blockIdx.x == 200 || blockIdx.x == 600 || blockIdx.x == 1000)) {
@@ -871,7 +968,23 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(Blen
         p.out_color[pid] = __fmaf_rn(__ldg(p.bg + 0), fin.w, fin.x);  // forward.cu:372
         p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), fin.w, fin.y);
         p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), fin.w, fin.z);
+        if constexpr (NP == 2) {
+            if (n > 0 && log_on) pixstate2_of(p)[pid] = fin2;
+            p.out_color2[pid] = __fmaf_rn(__ldg(p.bg2 + 0), fin.w, fin2.x);
+            p.out_color2[HW + pid] = __fmaf_rn(__ldg(p.bg2 + 1), fin.w, fin2.y);
+            p.out_color2[2 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 2), fin.w, fin2.z);
+        }
     }
+}
+__global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) k_blend_fwd(BlendParams p)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];  // (no pointer arithmetic through integers: it would demote every access to generic LD/ST/ATOM)
+    blend_fwd_body<1>(p, s_dyn);
+}
+__global__ void __launch_bounds__(FWD_THREADS, GSTAR_FWD2_CTAS) k_blend_fwd2(BlendParams p)  // two feature passes in one (BlendParams::colors2)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    blend_fwd_body<2>(p, s_dyn);
 }
 
 // keep = own half, send = other half; after the exchange every lane holds the pair-sum of its half
@@ -1060,9 +1173,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend_bwd(BlendParams p)
 // cross-lane reduction and no per-pixel atomics at all.  A pair was blended iff it lies in front of the pixel's last
 // contributor and passes the reference's power / alpha tests, which are re-evaluated here with the forward's arithmetic.
 constexpr int GATHER_THREADS = 256;
-__global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendParams p)
+// NP == 2: two feature passes blended in one (k_blend_fwd2).  The pair's alpha and T are shared, so dL/dalpha is the SUM of the
+// two passes' terms -- cdot and `behind` simply run over six channels -- and the three colour moments of the second pass go to
+// slots 9..11 of the Gaussian's gacc row (= that pass's dL_dcolors).
+template <int NP>
+__device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
 {
-    __shared__ float4 s_pix[GSTAR_TILE * GSTAR_TILE];    // dL_dpix rgb, (C_fin . dpx + T_final bg . dpx)
+    __shared__ float4 s_pix[GSTAR_TILE * GSTAR_TILE];    // dL_dpix rgb, (C_fin . dpx + T_final bg . dpx) summed over the passes
+    __shared__ float4 s_pix2[NP == 2 ? GSTAR_TILE * GSTAR_TILE : 1];  // dL_dpix of the second pass
     __shared__ uint32_t s_nc[GSTAR_TILE * GSTAR_TILE];  // n_contrib
     __shared__ uint32_t s_total;
     if (p.hdr->overflow || p.hdr->log_overflow) return;
@@ -1073,7 +1191,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
     const int tile_x0 = (tile % p.gx) * GSTAR_TILE, tile_y0 = (tile / p.gx) * GSTAR_TILE;
     {
         const int px = tile_x0 + (tid & 15), py = tile_y0 + (tid >> 4);
-        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), pv2 = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t nc = 0;
         if (px < p.W && py < p.H) {
             const size_t HW = (size_t)p.H * p.W, pid = (size_t)py * p.W + px;
@@ -1083,9 +1201,17 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
                 const float4 st = p.pixstate[pid];
                 const float bg_dot = __ldg(p.bg + 0) * d0 + __ldg(p.bg + 1) * d1 + __ldg(p.bg + 2) * d2;
                 pv = make_float4(d0, d1, d2, st.x * d0 + st.y * d1 + st.z * d2 + st.w * bg_dot);
+                if constexpr (NP == 2) {
+                    const float d3 = p.dL_dpix2[pid], d4 = p.dL_dpix2[HW + pid], d5 = p.dL_dpix2[2 * HW + pid];
+                    const float4 st2 = pixstate2_of(p)[pid];
+                    const float bg2_dot = __ldg(p.bg2 + 0) * d3 + __ldg(p.bg2 + 1) * d4 + __ldg(p.bg2 + 2) * d5;
+                    pv2 = make_float4(d3, d4, d5, 0.f);
+                    pv.w += st2.x * d3 + st2.y * d4 + st2.z * d5 + st.w * bg2_dot;
+                }
             }
         }
         s_pix[tid] = pv;
+        if constexpr (NP == 2) s_pix2[tid] = pv2;
         s_nc[tid] = nc;
         if (tid == 0) s_total = 0;
         __syncthreads();
@@ -1094,7 +1220,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
         __syncthreads();
     }
     const uint32_t total = s_total;  // instances behind every pixel's last contributor were never blended
-    const GHit* const hitlog = reinterpret_cast<const GHit*>(p.packed + p.hdr->off_log);
+    const GHit* const hitlog = reinterpret_cast<const GHit*>(p.packed + p.hdr->off_log);  // rows of NP GHit: (C_rgb, T)[, (C2_rgb, -)]
     const float4* const tile_packed = reinterpret_cast<const float4*>(p.packed + (size_t)rs * RS);
     const float tx0f = (float)tile_x0, ty0f = (float)tile_y0;
     // Lanes per instance, chosen per tile by the sort kernel from the mean footprint area and the list length: one for
@@ -1109,22 +1235,31 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
         if (f.w <= 0 || f.h <= 0) continue;
         const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
         const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
-        const GHit* hrow = hitlog + __float_as_uint(q2.w);
+        const GHit* hrow = hitlog + (size_t)__float_as_uint(q2.w) * NP;
         const int area = f.w * f.h;
         // The footprint's log slots are contiguous: pull all of its lines towards L2 now, for every lane at once, so
         // that the dependent loads in the pixel loop below find them there (the loop itself exposes one miss at a time).
-        for (int off = 0; off < area * (int)sizeof(GHit); off += 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
-        prefetch_l2(hrow + (area - 1));  // the row need not start on a line boundary
+        for (int off = 0; off < area * NP * (int)sizeof(GHit); off += 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
+        prefetch_l2(hrow + (area * NP - 1));  // the row need not start on a line boundary
         if (i + GATHER_THREADS < total) prefetch_l2(tile_packed + (size_t)(i + GATHER_THREADS) * 3);
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f;
+        float m9 = 0.f, m10 = 0.f, m11 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+        if constexpr (NP == 2) {
+            const float* c2 = p.colors2 + (size_t)__float_as_uint(q2.y) * 3;  // the record's second colour, by Gaussian id
+            e0 = __ldg(c2); e1 = __ldg(c2 + 1); e2 = __ldg(c2 + 2);
+        }
         bool any = false;
         int xx = 0, pl = f.y0 * GSTAR_TILE + f.x0;
-        GHit hn = hrow[0];  // the row of the next pixel is requested one step ahead of its use (the rows of a footprint are consecutive)
+        GHit hn = hrow[0], hn2 = hn;  // the row of the next pixel is requested one step ahead of its use (the rows of a footprint are consecutive)
+        if constexpr (NP == 2) hn2 = hrow[1];
 #pragma unroll 1
         for (int s = 0; s < area; s++) {
             const int cur_pl = pl;
-            const GHit hcur = hn;
-            if (s + 1 < area) hn = hrow[s + 1];
+            const GHit hcur = hn, hcur2 = hn2;
+            if (s + 1 < area) {
+                hn = hrow[(s + 1) * NP];
+                if constexpr (NP == 2) hn2 = hrow[(s + 1) * NP + 1];
+            }
             if (++xx == f.w) { xx = 0; pl += GSTAR_TILE - f.w + 1; } else pl++;
             if (i >= s_nc[cur_pl]) continue;  // behind this pixel's last contributor
             float dx, dy;
@@ -1136,8 +1271,14 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
             const GHit h = hcur;
             const float4 pv = s_pix[cur_pl];
             const float w = alpha * h.T;
-            const float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
-            const float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
+            float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
+            float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
+            if constexpr (NP == 2) {
+                const float4 pv2 = s_pix2[cur_pl];
+                cdot += e0 * pv2.x + e1 * pv2.y + e2 * pv2.z;
+                behind -= hcur2.c0 * pv2.x + hcur2.c1 * pv2.y + hcur2.c2 * pv2.z;
+                m9 = fmaf(w, pv2.x, m9); m10 = fmaf(w, pv2.y, m10); m11 = fmaf(w, pv2.z, m11);
+            }
             const float dL_dalpha = h.T * cdot - behind * __frcp_rn(1.0f - alpha);
             const float sG = (q1.y * dL_dalpha) * G;
             const float sx = sG * dx, sy = sG * dy;
@@ -1149,12 +1290,13 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
         if (any) {
             if (p.det_partial) {  // deterministic test mode: this record's own row, summed per Gaussian by k_det_reduce
                 float4* row = reinterpret_cast<float4*>(p.det_partial + (size_t)(rs + i) * GSTAR_GACC);
-                row[0] = make_float4(m0, m1, m2, m3); row[1] = make_float4(m4, m5, m6, m7); row[2] = make_float4(m8, 0.f, 0.f, 0.f);
+                row[0] = make_float4(m0, m1, m2, m3); row[1] = make_float4(m4, m5, m6, m7); row[2] = make_float4(m8, m9, m10, m11);
             } else {
                 float* dst = p.gacc + (size_t)__float_as_uint(q2.y) * GSTAR_GACC;
                 red_add_v4(dst, m0, m1, m2, m3);
                 red_add_v4(dst + 4, m4, m5, m6, m7);
-                atomicAdd(dst + 8, m8);
+                if constexpr (NP == 2) red_add_v4(dst + 8, m8, m9, m10, m11);
+                else atomicAdd(dst + 8, m8);
             }
         }
     }
@@ -1169,9 +1311,10 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
 #pragma unroll 1
     for (uint32_t r = 0; r < rounds; r++) {
         const uint32_t i = r * stride + ((uint32_t)tid >> lshift);
-        float m[9];
+        constexpr int NM = NP == 2 ? 12 : 9;  // moments per record
+        float m[NM];
 #pragma unroll
-        for (int c = 0; c < 9; c++) m[c] = 0.f;
+        for (int c = 0; c < NM; c++) m[c] = 0.f;
         bool any = false;
         uint32_t gid = 0;
         if (i < total) {
@@ -1181,17 +1324,28 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
             if (f.w > 0 && f.h > 0) {
                 const float4 q0 = ldg_nc_f4(tile_packed + (size_t)i * 3);      // x y A B
                 const float4 q1 = ldg_nc_f4(tile_packed + (size_t)i * 3 + 1);  // C o r g
-                const GHit* hrow = hitlog + __float_as_uint(q2.w);
+                const GHit* hrow = hitlog + (size_t)__float_as_uint(q2.w) * NP;
                 const int area = f.w * f.h;
-                for (int off = q * 128; off < area * (int)sizeof(GHit); off += L * 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
+                for (int off = q * 128; off < area * NP * (int)sizeof(GHit); off += L * 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
+                float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+                if constexpr (NP == 2) {
+                    const float* c2 = p.colors2 + (size_t)gid * 3;
+                    e0 = __ldg(c2); e1 = __ldg(c2 + 1); e2 = __ldg(c2 + 2);
+                }
                 int xx = q, yy = 0;
                 while (xx >= f.w) { xx -= f.w; yy++; }
-                GHit hn = {0.f, 0.f, 0.f, 0.f};
-                if (q < area) hn = hrow[q];  // the row of the lane's next pixel is requested one step ahead of its use
+                GHit hn = {0.f, 0.f, 0.f, 0.f}, hn2 = {0.f, 0.f, 0.f, 0.f};
+                if (q < area) {  // the row of the lane's next pixel is requested one step ahead of its use
+                    hn = hrow[q * NP];
+                    if constexpr (NP == 2) hn2 = hrow[q * NP + 1];
+                }
 #pragma unroll 1
                 for (int s = q; s < area; s += L) {
-                    const GHit h = hn;
-                    if (s + L < area) hn = hrow[s + L];
+                    const GHit h = hn, h2 = hn2;
+                    if (s + L < area) {
+                        hn = hrow[(s + L) * NP];
+                        if constexpr (NP == 2) hn2 = hrow[(s + L) * NP + 1];
+                    }
                     const int pl = (f.y0 + yy) * GSTAR_TILE + f.x0 + xx;
                     xx += L;
                     while (xx >= f.w) { xx -= f.w; yy++; }
@@ -1204,8 +1358,14 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
                     if (alpha < 1.0f / 255.0f) continue;
                     const float4 pv = s_pix[pl];
                     const float w = alpha * h.T;
-                    const float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
-                    const float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
+                    float cdot = q1.z * pv.x + q1.w * pv.y + q2.z * pv.z;
+                    float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
+                    if constexpr (NP == 2) {
+                        const float4 pv2 = s_pix2[pl];
+                        cdot += e0 * pv2.x + e1 * pv2.y + e2 * pv2.z;
+                        behind -= h2.c0 * pv2.x + h2.c1 * pv2.y + h2.c2 * pv2.z;
+                        m[9] = fmaf(w, pv2.x, m[9]); m[10] = fmaf(w, pv2.y, m[10]); m[11] = fmaf(w, pv2.z, m[11]);
+                    }
                     const float dL_dalpha = h.T * cdot - behind * __frcp_rn(1.0f - alpha);
                     const float sG = (q1.y * dL_dalpha) * G;
                     const float sx = sG * dx, sy = sG * dy;
@@ -1220,22 +1380,30 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendPar
         if (anyb == 0u) continue;
         for (int d = 1; d < L; d <<= 1) {
 #pragma unroll
-            for (int c = 0; c < 9; c++) m[c] += __shfl_xor_sync(FULL, m[c], d);
+            for (int c = 0; c < NM; c++) m[c] += __shfl_xor_sync(FULL, m[c], d);
         }
         const unsigned grp = (anyb >> ((tid & 31) & ~(L - 1))) & ((1u << L) - 1u);
         if (grp != 0u && q == 0) {
             if (p.det_partial) {
                 float4* row = reinterpret_cast<float4*>(p.det_partial + (size_t)(rs + i) * GSTAR_GACC);
-                row[0] = make_float4(m[0], m[1], m[2], m[3]); row[1] = make_float4(m[4], m[5], m[6], m[7]); row[2] = make_float4(m[8], 0.f, 0.f, 0.f);
+                row[0] = make_float4(m[0], m[1], m[2], m[3]); row[1] = make_float4(m[4], m[5], m[6], m[7]);
+                if constexpr (NP == 2) row[2] = make_float4(m[8], m[9], m[10], m[11]);
+                else row[2] = make_float4(m[8], 0.f, 0.f, 0.f);
             } else {
                 float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
                 red_add_v4(dst, m[0], m[1], m[2], m[3]);
                 red_add_v4(dst + 4, m[4], m[5], m[6], m[7]);
-                atomicAdd(dst + 8, m[8]);
+                if constexpr (NP == 2) red_add_v4(dst + 8, m[8], m[9], m[10], m[11]);
+                else atomicAdd(dst + 8, m[8]);
             }
         }
     }
 }
+__global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendParams p) { blend_bwd_gather_body<1>(p); }
+#ifndef GSTAR_GATHER2_CTAS
+#define GSTAR_GATHER2_CTAS 4
+#endif
+__global__ void __launch_bounds__(GATHER_THREADS, GSTAR_GATHER2_CTAS) k_blend_bwd_gather2(BlendParams p) { blend_bwd_gather_body<2>(p); }
 
 // ---- deterministic test mode: per-Gaussian sum of the per-record rows in a FIXED order ----------------------------------------
 // The only run-to-run freedom of the backward is the order in which the records of one Gaussian (one per tile of its rect) reach
@@ -1253,14 +1421,14 @@ __global__ void __launch_bounds__(256) k_det_reduce(BlendParams p)
     float* dst = p.gacc + (size_t)g * GSTAR_GACC;
     if (p.hdr->log_overflow) {
         const float nan = __int_as_float(0x7fc00000);
-        for (int c = 0; c < 9; c++) dst[c] = nan;
+        for (int c = 0; c < GSTAR_GACC; c++) dst[c] = nan;
         return;
     }
     const uint64_t key = ((uint64_t)a.x << 32) | (uint32_t)g;
     const int x0 = (int)(a.y & 0xffffu), y0 = (int)(a.y >> 16), x1 = (int)(a.z & 0xffffu), y1 = (int)(a.z >> 16);
-    float acc[9];
+    float acc[GSTAR_GACC];  // (slots 9..11: the second pass's colour moments, zero rows unless NP == 2)
 #pragma unroll
-    for (int c = 0; c < 9; c++) acc[c] = 0.f;
+    for (int c = 0; c < GSTAR_GACC; c++) acc[c] = 0.f;
     for (int ty = y0; ty < y1; ty++)
         for (int tx = x0; tx < x1; tx++) {
             const int tile = ty * p.gx + tx;
@@ -1277,10 +1445,11 @@ __global__ void __launch_bounds__(256) k_det_reduce(BlendParams p)
             const float4* row = reinterpret_cast<const float4*>(p.det_partial + (size_t)lo * GSTAR_GACC);
             const float4 r0 = row[0], r1 = row[1], r2 = row[2];
             acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
-            acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w; acc[8] += r2.x;
+            acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+            acc[8] += r2.x; acc[9] += r2.y; acc[10] += r2.z; acc[11] += r2.w;
         }
 #pragma unroll
-    for (int c = 0; c < 9; c++) dst[c] += acc[c];  // += : a scratch pre-loaded by an earlier pass over this geometry is added to (blend_only)
+    for (int c = 0; c < GSTAR_GACC; c++) dst[c] += acc[c];  // += : a scratch pre-loaded by an earlier pass over this geometry is added to (blend_only)
 }
 
 void launch_det_reduce(const BlendParams& p, cudaStream_t s)
@@ -1300,6 +1469,7 @@ __global__ void __launch_bounds__(256) k_recolor(const float4* __restrict__ src,
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && disable_log) hdr->log_overflow = 1u;  // inference re-blend: no hit log (the new binning buffer has none)
     if (i == 0) hdr->pad0[2] = 0u;  // k_blend_fwd_fat's tile cursor (the header is a copy of the source call's)
+    if (i == 0) { hdr->log_row_bytes = (uint32_t)sizeof(GHit); hdr->off_pixstate2 = 0ull; }  // the re-blend is a single pass whatever its source was
     if (i == 0 && cam.src_view) {
         // the caller's "same camera" claim, verified where it costs nothing: a re-blend through another camera must not
         // produce a plausible image of the wrong view.  overflow = 2 makes the blend kernels skip this call; k_poison
@@ -1351,15 +1521,28 @@ int blend_setup()
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_blend_fwd_fat, cudaFuncAttributeMaxDynamicSharedMemorySize, FAT_DYN_SMEM);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_blend_fwd_fat2, cudaFuncAttributeMaxDynamicSharedMemorySize, FAT_DYN_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_blend_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM2);
+    if (e != cudaSuccess) return (int)e;
     return (int)cudaFuncSetAttribute(k_blend_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_DYN_SMEM);
 }
 void launch_blend_fwd(const BlendParams& p, cudaStream_t s)
 {
-    k_blend_fwd<<<p.gx * p.gy, FWD_THREADS, FWD_DYN_SMEM, s>>>(p);
     const int sms = g_blend_sms > 0 ? g_blend_sms : 148;
+    if (p.colors2) {  // two feature passes in one
+        k_blend_fwd2<<<p.gx * p.gy, FWD_THREADS, FWD_DYN_SMEM2, s>>>(p);
+        k_blend_fwd_fat2<<<min(p.gx * p.gy, sms * 3), NCONS * 32, FAT_DYN_SMEM, s>>>(p);
+        return;
+    }
+    k_blend_fwd<<<p.gx * p.gy, FWD_THREADS, FWD_DYN_SMEM, s>>>(p);
     k_blend_fwd_fat<<<min(p.gx * p.gy, sms * FAT_CTAS_PER_SM), NCONS * 32, FAT_DYN_SMEM, s>>>(p);
 }
 void launch_blend_bwd(const BlendParams& p, cudaStream_t s) { k_blend_bwd<<<p.gx * p.gy, BLEND_THREADS, 0, s>>>(p); }
-void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s) { k_blend_bwd_gather<<<p.gx * p.gy, GATHER_THREADS, 0, s>>>(p); }
+void launch_blend_bwd_gather(const BlendParams& p, cudaStream_t s)
+{
+    if (p.dL_dpix2) k_blend_bwd_gather2<<<p.gx * p.gy, GATHER_THREADS, 0, s>>>(p);
+    else k_blend_bwd_gather<<<p.gx * p.gy, GATHER_THREADS, 0, s>>>(p);
+}
 
 }  // namespace gstar

@@ -56,8 +56,13 @@ struct GHeader {
     // kernel is persistent and pulls the tiles of a class through cls_cursor.
     uint32_t cls_end[4];
     uint32_t cls_cursor[4];
+    // two feature passes blended in one (gstar_fwd_args::colors2): bytes of a hit-log row (16, or 32 with the second pass's
+    // colour) and the byte offset, inside the binning buffer, of the second pass's per-pixel final colour (0: single pass)
+    unsigned long long off_pixstate2;
+    uint32_t log_row_bytes;
+    uint32_t pad1;
 };
-static_assert(sizeof(GHeader) == 96, "GHeader layout");
+static_assert(sizeof(GHeader) == 112, "GHeader layout");
 
 // One hit-log slot per (instance, pixel of its clipped footprint): what the forward blend knew when it blended the
 // pair -- transmittance in front of it and the colour accumulated up to and including it (blend.cu).

@@ -75,6 +75,8 @@ struct BinParams {
     unsigned long long log_capacity;    // hit-log slots available behind `entries` (0: log disabled)
     unsigned long long off_point_list;  // byte offsets inside the binning buffer, recorded in the header
     unsigned long long off_log;
+    unsigned long long off_pixstate2 = 0;  // (two feature passes in one: see GHeader)
+    uint32_t log_row_bytes = 16;
     volatile uint32_t* host_counts;  // mapped pinned host memory: [0]=R, [1]=overflow, [2]=max tile, [4..5]=hit-log slots needed
 };
 
@@ -101,6 +103,12 @@ struct BlendParams {
     float* det_partial = nullptr;
     const GAux* aux = nullptr;
     int P = 0;
+    // two feature passes in one blend (blend.cu, NP == 2): per-Gaussian colours [P,3] and background of the second pass, its image,
+    // and in the backward its upstream gradient; NULL: single pass
+    const float* colors2 = nullptr;
+    const float* bg2 = nullptr;
+    float* out_color2 = nullptr;
+    const float* dL_dpix2 = nullptr;
 };
 
 void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s);
@@ -112,6 +120,7 @@ void launch_geom_unpack(const GRec* recs, const GAux* aux, int P, float* depths,
 void launch_tile_scan(const BinParams& p, cudaStream_t s);
 void launch_emit(const BinParams& p, cudaStream_t s);
 void launch_tile_sort(const BinParams& p, cudaStream_t s);
+void launch_publish_log(const GHeader* hdr, volatile uint32_t* host_counts, cudaStream_t s);  // host_counts[4..5] = hit-log slots the view needs
 int  tile_sort_setup();  // one-time cudaFuncSetAttribute calls; returns cudaError_t
 int  preprocess_setup();
 int  blend_setup();

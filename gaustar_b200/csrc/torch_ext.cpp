@@ -50,12 +50,13 @@ void check(int rc)
 static thread_local bool t_forward_only = false;
 void set_forward_only(bool flag) { t_forward_only = flag; }
 
-std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> RasterizeGaussiansCUDA(
+// second: (colors2 [P,3], background2 [3]) of a second feature pass blended in the same kernel, or nullptr; out2 receives its image
+static std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> forward_impl(
     const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors, const torch::Tensor& opacity,
     const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
     const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
     const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const bool prefiltered,
-    const bool debug)
+    const bool debug, const std::pair<torch::Tensor, torch::Tensor>* second, torch::Tensor* out2)
 {
     if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
         AT_ERROR("means3D must have dimensions (num_points, 3)");
@@ -83,7 +84,7 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torc
         const torch::Tensor bg = prep(background, dev), m3 = prep(means3D, dev), col = prep(colors, dev), op = prep(opacity, dev),
                             sc = prep(scales, dev), rot = prep(rotations, dev), cov = prep(cov3D_precomp, dev), vm = prep(viewmatrix, dev),
                             pm = prep(projmatrix, dev), shc = prep(sh, dev), cp = prep(campos, dev);
-        gstar_fwd_args a;
+        gstar_fwd_args a = {};
         a.P = P; a.D = degree; a.M = M;
         a.background = fptr(bg); a.width = W; a.height = H;
         a.means3D = fptr(m3); a.shs = fptr(shc); a.colors_precomp = fptr(col); a.opacities = fptr(op);
@@ -92,12 +93,50 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torc
         a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered ? 1 : 0;
         a.out_color = out_color.data_ptr<float>(); a.radii = radii.data_ptr<int>(); a.debug = debug ? 1 : 0;
         a.forward_only = t_forward_only ? 1 : 0;
+        torch::Tensor col2, bg2;
+        if (second) {
+            TORCH_CHECK(second->first.is_cuda() && second->first.dim() == 2 && second->first.size(0) == P && second->first.size(1) == 3,
+                        "gaustar_b200: the second pass needs CUDA colours of shape (P, 3)");
+            col2 = prep(second->first, dev); bg2 = prep(second->second, dev);
+            *out2 = torch::empty({3, H, W}, float_opts);
+            a.colors2 = fptr(col2); a.background2 = fptr(bg2); a.out_color2 = out2->data_ptr<float>();
+        }
         rendered = gstar_raster_forward(&a, resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer, stream);
+        if (rendered == GSTAR_ERR_NOLOG) return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);  // the caller re-blends instead
         check(rendered);
     } else {
         out_color = torch::zeros({3, H, W}, float_opts);  // rasterize_points.cu:66
+        if (second) *out2 = torch::zeros({3, H, W}, float_opts);
     }
     return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);
+}
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> RasterizeGaussiansCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors, const torch::Tensor& opacity,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
+    const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const bool prefiltered,
+    const bool debug)
+{
+    return forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                        tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug, nullptr, nullptr);
+}
+
+// Two feature passes in one blend (gstar_fwd_args::colors2): the 19 arguments of rasterize_gaussians + the second pass's colours and
+// background.  Returns (num_rendered, out_color, out_color2, radii, geomBuffer, binningBuffer, imgBuffer); num_rendered ==
+// GSTAR_ERR_NOLOG (-5) means the view cannot have its hit log and nothing usable was rendered: re-blend the second pass instead.
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> RasterizeGaussiansDualCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors, const torch::Tensor& opacity,
+    const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
+    const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos, const bool prefiltered,
+    const bool debug, const torch::Tensor& colors2, const torch::Tensor& background2)
+{
+    const std::pair<torch::Tensor, torch::Tensor> second(colors2, background2);
+    torch::Tensor out2;
+    auto r = forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                          tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug, &second, &out2);
+    return std::make_tuple(std::get<0>(r), std::get<1>(r), out2, std::get<2>(r), std::get<3>(r), std::get<4>(r), std::get<5>(r));
 }
 
 // Shared-geometry re-blend (gstar_raster_reblend): second pass over the Gaussians and camera of an earlier
@@ -145,6 +184,9 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor> ReblendGaussiansCUD
 struct FusedTargets {
     torch::Tensor means3D, sh, opacity, scales, rotations;
 };
+struct SecondPass {  // backward of a two-pass forward: the second image's upstream gradient, background and colours
+    torch::Tensor dL_dout_color2, background2, colors2;
+};
 using BwdTuple = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
 static BwdTuple backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
                               const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
@@ -152,7 +194,7 @@ static BwdTuple backward_impl(const torch::Tensor& background, const torch::Tens
                               const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& sh,
                               const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
                               const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug, const FusedTargets* fused,
-                              const torch::Tensor* preloaded_scratch = nullptr);
+                              const torch::Tensor* preloaded_scratch = nullptr, const SecondPass* second = nullptr);
 
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
 RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
@@ -200,7 +242,7 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
               const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
               const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
               const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
-              const bool debug, const FusedTargets* fused, const torch::Tensor* preloaded_scratch)
+              const bool debug, const FusedTargets* fused, const torch::Tensor* preloaded_scratch, const SecondPass* second)
 {
     TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
     const torch::Device dev = means3D.device();
@@ -232,7 +274,7 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
                             pm = prep(projmatrix, dev), shc = prep(sh, dev), cp = prep(campos, dev), dpix = prep(dL_dout_color, dev);
         const torch::Tensor rad = radii.contiguous(), gb = geomBuffer.contiguous(), bb = binningBuffer.contiguous(),
                             ib = imageBuffer.contiguous();
-        gstar_bwd_args a;
+        gstar_bwd_args a = {};
         a.P = P; a.D = degree; a.M = M; a.R = R;
         a.background = fptr(bg); a.width = W; a.height = H;
         a.means3D = fptr(m3); a.shs = fptr(shc); a.colors_precomp = fptr(col); a.scales = fptr(sc); a.scale_modifier = scale_modifier;
@@ -252,6 +294,11 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
         a.debug = debug ? 1 : 0;
         a.accumulate_param_grads = fused ? 1 : 0;
         a.blend_only = 0;
+        torch::Tensor dpix2, bg2, col2;
+        if (second) {
+            dpix2 = prep(second->dL_dout_color2, dev); bg2 = prep(second->background2, dev); col2 = prep(second->colors2, dev);
+            a.dL_dpix2 = fptr(dpix2); a.background2 = fptr(bg2); a.colors2 = fptr(col2);
+        }
         check(gstar_raster_backward(&a, stream));
     }
     return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
@@ -308,6 +355,26 @@ BwdTuple RasterizeGaussiansBackwardPreloadedCUDA(const torch::Tensor& background
                          tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, nullptr, &scratch);
 }
 
+// Backward of rasterize_gaussians_dual: the 21 arguments of rasterize_gaussians_backward + the moment scratch (P x 12, zero or
+// pre-loaded by blend-only calls of further passes) + the second image's upstream gradient, background and colours.  Afterwards
+// columns 9..11 of the scratch are the second pass's dL_dcolors.
+BwdTuple RasterizeGaussiansBackwardDualCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                                            const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                                            const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                                            const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                                            const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree,
+                                            const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                                            const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug,
+                                            torch::Tensor scratch, const torch::Tensor& dL_dout_color2, const torch::Tensor& background2,
+                                            const torch::Tensor& colors2)
+{
+    check_scratch(scratch, means3D, means3D.size(0));
+    TORCH_CHECK(dL_dout_color2.is_cuda() && dL_dout_color2.sizes() == dL_dout_color.sizes(), "gaustar_b200: the two upstream gradients must have the same shape");
+    const SecondPass sp{dL_dout_color2, background2, colors2};
+    return backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                         tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, nullptr, &scratch, &sp);
+}
+
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix)
 {
     TORCH_CHECK(means3D.is_cuda(), "gaustar_b200: means3D must be a CUDA tensor (there is no CPU path)");
@@ -331,6 +398,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rasterize_gaussians_reblend", &ReblendGaussiansCUDA);
     m.def("rasterize_gaussians_blend_backward", &BlendBackwardCUDA);
     m.def("rasterize_gaussians_backward_preloaded", &RasterizeGaussiansBackwardPreloadedCUDA);
+    m.def("rasterize_gaussians_dual", &RasterizeGaussiansDualCUDA);
+    m.def("rasterize_gaussians_backward_dual", &RasterizeGaussiansBackwardDualCUDA);
     m.def("mark_visible", &markVisible);
     m.def("set_forward_only", &set_forward_only);
 }

@@ -320,13 +320,29 @@ class _ReblendGaussians(torch.autograd.Function):
                 None, None)
 
 
+_PASS_FUSION = True
+_ERR_NOLOG = -5  # GSTAR_ERR_NOLOG
+
+
+def set_pass_fusion(enabled: bool) -> bool:
+    """forward_passes(): blend the first extra pass in the SAME kernel as the main pass (on by default; returns the previous
+    setting).  Off: every extra pass is a re-blend of its own, as in round 1.  Results are the same either way -- images bit for
+    bit, gradients up to the order of fp32 sums."""
+    global _PASS_FUSION
+    old, _PASS_FUSION = _PASS_FUSION, bool(enabled)
+    return old
+
+
 class _RasterizePasses(torch.autograd.Function):
     """ONE autograd node for several feature passes over the same Gaussians and camera (config #5: RGB through SH, depth,
-    normals): a full forward for the first pass, a re-blend per extra (colours, background) pair, and a backward whose
-    per-Gaussian stage (cov2D / projection / SH / cov3D, backward.cu:144-396) runs ONCE for all passes -- the six
-    geometric blend moments of the passes add, the three colour moments of an extra pass are its dL_dcolors
-    (gstar_bwd_args.blend_only).  Inputs: the nine of _RasterizeGaussians, a tuple of backgrounds, then the extra colour
-    tensors.  Outputs: (color, radii, *extra_images).  dL_dmeans2D is the sum over the passes."""
+    normals): a forward that blends the main pass and the FIRST extra pass in one kernel (the passes share every pair's alpha
+    and transmittance: gstar_fwd_args::colors2), a re-blend per further (colours, background) pair, and a backward whose blend
+    stage serves the two fused passes at once and whose per-Gaussian stage (cov2D / projection / SH / cov3D,
+    backward.cu:144-396) runs ONCE for all passes -- the six geometric blend moments of the passes add, the three colour
+    moments of an extra pass are its dL_dcolors (gstar_bwd_args.blend_only).  A view whose hit log cannot be had (switched off,
+    or larger than GSTAR_HIT_LOG_MAX_MB) re-blends the first extra pass as well.  Inputs: the nine of _RasterizeGaussians, a
+    tuple of backgrounds, then the extra colour tensors.  Outputs: (color, radii, *extra_images).  dL_dmeans2D is the sum over
+    the passes."""
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, extra_bgs,
@@ -338,10 +354,18 @@ class _RasterizePasses(torch.autograd.Function):
         fwd_only = not any(ctx.needs_input_grad) and not rs.debug
         if fwd_only:
             _C.set_forward_only(True)
+        dual = False
         try:
-            num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
             extras, bufs = [], []
-            for bg_k, col_k in zip(extra_bgs, extra_colors):
+            if _PASS_FUSION and extra_colors and means3D.shape[0] > 0:
+                r = _C.rasterize_gaussians_dual(*args, extra_colors[0], extra_bgs[0])
+                dual = r[0] != _ERR_NOLOG
+                if dual:
+                    num_rendered, color, img2, radii, geomBuffer, binningBuffer, imgBuffer = r
+                    extras.append(img2)
+            if not dual:
+                num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+            for bg_k, col_k in list(zip(extra_bgs, extra_colors))[1 if dual else 0:]:
                 if means3D.shape[0] == 0:
                     extras.append(torch.zeros_like(color))
                     continue
@@ -356,8 +380,10 @@ class _RasterizePasses(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.extra_bgs = tuple(extra_bgs)
+        ctx.dual = dual
         ctx.set_materialize_grads(False)  # an extra image nobody differentiated costs no backward pass
-        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, *bufs)
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer,
+                              extra_colors[0] if dual else torch.empty(0, device=means3D.device), *bufs)
         ctx.mark_non_differentiable(radii)
         return (color, radii, *extras)
 
@@ -365,9 +391,10 @@ class _RasterizePasses(torch.autograd.Function):
     def backward(ctx, grad_out_color, _grad_radii, *grad_extras):
         _sync_deterministic()
         rs = ctx.raster_settings
-        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, *bufs = ctx.saved_tensors
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, colors2, *bufs = ctx.saved_tensors
         P = means3D.shape[0]
         n_extra = len(ctx.extra_bgs)
+        first = 1 if ctx.dual else 0  # extra passes from here on have binning / image buffers of their own
         extra_grads = [None] * n_extra
         if grad_out_color is None:
             grad_out_color = torch.zeros(3, rs.image_height, rs.image_width, dtype=torch.float32, device=means3D.device)
@@ -380,14 +407,20 @@ class _RasterizePasses(torch.autograd.Function):
         else:
             scratch = torch.zeros(P, 12, dtype=torch.float32, device=means3D.device)
             for k, g_k in enumerate(grad_extras):
-                if g_k is None:
+                if g_k is None or k < first:
                     continue
-                _C.rasterize_gaussians_blend_backward(ctx.extra_bgs[k], g_k, radii, geomBuffer, ctx.num_rendered, bufs[2 * k], bufs[2 * k + 1],
-                                                      scratch, rs.debug)
+                _C.rasterize_gaussians_blend_backward(ctx.extra_bgs[k], g_k, radii, geomBuffer, ctx.num_rendered, bufs[2 * (k - first)],
+                                                      bufs[2 * (k - first) + 1], scratch, rs.debug)
                 if ctx.needs_input_grad[10 + k]:
                     extra_grads[k] = scratch[:, 6:9].clone()
                 scratch[:, 6:9].zero_()  # the colour moments are per pass; the geometric ones (columns 0..5) add
-            out = _C.rasterize_gaussians_backward_preloaded(*args, scratch)
+            if ctx.dual:
+                g2 = grad_extras[0] if grad_extras[0] is not None else torch.zeros_like(grad_out_color)
+                out = _C.rasterize_gaussians_backward_dual(*args, scratch, g2, ctx.extra_bgs[0], colors2)
+                if ctx.needs_input_grad[10]:
+                    extra_grads[0] = scratch[:, 9:12].clone()  # the second pass's colour moments
+            else:
+                out = _C.rasterize_gaussians_backward_preloaded(*args, scratch)
         grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations = out
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
                 grad_cov3Ds_precomp, None, None, *extra_grads)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GSTAR_ABI_VERSION 4
+#define GSTAR_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define GSTAR_API __attribute__((visibility("default")))
@@ -47,6 +47,7 @@ extern "C" {
 #define GSTAR_ERR_CUDA     (-2) /* a CUDA call failed (debug mode: after a device synchronize) */
 #define GSTAR_ERR_ALLOC    (-3) /* a buffer callback returned NULL */
 #define GSTAR_ERR_NONRGB   (-4) /* "For non-RGB, provide precomputed Gaussian colors!" rasterizer_impl.cu:242-245 */
+#define GSTAR_ERR_NOLOG    (-5) /* a two-pass forward (colors2) that must serve a backward cannot get its hit log: use gstar_raster_reblend */
 
 /* Resizable-buffer callback: mirrors the three std::function<char*(size_t)> of rasterizer.h:32-34
  * (created by resizeFunctional(), DGR/rasterize_points.cu:27-33).  Must return a device pointer to
@@ -79,6 +80,17 @@ typedef struct gstar_fwd_args {
     int debug;                   /* !=0: synchronize + check after every stage (auxiliary.h:166-173) */
     int forward_only;            /* !=0: no backward will follow (inference): the forward skips the hit log; a backward on
                                   * these buffers is still correct (it takes the walk-back kernel) */
+    /* Two feature passes in ONE blend (no counterpart in the reference, whose NUM_CHANNELS is a compile-time 3: config.h:15;
+     * GauSTAR renders RGB and then depth from the same Gaussians and camera, refine.py:552-564 / :607-616).  With colors2 != NULL
+     * the call also renders what a second call with colors_precomp = colors2 and background = background2 would: the passes
+     * share every pair's alpha and transmittance, so the second image costs three multiply-adds per blended pair instead of a
+     * blend of its own -- bit-identical to that second call.  All three pointers or none.  Unless forward_only is set the call
+     * must end with a hit log (gstar_set_hit_log): it waits for the sort instead of the scan, grows the log and re-blends if
+     * the view needs more than was provisioned, and fails with GSTAR_ERR_NOLOG when the log is switched off or capped below
+     * the need -- the caller then renders the second pass with gstar_raster_reblend.  Not available while capturing. */
+    const float* colors2;        /* [P,3] or NULL */
+    const float* background2;    /* [3] */
+    float* out_color2;           /* [3,H,W] fully written */
 } gstar_fwd_args;
 
 /* Forward pass.  Returns num_rendered (sum of tiles touched), exactly like Rasterizer::forward.
@@ -143,6 +155,12 @@ typedef struct gstar_bwd_args {
      * dL_dcolor, zeroes them, and hands the same scratch -- now pre-loaded -- to the full backward of the last pass: the
      * per-Gaussian stage then runs ONCE for all passes.  (A scratch that is not zero on entry is simply added to.) */
     int blend_only;
+    /* Backward of a two-pass forward (gstar_fwd_args::colors2): the second image's upstream gradient [3,H,W], its background and
+     * its colours.  dL/dalpha of a pair sums both passes; the second pass's dL_dcolors (colour moments) are left in floats 9..11
+     * of every row of blend_grad_scratch, the first pass's go where they always do.  All three or none; must match the forward. */
+    const float* dL_dpix2;
+    const float* background2;
+    const float* colors2;
 } gstar_bwd_args;
 #define GSTAR_GRAD_SCRATCH_FLOATS 12
 

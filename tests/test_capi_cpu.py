@@ -28,7 +28,7 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_stage_names():
     L = capi.lib()
-    assert L.gstar_abi_version() == 4
+    assert L.gstar_abi_version() == 5
     assert [L.gstar_stage_name(i).decode() for i in range(len(capi.STAGES))] == capi.STAGES
     assert L.gstar_stage_name(99) == b""
 

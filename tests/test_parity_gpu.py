@@ -34,6 +34,13 @@ GRAD_TOL = 3e-4        # max-abs error / max |ref|, vs oracle and golden (hit-lo
 GRAD_TOL_WALK = 6e-4
 GRAD_RTOL_ELEM = 1e-3  # element-wise, on entries above GRAD_ELEM_FLOOR of the tensor's max
 GRAD_ELEM_FLOOR = 1e-2
+# dL_dcov3D / dL_dscales / dL_drotations come out of a chain with cancellation (backward.cu:278-341), and the oracle restates that
+# chain in the REFERENCE's fp32 operation order (only the blend sums are fp64), so on ill-conditioned entries the oracle is one valid
+# fp32 evaluation, not the true value.  Measured over 12 runs per arm (profiles/r2bb_elementwise_noise.txt): the reference's own
+# worst entry moves between 7e-4 and 2.2e-3 (rotations, close-up scene), 1.1e-2 .. 1.9e-2 (scales, big splats); this library's
+# between 1.7e-3 and 2.2e-3, resp. 2.5e-3 (deterministic mode) .. 1.6e-2.  A single reference run is therefore not a yardstick for
+# these three tensors: the check takes the reference's worst over three runs and never asks for less than this floor.
+GRAD_RTOL_ELEM_CHAIN = 5e-3
 # The reference sums its blend gradients with order-nondeterministic fp32 atomics, and dL_dcov3D / dL_dscales /
 # dL_drotations amplify that noise through 1/det^2 (backward.cu:201-212).  Where a test can run the reference itself
 # (test_against_live_reference, the full-size tests) the bound comes from the reference's measured spread; the fixed table
@@ -111,8 +118,9 @@ def default_grad_tol():
 
 def check_grads(mine, ref, tol=None, per_key=None, elementwise_against=None):
     """max-norm bound per tensor (per_key raises it for single tensors).  elementwise_against: the unmodified reference's gradients
-    for the same inputs -- our worst element-wise relative error (entries above 1 % of the max) vs `ref` must stay below
-    max(GRAD_RTOL_ELEM, 2 x the reference's own)."""
+    for the same inputs (one dict, or several runs of it) -- our worst element-wise relative error (entries above 1 % of the max) vs
+    `ref` must stay below max(GRAD_RTOL_ELEM, 2 x the reference's own worst over those runs); for the three tensors behind the
+    cov3D -> scale / rotation chain the floor is GRAD_RTOL_ELEM_CHAIN (see there)."""
     for k in Hh.GRAD_KEYS:
         r = np.asarray(ref[k])
         if r.size == 0:
@@ -122,8 +130,10 @@ def check_grads(mine, ref, tol=None, per_key=None, elementwise_against=None):
         bound = max(default_grad_tol() if tol is None else tol, (per_key or {}).get(k, 0.0))
         assert Hh.rel_err(m, r) < bound, (k, Hh.rel_err(m, r), bound)
         if elementwise_against is not None:
-            ours, theirs = elementwise_worst(m, r), elementwise_worst(np.asarray(elementwise_against[k]), r)
-            assert ours < max(GRAD_RTOL_ELEM, 2.0 * theirs), (k, "element-wise", ours, "reference:", theirs)
+            runs = elementwise_against if isinstance(elementwise_against, (list, tuple)) else [elementwise_against]
+            ours, theirs = elementwise_worst(m, r), max(elementwise_worst(np.asarray(e[k]), r) for e in runs)
+            floor = GRAD_RTOL_ELEM_CHAIN if k in ("dL_dcov3D", "dL_dscales", "dL_drotations") else GRAD_RTOL_ELEM
+            assert ours < max(floor, 2.0 * theirs), (k, "element-wise", ours, "reference:", theirs)
 
 
 def reference_spread(ref, dpix, bkw, runs=3):
@@ -187,9 +197,9 @@ def test_against_cpu_oracle(name):
     of.final_T = st["final_T"].copy()
     ob = O.backward(inp, of, dpix)
     ref_grads = None
-    if refgpu.available():  # the reference on the same inputs: the yardstick of the element-wise check
+    if refgpu.available():  # the reference on the same inputs, three runs (it is not reproducible): the yardstick of the element-wise check
         rf = refgpu.forward(**kw)
-        ref_grads = {k: v.cpu().numpy() for k, v in refgpu.backward(rf, torch.from_numpy(dpix).cuda(), **Hh.bwd_kwargs(kw)).items()}
+        ref_grads = [{k: v.cpu().numpy() for k, v in refgpu.backward(rf, torch.from_numpy(dpix).cuda(), **Hh.bwd_kwargs(kw)).items()} for _ in range(3)]
     check_grads(mine, ob.__dict__, elementwise_against=ref_grads)
 
 

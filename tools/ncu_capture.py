@@ -15,6 +15,8 @@ def sources_sha():
     h = hashlib.sha256()
     d = os.path.join(ROOT, "gaustar_b200", "csrc")
     for f in sorted(os.listdir(d)):
+        if not os.path.isfile(os.path.join(d, f)) or f.startswith("."):
+            continue
         h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
