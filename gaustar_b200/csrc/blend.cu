@@ -1399,7 +1399,10 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
         }
     }
 }
-__global__ void __launch_bounds__(GATHER_THREADS, 4) k_blend_bwd_gather(BlendParams p) { blend_bwd_gather_body<1>(p); }
+#ifndef GSTAR_GATHER_CTAS
+#define GSTAR_GATHER_CTAS 4
+#endif
+__global__ void __launch_bounds__(GATHER_THREADS, GSTAR_GATHER_CTAS) k_blend_bwd_gather(BlendParams p) { blend_bwd_gather_body<1>(p); }
 #ifndef GSTAR_GATHER2_CTAS
 #define GSTAR_GATHER2_CTAS 4
 #endif
