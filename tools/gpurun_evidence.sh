@@ -1,10 +1,4 @@
-# round-2 evidence run (edit per run; outputs to gpurun_out/, the keepers are copied to profiles/ afterwards)
 mkdir -p gpurun_out
-T=r2bj
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${T}_smoke.txt 2>&1; tail -2 gpurun_out/${T}_smoke.txt | cut -c1-200
-timeout 900 python bench.py --impl reference > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; tail -c 400 gpurun_out/${T}_bench_reference.json
-timeout 900 python bench.py > gpurun_out/${T}_bench_ours.json 2> gpurun_out/${T}_bench_ours.err; tail -c 1500 gpurun_out/${T}_bench_ours.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_bench_steps1.csv python bench.py --steps 1 --warmup 3 --quick > gpurun_out/${T}_launches.log 2>&1; tail -1 gpurun_out/${T}_launches.log | cut -c1-200
-timeout 900 ncu --set full --clock-control none --import-source on -c 40 -o gpurun_out/${T}_full python tools/profile_view.py --views 3 > gpurun_out/${T}_full.log 2>&1; tail -2 gpurun_out/${T}_full.log | cut -c1-200
-timeout 600 ncu --nvtx --nvtx-include "gstar::blend_fwd/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_nvtx_blend_fwd.csv python tools/profile_view.py --views 2 > gpurun_out/${T}_nvtx.log 2>&1; tail -2 gpurun_out/${T}_nvtx_blend_fwd.csv | cut -c1-300
-timeout 900 python tools/config_table.py > gpurun_out/${T}_config_table.json 2> gpurun_out/${T}_config_table.err; tail -c 1500 gpurun_out/${T}_config_table.json
+T=r2bk
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/${T}_bench_ours_2gpu.json 2> gpurun_out/${T}_bench_ours_2gpu.err; tail -c 700 gpurun_out/${T}_bench_ours_2gpu.json
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 5 --warmup 3 > gpurun_out/${T}_bench_reference_2gpu.json 2> gpurun_out/${T}_bench_reference_2gpu.err; tail -c 400 gpurun_out/${T}_bench_reference_2gpu.json
