@@ -33,8 +33,8 @@ def mesh_normal_consistency(meshes):
             has = counts > l
             pairs_a.append(start[has] + k)
             pairs_b.append(start[has] + l)
-    if not pairs_a:
-        return torch.tensor([0.0], dtype=torch.float32, device=meshes.device, requires_grad=True)
+    if not pairs_a:  # no edge with two faces: the sum over no terms, a scalar (0.7.4: `loss.sum() / N`)
+        return (verts * 0.0).sum() / N
     ia, ib = torch.cat(pairs_a), torch.cat(pairs_b)
     edges = meshes.edges_packed()[edge_of[ia]]
     v0, v1 = verts[edges[:, 0]], verts[edges[:, 1]]
@@ -59,7 +59,7 @@ def mesh_laplacian_smoothing(meshes, method: str = "uniform"):
     deg = torch.zeros(V, dtype=verts.dtype, device=verts.device).index_add(0, e0, torch.ones_like(e0, dtype=verts.dtype)).index_add(
         0, e1, torch.ones_like(e1, dtype=verts.dtype))
     nbr = torch.zeros_like(verts).index_add(0, e0, verts[e1]).index_add(0, e1, verts[e0])
-    lap = nbr / deg.clamp(min=1.0)[:, None] - verts * (deg > 0).to(verts.dtype)[:, None]
+    lap = nbr / deg.clamp(min=1.0)[:, None] - verts  # L = D^-1 A - I: the -I term also for a vertex without neighbours (its row gives -v_i)
     mesh_idx = meshes.verts_packed_to_mesh_idx()
     weights = 1.0 / meshes.num_verts_per_mesh()[mesh_idx].to(verts.dtype)
     return (lap.norm(dim=1) * weights).sum() / N

@@ -164,3 +164,21 @@ def test_camera_container_and_calibration_matrix():
     assert RasterizationSettings(image_size=(4, 5)).image_size == (4, 5)
     tv = TexturesVertex(verts_features=torch.rand(1, 7, 3))
     assert tv.verts_features_packed().shape == (7, 3)
+
+
+def test_regularisers_on_degenerate_meshes_follow_0_7_4():
+    """An isolated vertex keeps the -I row of L = D^-1 A - I (its term is ||v_i||); a mesh without an edge shared by two faces gives a
+    SCALAR zero normal-consistency loss (`loss.sum() / N`), not a one-element tensor."""
+    from pytorch3d.loss import mesh_laplacian_smoothing, mesh_normal_consistency
+    from pytorch3d.structures import Meshes
+    v = torch.tensor([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [3.0, 4.0, 0.0]], dtype=torch.float64, requires_grad=True)  # vertex 3 is in no face
+    f = torch.tensor([[0, 1, 2]])
+    m = Meshes([v], [f])
+    nc = mesh_normal_consistency(m)
+    assert nc.dim() == 0 and float(nc) == 0.0
+    nc.backward()  # differentiable (zero gradient)
+    lap = mesh_laplacian_smoothing(m)
+    # the triangle's vertices: ||mean of the two neighbours - v||; the isolated one: ||v_3|| = 5
+    tri = [((v[1] + v[2]) / 2 - v[0]).norm(), ((v[0] + v[2]) / 2 - v[1]).norm(), ((v[0] + v[1]) / 2 - v[2]).norm()]
+    want = (sum(float(t) for t in tri) + 5.0) / 4.0
+    assert abs(float(lap) - want) < 1e-12
