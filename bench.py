@@ -171,12 +171,15 @@ class OursCABI:
 
     fused_accumulate = True  # K8 adds each view's parameter gradients straight into the flat allreduce buffer
 
+    atomic = False  # several streams add into ONE flat buffer (accumulate_param_grads = 2)
+
     def fwd_bwd(self, params, cam, bg, grad_fn, flat=None):
         kw = dict(means3D=params["means3D"], viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], campos=cam["campos"], bg=bg,
                   tan_fovx=cam["tanfovx"], tan_fovy=cam["tanfovy"], shs=params["shs"], scales=params["scales"], rotations=params["rotations"],
                   sh_degree=SH_DEG)
         f = self.capi.forward(opacities=params["opacities"], W=W, H=H, **kw)
-        g = self.capi.backward(f, grad_fn(f["out_color"]), accumulate_into=flat.views if flat is not None else None, lean=True, **kw)
+        g = self.capi.backward(f, grad_fn(f["out_color"]), accumulate_into=flat.views if flat is not None else None, lean=True,
+                               atomic_accumulate=self.atomic, **kw)
         return f["num_rendered"], int(0), g
 
 
@@ -292,12 +295,16 @@ def run_gpu(args, impl_name, rank, world, local):
         torch.cuda.synchronize()
     R_sum, V_count = 0, 0
     # Our arm keeps TWO views of a step in flight on two CUDA streams (the views of a multi-view step are independent;
-    # every kernel of the library is launched on the caller's current stream).  Each stream accumulates into its own flat
-    # gradient buffer; the two are summed once per step before the single allreduce.  The reference launches on the
-    # legacy default stream and blocks on a D2H copy inside every forward, so it runs its views one after the other.
+    # every kernel of the library is launched on the caller's current stream).  Both streams add into ONE flat gradient buffer
+    # (accumulate_param_grads = 2: reductions at L2), which is all-reduced once per step; with --per-stream-buffers each stream
+    # has a buffer of its own (plain read-modify-write) and the two are summed before the allreduce, as in round 1.  The reference
+    # launches on the legacy default stream and blocks on a D2H copy inside every forward, so it runs its views one after the other.
     n_streams = max(1, args.streams) if impl.fused_accumulate else 1
     side = [torch.cuda.Stream(device) for _ in range(n_streams)] if n_streams > 1 else []
-    flats = [flat] + [gdist.FlatGrads(P, M, device) for _ in range(n_streams - 1)]
+    shared_flat = impl.fused_accumulate and n_streams > 1 and not args.per_stream_buffers
+    if impl_name == "ours":
+        impl.atomic = shared_flat
+    flats = [flat] + ([] if shared_flat else [gdist.FlatGrads(P, M, device) for _ in range(n_streams - 1)])
     fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in side]
 
     def one_view(step, i, v, timed, fl):
@@ -328,7 +335,7 @@ def run_gpu(args, impl_name, rank, world, local):
                 st.wait_event(fork)
             for i, v in enumerate(views):
                 with torch.cuda.stream(side[i % n_streams]):
-                    one_view(step, i, v, timed, flats[i % n_streams])
+                    one_view(step, i, v, timed, flats[i % len(flats)])
             for st, ev in zip(side, joins):
                 ev.record(st)
                 main.wait_event(ev)
@@ -379,8 +386,9 @@ def run_gpu(args, impl_name, rank, world, local):
         cap, cap_note = ncu_capture()
         sm_mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
         n_sms = torch.cuda.get_device_properties(device).multi_processor_count or NUM_SMS_FALLBACK
+        cap_kernels = {kn.split("::")[-1]: kv for kn, kv in (cap or {}).get("kernels", {}).items()}  # (ncu prints the namespace: gstar::k_...)
         for name, st_ in per.items():
-            k = (cap or {}).get("kernels", {}).get(kernel_of[name])
+            k = cap_kernels.get(kernel_of[name])
             st_["traffic"] = k["dram_bytes"] if k else None
             st_["warp_instructions"] = k["warp_inst"] if k else None
             st_["issue_frac"] = round(k["warp_inst"] / (st_["ms"] * 1e-3 * n_sms * 4 * sm_mhz * 1e6), 4) if k else None
@@ -403,11 +411,13 @@ def run_gpu(args, impl_name, rank, world, local):
     def measure_e2e(ns, fusion):
         """views/s through the operator API with `ns` views in flight on `ns` CUDA streams; fusion: gradient accumulation inside the
         backward kernel into the leaves' .grad (ours only; needs LEAF inputs -- GauSTAR's own call sites pass non-leaf tensors)."""
+        one_buffer = bool(fusion) and shared_flat and ns > 1  # every stream's leaves share ONE .grad buffer; the kernel adds atomically
         if impl_name == "ours":
             import gaustar_b200
-            gaustar_b200.set_grad_accumulation_fusion(bool(fusion))
+            gaustar_b200.set_grad_accumulation_fusion(bool(fusion), atomic=one_buffer)
         streams = [torch.cuda.Stream(device) for _ in range(ns)] if ns > 1 else [torch.cuda.current_stream(device)]
-        fl_set = flats[:ns] if len(flats) >= ns else flats + [gdist.FlatGrads(P, M, device) for _ in range(ns - len(flats))]
+        nbuf = 1 if one_buffer else ns
+        fl_set = flats[:nbuf] if len(flats) >= nbuf else flats + [gdist.FlatGrads(P, M, device) for _ in range(nbuf - len(flats))]
         # one set of autograd leaves per compute stream (same storage, separate .grad buffers = the per-stream flat buffers),
         # so that each stream's AccumulateGrad nodes run on that stream and never touch the other stream's buffer
         leaf_sets, m2d_sets = [], []
@@ -415,7 +425,7 @@ def run_gpu(args, impl_name, rank, world, local):
             with torch.cuda.stream(st):
                 ls = {k: base_leaves[k].detach().requires_grad_(True) for k in name_of}
                 for k, p_ in ls.items():
-                    p_.grad = fl_set[si].views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
+                    p_.grad = fl_set[si % nbuf].views[name_of[k]]  # autograd accumulates in place into the flat allreduce buffer
                 leaf_sets.append(ls)
                 m2d_sets.append(torch.zeros(P, 3, device=device, requires_grad=True))
         torch.cuda.synchronize()
@@ -604,6 +614,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (CUDA streams) in our arm")
+    ap.add_argument("--per-stream-buffers", action="store_true", help="our arm: one flat gradient buffer per stream + a merge before the allreduce (round 1) instead of "
+                    "ONE buffer that all streams add into atomically")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (skip the unfused / like-for-like e2e variants, the refine step, the CPU baselines)")
     ap.add_argument("--workload", default="headline", choices=["headline", "config3"],
                     help="headline: 1 M Gaussians at 1920x1080 (BASELINE.json's metric); config3: the same Gaussians at 1352x1014 (ActorsHQ shape)")
@@ -618,7 +630,7 @@ def main():
     wl_name = "surface-1M-1080p-sh3" if args.workload == "headline" else "config3: surface-1M-1352x1014-sh3 (160 views / 8 GPUs)"
     config = {"workload": f"{wl_name} ({VIEWS_PER_GPU} views/GPU/step, dome cameras, SuGaR-bound Gaussians, L1 upstream grad)",
               "gaussians": None, "resolution": [W, H], "sh_degree": SH_DEG, "views_per_step": VIEWS_PER_GPU * world,
-              "parallelism": f"view-sharded dp{world} + 1 allreduce/step; ours: {args.streams} views in flight on {args.streams} CUDA streams per GPU", "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
+              "parallelism": f"view-sharded dp{world} + 1 allreduce/step; ours: {args.streams} views in flight on {args.streams} CUDA streams per GPU adding into " + ("one buffer per stream, merged" if args.per_stream_buffers else "ONE flat gradient buffer (reductions at L2)"), "l2_policy": "inputs (>= 236 MB of parameters per view) exceed the 126 MB L2"}
 
     if args.impl == "reference":
         use_gpu_ref = have_gpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C.so"))

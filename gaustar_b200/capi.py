@@ -219,14 +219,15 @@ def reblend(src, colors_precomp, bg, W, H, debug=False, forward_only=False, view
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, shs=None, colors_precomp=None,
              scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=0, debug=False, accumulate_into=None, lean=False,
-             scratch=None, dL_dout_color2=None, colors2=None, bg2=None):
+             scratch=None, dL_dout_color2=None, colors2=None, bg2=None, atomic_accumulate=False):
     """gstar_raster_backward.  Returns dict of the nine gradient tensors (reference layouts).
     scratch: optional [P,12] moment buffer pre-loaded by blend_moments() calls of other passes over the same geometry (the
     per-Gaussian stage then serves all of them at once); default: a fresh zero-filled one.
     lean: do not materialise the intermediates dL_dconic and -- for inputs that were not given -- dL_dcolors / dL_dcov3D
     (NULL in the C ABI; the dict then holds empty tensors for them).
     accumulate_into: optional dict with dL_dmeans3D/dL_dscales/dL_drotations/dL_dopacity/dL_dsh tensors; the
-    parameter gradients are then ADDED to them inside the kernel (accumulate_param_grads=1).
+    parameter gradients are then ADDED to them inside the kernel (accumulate_param_grads=1; atomic_accumulate: =2, reductions at
+    L2, so that calls running concurrently on different streams may add into the same tensors).
     dL_dout_color2, colors2, bg2: backward of a two-pass forward (forward(colors2=..., bg2=...)); the dict then also holds
     dL_dcolors2 [P,3] (floats 9..11 of the moment scratch)."""
     L = lib()
@@ -257,7 +258,7 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
                 _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]), _ptr(fwd["binning"]),
                 _ptr(fwd["image"]), _ptr(dpix), _ptr(g["dL_dmeans2D"]), _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolors"]),
                 _ptr(g["dL_dmeans3D"]), _ptr(g["dL_dcov3D"]), _ptr(g["dL_dsh"]), _ptr(g["dL_dscales"]), _ptr(g["dL_drotations"]),
-                _ptr(scratch), int(debug), int(accumulate_into is not None))
+                _ptr(scratch), int(debug), (2 if atomic_accumulate else 1) if accumulate_into is not None else 0)
     if dL_dout_color2 is not None:
         keep += [_f32(dL_dout_color2, dev), _f32(bg2, dev), _f32(colors2, dev)]
         a.dL_dpix2, a.background2, a.colors2 = _ptr(keep[-3]), _ptr(keep[-2]), _ptr(keep[-1])

@@ -55,7 +55,7 @@ struct PreBwdParams {
     float* dL_dsh;
     float* dL_dscale;
     float* dL_drot;
-    int accumulate;  // += into the parameter gradients (mean3D, scale, rot, sh, opacity)
+    int accumulate;  // += into the parameter gradients (mean3D, scale, rot, sh, opacity): 1 plain read-modify-write, 2 atomic (concurrent calls)
 };
 
 struct BinParams {

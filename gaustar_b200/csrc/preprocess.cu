@@ -177,9 +177,11 @@ __device__ __forceinline__ void sh_stage_load(const ShStage& st, const float* __
     __syncwarp();
 }
 
-// coalesced shared -> global copy of the rows selected by row_mask; accumulate: global += shared
+// coalesced shared -> global copy of the rows selected by row_mask; accumulate 1: global += shared (plain read-modify-write: one
+// backward at a time per array), 2: the same with reductions at L2 (red.global.add: several backward calls on different streams
+// may add into the same array at once)
 __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restrict__ dst, int M, long long first_row, int P, unsigned row_mask,
-                                               bool accumulate)
+                                               int accumulate)
 {
     __syncwarp();
     const int lane = threadIdx.x & 31;
@@ -189,6 +191,17 @@ __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restr
         float4* b4 = reinterpret_cast<float4*>(base);
         const float4* r4 = reinterpret_cast<const float4*>(st.rows);
         float4 o[12];
+        if (accumulate == 2) {
+#pragma unroll
+            for (int it = 0; it < 12; it++) {
+                const int q = lane + 32 * it, g = q / 12, j = q - g * 12;
+                if (((row_mask >> g) & 1u) && first_row + g < P) {
+                    const float4 v = r4[g * 13 + j];
+                    red_add_v4(reinterpret_cast<float*>(b4 + q), v.x, v.y, v.z, v.w);
+                }
+            }
+            return;
+        }
         if (accumulate) {
 #pragma unroll
             for (int it = 0; it < 12; it++) {
@@ -213,6 +226,7 @@ __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restr
             const int g = q / row4, j = q - g * row4;
             if (((row_mask >> g) & 1u) && first_row + g < P) {
                 float4 v = r4[g * str4 + j];
+                if (accumulate == 2) { red_add_v4(reinterpret_cast<float*>(b4 + q), v.x, v.y, v.z, v.w); continue; }
                 if (accumulate) {
                     const float4 o = b4[q];
                     v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -225,7 +239,8 @@ __device__ __forceinline__ void sh_stage_store(const ShStage& st, float* __restr
             const int g = q / rowf, j = q - g * rowf;
             if (((row_mask >> g) & 1u) && first_row + g < P) {
                 const float v = st.rows[g * st.stride + j];
-                base[q] = accumulate ? base[q] + v : v;
+                if (accumulate == 2) atomicAdd(base + q, v);
+                else base[q] = accumulate ? base[q] + v : v;
             }
         }
     }
@@ -487,7 +502,7 @@ __global__ void k_geom_unpack(const GRec* __restrict__ recs, const GAux* __restr
 // read before the first gradient is written)
 template <bool VEC>
 __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, float3 pos, float3 campos, uint32_t clamp_bits,
-                                            float3 dL_dcolor, float3& dmean_add, float* dL_dsh, bool acc_out)
+                                            float3 dL_dcolor, float3& dmean_add, float* dL_dsh, int acc_out)
 {
     const float3 dorig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
     const float len = sqrtf(dorig.x * dorig.x + dorig.y * dorig.y + dorig.z * dorig.z);
@@ -567,7 +582,9 @@ __device__ __forceinline__ void sh_backward(int deg, int M, const float* sh, flo
             float wk = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; j++) wk = (j == k && j < ncoef) ? w[j] : wk;
-            if (acc_out) {  // direct-to-global path in accumulate mode
+            if (acc_out == 2) {  // direct-to-global path in atomic accumulate mode
+                atomicAdd(dL_dsh + 3 * k, wk * g.x); atomicAdd(dL_dsh + 3 * k + 1, wk * g.y); atomicAdd(dL_dsh + 3 * k + 2, wk * g.z);
+            } else if (acc_out) {  // direct-to-global path in accumulate mode
                 dL_dsh[3 * k] += wk * g.x; dL_dsh[3 * k + 1] += wk * g.y; dL_dsh[3 * k + 2] += wk * g.z;
             } else {
                 dL_dsh[3 * k] = wk * g.x; dL_dsh[3 * k + 1] = wk * g.y; dL_dsh[3 * k + 2] = wk * g.z;
@@ -643,7 +660,8 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
     p.dL_dmean2D[3 * i] = acc[0]; p.dL_dmean2D[3 * i + 1] = acc[1]; p.dL_dmean2D[3 * i + 2] = 0.f;
     if (p.dL_dconic) { p.dL_dconic[4 * i] = acc[2]; p.dL_dconic[4 * i + 1] = acc[3]; p.dL_dconic[4 * i + 2] = 0.f; p.dL_dconic[4 * i + 3] = acc[4]; }
     if (p.dL_dcolor) { p.dL_dcolor[3 * i] = acc[5]; p.dL_dcolor[3 * i + 1] = acc[6]; p.dL_dcolor[3 * i + 2] = acc[7]; }
-    if (p.accumulate) { if (vis) p.dL_dopacity[i] += acc[8]; } else p.dL_dopacity[i] = acc[8];
+    if (p.accumulate == 2) { if (vis) atomicAdd(p.dL_dopacity + i, acc[8]); }
+    else if (p.accumulate) { if (vis) p.dL_dopacity[i] += acc[8]; } else p.dL_dopacity[i] = acc[8];
     float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     if (vis) {
         const float mx = p.means3D[3 * i], my = p.means3D[3 * i + 1], mz = p.means3D[3 * i + 2];
@@ -715,7 +733,7 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
                                   make_float3(acc[5], acc[6], acc[7]), add, sh_out, false);
             else
                 sh_backward<false>(p.D, M, sh_in, make_float3(mx, my, mz), make_float3(p.campos[0], p.campos[1], p.campos[2]), p.recs[idx].flags,
-                                   make_float3(acc[5], acc[6], acc[7]), add, sh_out, !sh_staged && p.accumulate != 0);
+                                   make_float3(acc[5], acc[6], acc[7]), add, sh_out, sh_staged ? 0 : p.accumulate);
             dmean[0] += add.x; dmean[1] += add.y; dmean[2] += add.z;
         }
         if (p.scales) {
@@ -756,6 +774,10 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
         p.dL_dmean3D[3 * i] = dmean[0]; p.dL_dmean3D[3 * i + 1] = dmean[1]; p.dL_dmean3D[3 * i + 2] = dmean[2];
         if (p.dL_dscale) { p.dL_dscale[3 * i] = dscale[0]; p.dL_dscale[3 * i + 1] = dscale[1]; p.dL_dscale[3 * i + 2] = dscale[2]; }
         if (p.dL_drot) *reinterpret_cast<float4*>(p.dL_drot + 4 * i) = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    } else if (vis && p.accumulate == 2) {  // several backward calls may be adding into these arrays at once
+        atomicAdd(p.dL_dmean3D + 3 * i, dmean[0]); atomicAdd(p.dL_dmean3D + 3 * i + 1, dmean[1]); atomicAdd(p.dL_dmean3D + 3 * i + 2, dmean[2]);
+        if (p.dL_dscale) { atomicAdd(p.dL_dscale + 3 * i, dscale[0]); atomicAdd(p.dL_dscale + 3 * i + 1, dscale[1]); atomicAdd(p.dL_dscale + 3 * i + 2, dscale[2]); }
+        if (p.dL_drot) red_add_v4(p.dL_drot + 4 * i, drot[0], drot[1], drot[2], drot[3]);
     } else if (vis) {  // accumulate: invisible Gaussians contribute nothing and are not touched
         p.dL_dmean3D[3 * i] += dmean[0]; p.dL_dmean3D[3 * i + 1] += dmean[1]; p.dL_dmean3D[3 * i + 2] += dmean[2];
         if (p.dL_dscale) { p.dL_dscale[3 * i] += dscale[0]; p.dL_dscale[3 * i + 1] += dscale[1]; p.dL_dscale[3 * i + 2] += dscale[2]; }
@@ -772,7 +794,7 @@ __global__ void __launch_bounds__(256, 3) k_preprocess_bwd(PreBwdParams p)
     }  // valid
     if (sh_staged) {
         const unsigned rows = p.accumulate ? __ballot_sync(0xffffffffu, valid && vis) : 0xffffffffu;
-        sh_stage_store(st, p.dL_dsh, M, (long long)idx - lane, p.P, rows, p.accumulate != 0);
+        sh_stage_store(st, p.dL_dsh, M, (long long)idx - lane, p.P, rows, p.accumulate);
     }
 }
 

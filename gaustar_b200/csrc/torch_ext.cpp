@@ -183,6 +183,7 @@ std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor> ReblendGaussiansCUD
 
 struct FusedTargets {
     torch::Tensor means3D, sh, opacity, scales, rotations;
+    bool atomic = false;  // several backward calls (different streams) may be adding into these tensors at once
 };
 struct SecondPass {  // backward of a two-pass forward: the second image's upstream gradient, background and colours
     torch::Tensor dL_dout_color2, background2, colors2;
@@ -221,7 +222,7 @@ RasterizeGaussiansBackwardFusedCUDA(const torch::Tensor& background, const torch
                                     const torch::Tensor& dL_dout_color, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
                                     const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
                                     const torch::Tensor& imageBuffer, const bool debug, torch::Tensor acc_means3D, torch::Tensor acc_sh,
-                                    torch::Tensor acc_opacity, torch::Tensor acc_scales, torch::Tensor acc_rotations)
+                                    torch::Tensor acc_opacity, torch::Tensor acc_scales, torch::Tensor acc_rotations, const bool atomic)
 {
     const int P = means3D.size(0);
     const int M = sh.size(0) != 0 ? (int)sh.size(1) : 0;
@@ -231,7 +232,7 @@ RasterizeGaussiansBackwardFusedCUDA(const torch::Tensor& background, const torch
     TORCH_CHECK(ok(acc_means3D, (int64_t)P * 3) && ok(acc_opacity, P) && ok(acc_scales, (int64_t)P * 3) && ok(acc_rotations, (int64_t)P * 4) &&
                     (M == 0 || ok(acc_sh, (int64_t)P * M * 3)),
                 "gaustar_b200: fused accumulation targets must be contiguous float32 CUDA tensors of the parameters' sizes");
-    FusedTargets ft{acc_means3D, acc_sh, acc_opacity, acc_scales, acc_rotations};
+    FusedTargets ft{acc_means3D, acc_sh, acc_opacity, acc_scales, acc_rotations, atomic};
     return backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
                          tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, &ft);
 }
@@ -292,7 +293,7 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
         a.dL_dscale = dL_dscales.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
         a.blend_grad_scratch = scratch.data_ptr<float>();
         a.debug = debug ? 1 : 0;
-        a.accumulate_param_grads = fused ? 1 : 0;
+        a.accumulate_param_grads = fused ? (fused->atomic ? 2 : 1) : 0;
         a.blend_only = 0;
         torch::Tensor dpix2, bg2, col2;
         if (second) {

@@ -25,9 +25,10 @@ except ImportError as e:  # fail loudly: there is no fallback implementation
 
 
 _GRAD_FUSION = False
+_GRAD_FUSION_ATOMIC = False
 
 
-def set_grad_accumulation_fusion(enabled: bool) -> bool:
+def set_grad_accumulation_fusion(enabled: bool, atomic: bool = False) -> bool:
     """Gradient-accumulation fusion for multi-view steps (off by default; returns the previous setting).
 
     When on, and every differentiable parameter input of a call (means3D, opacities, scales, rotations, shs) is a LEAF
@@ -36,9 +37,13 @@ def set_grad_accumulation_fusion(enabled: bool) -> bool:
     instead of writing five fresh tensors that AccumulateGrad then re-reads and sums (236 MB per view at 1 M Gaussians /
     SH degree 3).  Point the ``.grad`` tensors at views of one flat buffer (``gaustar_b200.dist.FlatGrads``) and a
     multi-view step needs a single all-reduce.  Any call that does not qualify takes the ordinary path, so results are
-    the same either way; tensor hooks on those leaves are not run for fused calls."""
-    global _GRAD_FUSION
-    old, _GRAD_FUSION = _GRAD_FUSION, bool(enabled)
+    the same either way; tensor hooks on those leaves are not run for fused calls.
+
+    atomic=True: the kernel adds with reductions at L2 instead of a plain read-modify-write, so backward passes running at the
+    same time on different CUDA streams may share ONE set of ``.grad`` tensors (several sets of leaves over the same storage whose
+    ``.grad`` all point at the same buffer) -- no per-stream buffers, no merge before the all-reduce."""
+    global _GRAD_FUSION, _GRAD_FUSION_ATOMIC
+    old, _GRAD_FUSION, _GRAD_FUSION_ATOMIC = _GRAD_FUSION, bool(enabled), bool(atomic)
     return old
 
 
@@ -261,7 +266,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 and all(_fusable(t, ctx.needs_input_grad[i]) for t, i in zip(pin, (0, 2, 4, 5, 6)))):
             m3, shp, op, sc, rot = pin
             e = torch.Tensor([])
-            out = _C.rasterize_gaussians_backward_fused(*args, m3.grad, shp.grad if shp.numel() else e, op.grad, sc.grad, rot.grad)
+            out = _C.rasterize_gaussians_backward_fused(*args, m3.grad, shp.grad if shp.numel() else e, op.grad, sc.grad, rot.grad, _GRAD_FUSION_ATOMIC)
             grad_means2D, grad_colors_precomp, _go, _gm, grad_cov3Ds_precomp, _gs, _gsc, _gr = out
             return (None, grad_means2D, None, grad_colors_precomp, None, None, None, None, None)
         if rs.debug:

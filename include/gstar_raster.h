@@ -146,7 +146,10 @@ typedef struct gstar_bwd_args {
     /* Multi-view steps: if non-zero, the five PARAMETER gradients (dL_dmean3D, dL_dscale, dL_drot, dL_dsh,
      * dL_dopacity) are ACCUMULATED (+=) into the given arrays instead of overwritten -- a step's views sum
      * straight into the flat buffer that is all-reduced once per step, with no separate
-     * accumulation pass.  Invisible Gaussians are then not touched at all.  The other outputs are unaffected. */
+     * accumulation pass.  Invisible Gaussians are then not touched at all.  The other outputs are unaffected.
+     * 1: plain read-modify-write -- one backward at a time per array (calls on one stream).  2: reductions at L2
+     * (red.global.add) -- backward calls running concurrently on different streams may add into the SAME arrays, so a step that
+     * keeps several views in flight needs one gradient buffer, not one per stream plus a merge. */
     int accumulate_param_grads;
     /* Several feature passes over one geometry (gstar_raster_reblend): if non-zero, only the blend stage runs -- the nine
      * raw moments of this pass ([S, S dx, S dy, S dx2, S dxdy, S dy2] and the three colour moments = this pass's

@@ -401,6 +401,39 @@ def test_accumulate_param_grads_equals_sum_of_views():
         assert Hh.rel_err(flat.views[k].cpu(), ref.views[k].cpu()) < 1e-5, k
 
 
+@pytest.mark.parametrize("sh_degree", [3, 2, 0])
+def test_atomic_accumulate_from_two_streams_into_one_buffer(sh_degree):
+    """accumulate_param_grads=2: backward passes of different views running at the same time on two CUDA streams add into ONE flat
+    buffer with reductions at L2 (bench.py's value arm; SH rows of 48 / 27 floats take the vector / scalar store paths, degree 0
+    with colors_precomp the no-SH path) == the sum of the per-view gradients."""
+    from gaustar_b200 import dist as gdist
+    g = scene.surface_gaussians(40000, max(sh_degree, 1), seed=4)
+    cams = scene.dome_cameras(8, 320, 200)
+    P, M = g.P, (g.shs.shape[1] if sh_degree else 0)
+    flat, ref = gdist.FlatGrads(P, M, "cuda"), gdist.FlatGrads(P, M, "cuda")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    views = []
+    for ci in range(8):
+        kw = Hh.to_torch_kwargs(Hh.scene_dict(g, cams[ci], use_sh=sh_degree > 0))
+        fwd = capi.forward(**kw)
+        dpix = torch.randn(3, 200, 320, device="cuda", generator=torch.Generator("cuda").manual_seed(ci))
+        plain = capi.backward(fwd, dpix, **Hh.bwd_kwargs(kw))
+        plain = dict(plain, dL_dsh=plain["dL_dsh"] if M else torch.zeros(P, 0, 3, device="cuda"))
+        ref.accumulate(plain)
+        views.append((kw, fwd, dpix))
+    torch.cuda.synchronize()
+    for rep in range(3):  # repeated: a lost update would not show every time
+        flat.zero_()
+        torch.cuda.synchronize()
+        for i, (kw, fwd, dpix) in enumerate(views):
+            with torch.cuda.stream(streams[i & 1]):
+                capi.backward(fwd, dpix, accumulate_into=flat.views, atomic_accumulate=True, lean=True, **Hh.bwd_kwargs(kw))
+        torch.cuda.synchronize()
+        for k in gdist.GRAD_FIELDS:
+            if flat.views[k].numel():
+                assert Hh.rel_err(flat.views[k].cpu(), ref.views[k].cpu()) < 2e-5, (k, rep)
+
+
 def test_two_streams_autograd_equals_single_stream():
     """bench.py's e2e arm keeps two views in flight on two CUDA streams with one set of autograd leaves per stream
     (same storage, separate .grad buffers).  The summed gradients must equal the single-stream result."""

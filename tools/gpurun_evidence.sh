@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-T=r2bk
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/${T}_bench_ours_2gpu.json 2> gpurun_out/${T}_bench_ours_2gpu.err; tail -c 700 gpurun_out/${T}_bench_ours_2gpu.json
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 5 --warmup 3 > gpurun_out/${T}_bench_reference_2gpu.json 2> gpurun_out/${T}_bench_reference_2gpu.err; tail -c 400 gpurun_out/${T}_bench_reference_2gpu.json
+T=r2bn
+timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -q -x -k "accumulate or two_streams or fusion" > gpurun_out/${T}_pytest.txt 2>&1; tail -5 gpurun_out/${T}_pytest.txt | cut -c1-200
+timeout 600 python bench.py --quick --per-stream-buffers > gpurun_out/${T}_bench_perstream.json 2> gpurun_out/${T}_bench_perstream.err; python -c "
+import json; d=json.loads(open('gpurun_out/${T}_bench_perstream.json').read().strip().splitlines()[-1]); print('per-stream', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['stages']['preprocess_bwd'])"
+timeout 600 python bench.py --quick > gpurun_out/${T}_bench_onebuf.json 2> gpurun_out/${T}_bench_onebuf.err; python -c "
+import json; d=json.loads(open('gpurun_out/${T}_bench_onebuf.json').read().strip().splitlines()[-1]); print('one-buffer', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['stages']['preprocess_bwd'], d['roofline'].get('traffic'), d['roofline'].get('issue_frac'))"
+tail -3 gpurun_out/${T}_bench_onebuf.err
