@@ -214,3 +214,29 @@ def test_fused_headline_size():
     for k in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations"):
         assert float((gf[k] - (g1[k] + g2[k])).abs().max() / (g1[k].abs().max() + g2[k].abs().max())) < _tol(k), k
     assert Hh.rel_err(gf["dL_dcolors2"].cpu(), g2["dL_dcolors"].cpu()) < GRAD_TOL
+
+
+def test_fused_edge_cases_empty_view_and_no_gaussians():
+    """A view without a single instance (everything behind the camera): both images are their backgrounds, the backward gives zeros;
+    P == 0: the same without any launch."""
+    dev = "cuda"
+    P, W, H = 64, 56, 40
+    g = torch.Generator(dev).manual_seed(0)
+    m = torch.randn(P, 3, device=dev, generator=g)
+    m[:, 2] = -5.0  # behind the camera (view matrix = identity)
+    eye = torch.eye(4, device=dev)
+    kw = dict(means3D=m, opacities=torch.rand(P, 1, device=dev, generator=g), scales=torch.rand(P, 3, device=dev, generator=g) * 0.1,
+              rotations=torch.nn.functional.normalize(torch.randn(P, 4, device=dev, generator=g), dim=-1), colors_precomp=torch.rand(P, 3, device=dev, generator=g),
+              viewmatrix=eye, projmatrix=eye, campos=torch.zeros(3, device=dev), bg=torch.tensor([0.1, 0.2, 0.3], device=dev), tan_fovx=0.7, tan_fovy=0.5, W=W, H=H)
+    col2, bg2 = torch.rand(P, 3, device=dev, generator=g), torch.tensor([7.0, 8.0, 9.0], device=dev)
+    f = capi.forward(colors2=col2, bg2=bg2, debug=True, **kw)
+    torch.cuda.synchronize()
+    assert f["num_rendered"] == 0
+    assert torch.equal(f["out_color"], kw["bg"][:, None, None].expand(3, H, W)) and torch.equal(f["out_color2"], bg2[:, None, None].expand(3, H, W))
+    dp = torch.ones(3, H, W, device=dev)
+    gr = capi.backward(f, dp, dL_dout_color2=dp, colors2=col2, bg2=bg2, **Hh.bwd_kwargs(kw))
+    torch.cuda.synchronize()
+    assert float(gr["dL_dmeans3D"].abs().max()) == 0.0 and float(gr["dL_dcolors2"].abs().max()) == 0.0
+    kw0 = dict(kw, means3D=m[:0], opacities=kw["opacities"][:0], scales=kw["scales"][:0], rotations=kw["rotations"][:0], colors_precomp=kw["colors_precomp"][:0])
+    f0 = capi.forward(colors2=col2[:0], bg2=bg2, **kw0)
+    assert f0["num_rendered"] == 0 and float(f0["out_color2"].abs().max()) == 0.0  # the reference returns zeros for P == 0 (rasterize_points.cu:66)
