@@ -621,9 +621,15 @@ __device__ __forceinline__ void blend_fwd_body(const BlendParams& p, unsigned ch
                 if (hdr_grp >= 0) {
                     if ((uint32_t)hdr_grp < ng) fwd_group_header<NP>(sm, stage, buf, hdr_grp, cnt, slot_b0, lane, sm2, p.colors2);
                     __syncwarp();
+#ifndef GSTAR_RACECHECK_BUILD
                     if (lane == 0) mbar_arrive(&sm.hbar[buf]);
+#endif
                 }
+#ifdef GSTAR_RACECHECK_BUILD
+                __syncthreads();  // (compute-sanitizer's racecheck does not model the mbarrier hand-over below: this build lets it check the rest)
+#else
                 mbar_wait(&sm.hbar[buf], (uint32_t)(b >> 1) & 1u);
+#endif
 #ifdef GSTAR_FWD_DEBUG_TIME
                 dbg_t[0] += clock64() - dbg_c; dbg_c = clock64();
 #endif
@@ -789,9 +795,12 @@ __device__ __forceinline__ void blend_fwd_body(const BlendParams& p, unsigned ch
                     left += __popc(w[k]);
                 }
                 const uint32_t lx = (uint32_t)pid & 15u, ly = (uint32_t)pid >> 4;
-                float4 S = sm.state[pid];  // C0 C1 C2 T
+                float4 S = make_float4(0.f, 0.f, 0.f, 1.0f);  // C0 C1 C2 T
                 float4 S2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (NP == 2) S2 = sm2->state2[pid];
+                if (have) {  // (a lane without a list entry must not even read pixel 0's state: its owner may be writing it)
+                    S = sm.state[pid];
+                    if constexpr (NP == 2) S2 = sm2->state2[pid];
+                }
                 uint32_t lastr = 0xffffffffu, fin_flag = 0;
                 unsigned cw = w[0];
                 int ck = 0;

@@ -18,13 +18,15 @@ from test_parity_gpu import GRAD_TOL, SCENES
 
 pytestmark = pytest.mark.gpu
 
-# both sides of these comparisons sum with fp32 atomics in scheduling order; the tensors behind the cov3D -> scale / rotation chain
-# amplify that noise (test_parity_gpu.py: GRAD_RTOL_ELEM_CHAIN, LIVE_REF_TOL), the others meet the bound used against the oracle
-CHAIN_TOL = 1e-3
+# BOTH sides of these comparisons are fp32 sums in scheduling order (each within GRAD_TOL of the exact value: test_parity_gpu.py), so
+# two of them may differ by twice that; the tensors behind the cov3D -> scale / rotation chain amplify the noise
+# (GRAD_RTOL_ELEM_CHAIN, LIVE_REF_TOL there).  The close-up scene sits right at the single bound (3.1e-4 seen once in five runs).
+PAIR_TOL = 2 * GRAD_TOL
+CHAIN_TOL = 5 * GRAD_TOL
 
 
 def _tol(k):
-    return CHAIN_TOL if k in ("dL_dscales", "dL_drotations", "dL_dcov3D", "scales", "rotations") else GRAD_TOL
+    return CHAIN_TOL if k in ("dL_dscales", "dL_drotations", "dL_dcov3D", "scales", "rotations") else PAIR_TOL
 
 
 @pytest.fixture(autouse=True)
@@ -84,10 +86,10 @@ def test_fused_forward_and_backward_equal_two_separate_passes(name):
         err = float((gf[k] - (g1[k] + g2[k])).abs().max() / (g1[k].abs().max() + g2[k].abs().max()))
         assert err < _tol(k), (k, err)
     if "shs" in kw and kw["shs"] is not None and kw["shs"].numel():
-        assert Hh.rel_err(gf["dL_dsh"].cpu(), g1["dL_dsh"].cpu()) < GRAD_TOL
+        assert Hh.rel_err(gf["dL_dsh"].cpu(), g1["dL_dsh"].cpu()) < PAIR_TOL
     else:
-        assert Hh.rel_err(gf["dL_dcolors"].cpu(), g1["dL_dcolors"].cpu()) < GRAD_TOL
-    assert Hh.rel_err(gf["dL_dcolors2"].cpu(), g2["dL_dcolors"].cpu()) < GRAD_TOL
+        assert Hh.rel_err(gf["dL_dcolors"].cpu(), g1["dL_dcolors"].cpu()) < PAIR_TOL
+    assert Hh.rel_err(gf["dL_dcolors2"].cpu(), g2["dL_dcolors"].cpu()) < PAIR_TOL
     # the deterministic mode covers the fused kernels: same bits twice, same values as the atomic path
     old = capi.set_deterministic(True)
     try:
@@ -190,7 +192,7 @@ def test_forward_passes_without_a_hit_log_falls_back_to_the_reblend():
     for a, b in zip(imgs, imgs_ref):
         assert torch.equal(a, b)
     for k in grads_ref:
-        assert Hh.rel_err(grads[k].cpu(), grads_ref[k].cpu()) < 2 * GRAD_TOL, k
+        assert Hh.rel_err(grads[k].cpu(), grads_ref[k].cpu()) < _tol(k), k
 
 
 def test_fused_headline_size():
@@ -213,7 +215,7 @@ def test_fused_headline_size():
     torch.cuda.synchronize()
     for k in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations"):
         assert float((gf[k] - (g1[k] + g2[k])).abs().max() / (g1[k].abs().max() + g2[k].abs().max())) < _tol(k), k
-    assert Hh.rel_err(gf["dL_dcolors2"].cpu(), g2["dL_dcolors"].cpu()) < GRAD_TOL
+    assert Hh.rel_err(gf["dL_dcolors2"].cpu(), g2["dL_dcolors"].cpu()) < PAIR_TOL
 
 
 def test_fused_edge_cases_empty_view_and_no_gaussians():
