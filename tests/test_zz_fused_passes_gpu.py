@@ -242,3 +242,60 @@ def test_fused_edge_cases_empty_view_and_no_gaussians():
     kw0 = dict(kw, means3D=m[:0], opacities=kw["opacities"][:0], scales=kw["scales"][:0], rotations=kw["rotations"][:0], colors_precomp=kw["colors_precomp"][:0])
     f0 = capi.forward(colors2=col2[:0], bg2=bg2, **kw0)
     assert f0["num_rendered"] == 0 and float(f0["out_color2"].abs().max()) == 0.0  # the reference returns zeros for P == 0 (rasterize_points.cu:66)
+
+
+def test_fused_config5_shape_is_bit_identical():
+    """Config #5's shape (4 M Gaussians, 3840x2160): both images of the two-pass blend equal separate calls bit for bit (the log rows are
+    32 bytes here: 72 M slots, 2.3 GB)."""
+    g = scene.surface_gaussians(4_000_000, 3, seed=0)
+    kw = Hh.to_torch_kwargs(Hh.scene_dict(g, scene.dome_cameras(8, 3840, 2160)[1]))
+    del g
+    col2, bg2 = _second_pass(kw, 5)
+    fused = capi.forward(colors2=col2, bg2=bg2, **kw)
+    torch.cuda.synchronize()
+    need, cap, used = capi.hit_log_state(fused)
+    assert used and need <= cap
+    img1, img2 = fused["out_color"].clone(), fused["out_color2"].clone()
+    del fused
+    one = _single(kw, forward_only=True)
+    assert torch.equal(img1, one["out_color"])
+    del one
+    two = _single({k: v for k, v in kw.items() if k not in ("shs", "colors_precomp")}, colors_precomp=col2, bg=bg2, sh_degree=0, forward_only=True)
+    assert torch.equal(img2, two["out_color"])
+
+
+def test_fused_forward_is_refused_while_capturing_a_cuda_graph():
+    """The two-pass forward reads the sort's slot count back on the host: inside a stream capture it says so instead of hanging or
+    returning an image without a log (in a thread of its own: a capture is per-thread state)."""
+    import threading
+    result = {}
+
+    def body():
+        try:
+            torch.cuda.set_device(0)
+            kw = Hh.to_torch_kwargs(SCENES["surface_sh3"]())
+            col2, bg2 = _second_pass(kw, 6)
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                capi.forward(**kw)  # the thread's one-time setup and capacity provision
+                graph = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(graph, stream=s):
+                        try:
+                            capi.forward(colors2=col2, bg2=bg2, **kw)
+                            result["raised"] = False
+                        except capi.GstarError as e:
+                            result["raised"] = "capturing" in str(e)
+                        f = capi.forward(**kw)  # a single-pass forward captures fine in the same graph
+                    graph.replay()
+                    torch.cuda.synchronize()
+                    result["finite"] = bool(torch.isfinite(f["out_color"]).all())
+                except Exception as e:  # noqa: BLE001
+                    result["error"] = repr(e)
+        except Exception as e:  # noqa: BLE001
+            result["error"] = repr(e)
+
+    t = threading.Thread(target=body)
+    t.start()
+    t.join()
+    assert "error" not in result and result.get("raised") is True and result.get("finite") is True, result
