@@ -483,6 +483,28 @@ def test_two_streams_autograd_equals_single_stream():
         total = flats[0].flat + flats[1].flat
         assert Hh.rel_err(total.cpu(), ref.flat.cpu()) < 1e-4, rep
 
+    # the same with ONE buffer: both streams' leaves share their .grad tensors and the kernel adds with reductions at L2
+    # (set_grad_accumulation_fusion(True, atomic=True): what bench.py's e2e arm does)
+    import gaustar_b200
+    one = gdist.FlatGrads(g.P, 16, "cuda")
+    shared_sets = []
+    for st in streams:
+        with torch.cuda.stream(st):
+            shared_sets.append(make_leaves(one))
+    torch.cuda.synchronize()
+    old = gaustar_b200.set_grad_accumulation_fusion(True, atomic=True)
+    try:
+        for rep in range(3):
+            one.zero_()
+            torch.cuda.synchronize()
+            for i in range(4):
+                with torch.cuda.stream(streams[i & 1]):
+                    render_loss(shared_sets[i & 1], cams[i], targets[i])
+            torch.cuda.synchronize()
+            assert Hh.rel_err(one.flat.cpu(), ref.flat.cpu()) < 1e-4, rep
+    finally:
+        gaustar_b200.set_grad_accumulation_fusion(old)
+
 
 def test_grad_accumulation_fusion_matches_autograd():
     """set_grad_accumulation_fusion(True): leaves with preallocated .grad receive the views' gradients inside the kernel
