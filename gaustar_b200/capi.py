@@ -37,7 +37,7 @@ class FwdArgs(C.Structure):
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("cam_pos", C.c_void_p),
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int),
         ("out_color", C.c_void_p), ("radii", C.c_void_p), ("debug", C.c_int), ("forward_only", C.c_int),
-        ("colors2", C.c_void_p), ("background2", C.c_void_p), ("out_color2", C.c_void_p),
+        ("colors2", C.c_void_p), ("background2", C.c_void_p), ("out_color2", C.c_void_p), ("channels2", C.c_int),
     ]
 
 
@@ -55,7 +55,7 @@ class BwdArgs(C.Structure):
         ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p), ("blend_grad_scratch", C.c_void_p), ("debug", C.c_int), ("accumulate_param_grads", C.c_int),
         ("blend_only", C.c_int),
-        ("dL_dpix2", C.c_void_p), ("background2", C.c_void_p), ("colors2", C.c_void_p),
+        ("dL_dpix2", C.c_void_p), ("background2", C.c_void_p), ("colors2", C.c_void_p), ("channels2", C.c_int), ("blend_grad_scratch2", C.c_void_p),
     ]
 
 
@@ -134,6 +134,15 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
 
 
+def _pad4(t):
+    """[P,c] -> contiguous [P,4] (zeros in the unused channels): the second pass's colours are one float4 per Gaussian."""
+    if t.shape[1] == 4:
+        return t.contiguous()
+    out = torch.zeros(t.shape[0], 4, dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out
+
+
 def _f32(t, dev):
     if t is None:
         return None
@@ -162,8 +171,8 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
             forward_only=False, colors2=None, bg2=None):
     """gstar_raster_forward.  Returns dict(num_rendered, out_color, radii, geom, binning, image).
     forward_only: no backward will follow (the forward then skips the hit log).
-    colors2 [P,3], bg2 [3]: a second feature pass blended in the same kernel (gstar_fwd_args::colors2); the dict then also holds
-    out_color2 (what a call with colors_precomp=colors2, bg=bg2 renders, bit for bit)."""
+    colors2 [P,c], bg2 [c], c = 1..4: a second feature pass blended in the same kernel (gstar_fwd_args::colors2); the dict then also
+    holds out_color2 [c,H,W] (per channel what a call with that channel as colours and background renders, bit for bit)."""
     L = lib()
     dev = means3D.device
     assert dev.type == "cuda", "gaustar_b200 has no CPU path"
@@ -178,9 +187,10 @@ def forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, tan_fovx, ta
                 _ptr(vm), _ptr(pm), _ptr(cp), tan_fovx, tan_fovy, int(prefiltered), _ptr(out_color), _ptr(radii), int(debug), int(forward_only))
     out_color2 = None
     if colors2 is not None:
-        keep += [_f32(colors2, dev), _f32(bg2, dev)]
-        out_color2 = torch.empty(3, H, W, dtype=torch.float32, device=dev)
-        a.colors2, a.background2, a.out_color2 = _ptr(keep[-2]), _ptr(keep[-1]), _ptr(out_color2)
+        c2 = int(colors2.shape[1]) if P else max(int(bg2.numel()), 1)
+        keep += [_pad4(_f32(colors2, dev)), _f32(bg2, dev)]
+        out_color2 = torch.empty(c2, H, W, dtype=torch.float32, device=dev)
+        a.colors2, a.background2, a.out_color2, a.channels2 = _ptr(keep[-2]), _ptr(keep[-1]), _ptr(out_color2), c2
     with torch.cuda.device(dev):
         R = _check(L.gstar_raster_forward(C.byref(a), geom_cb, None, binning_cb, None, image_cb, None, _stream(dev)))
     if P == 0:
@@ -259,13 +269,18 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, projmatrix, campos, bg, ta
                 _ptr(fwd["image"]), _ptr(dpix), _ptr(g["dL_dmeans2D"]), _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolors"]),
                 _ptr(g["dL_dmeans3D"]), _ptr(g["dL_dcov3D"]), _ptr(g["dL_dsh"]), _ptr(g["dL_dscales"]), _ptr(g["dL_drotations"]),
                 _ptr(scratch), int(debug), (2 if atomic_accumulate else 1) if accumulate_into is not None else 0)
+    scratch2 = None
     if dL_dout_color2 is not None:
-        keep += [_f32(dL_dout_color2, dev), _f32(bg2, dev), _f32(colors2, dev)]
-        a.dL_dpix2, a.background2, a.colors2 = _ptr(keep[-3]), _ptr(keep[-2]), _ptr(keep[-1])
+        c2 = int(dL_dout_color2.shape[0])
+        keep += [_f32(dL_dout_color2, dev), _f32(bg2, dev), _pad4(_f32(colors2, dev))]
+        a.dL_dpix2, a.background2, a.colors2, a.channels2 = _ptr(keep[-3]), _ptr(keep[-2]), _ptr(keep[-1]), c2
+        if c2 == 4:
+            scratch2 = torch.zeros(P, dtype=torch.float32, device=dev)
+            a.blend_grad_scratch2 = _ptr(scratch2)
     with torch.cuda.device(dev):
         _check(L.gstar_raster_backward(C.byref(a), _stream(dev)))
     if dL_dout_color2 is not None:
-        g["dL_dcolors2"] = scratch[:, 9:12].clone()
+        g["dL_dcolors2"] = scratch[:, 9:9 + min(c2, 3)].clone() if c2 < 4 else torch.cat([scratch[:, 9:12], scratch2[:, None]], 1)
     g["_keep"] = keep + [scratch]
     return g
 

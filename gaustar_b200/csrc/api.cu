@@ -256,6 +256,8 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     const bool dual = a->colors2 != nullptr;
     if (dual != (a->background2 != nullptr) || dual != (a->out_color2 != nullptr))
         return fail(GSTAR_ERR_INVALID, "two-pass forward: colors2, background2 and out_color2 go together");
+    const int ch2 = dual ? (a->channels2 == 0 ? 3 : a->channels2) : 3;
+    if (ch2 < 1 || ch2 > 4) return fail(GSTAR_ERR_INVALID, "two-pass forward: channels2 must be 1..4");
     if (dual && !a->forward_only && !hit_log_enabled())
         return fail(GSTAR_ERR_NOLOG, "two-pass forward: the hit log is switched off (gstar_set_hit_log / GSTAR_HIT_LOG); re-blend the second pass instead");
     // CUDA-graph capture: while `stream` is being captured the forward stays entirely on the device -- no
@@ -320,7 +322,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
     bl.out_color = a->out_color; bl.final_T = (float*)(img + IL.final_T); bl.n_contrib = (uint32_t*)(img + IL.n_contrib);
     bl.dL_dpix = nullptr; bl.gacc = nullptr; bl.tile_lanes = bp.tile_lanes;
     bl.pixstate = (float4*)(img + IL.pixstate); bl.host_counts = capturing ? nullptr : ctx->host_counts_dev;
-    bl.colors2 = a->colors2; bl.bg2 = a->background2; bl.out_color2 = a->out_color2;
+    bl.colors2 = a->colors2; bl.bg2 = a->background2; bl.out_color2 = a->out_color2; bl.ch2 = ch2;
     const size_t row_bytes = dual ? 2 * sizeof(GHit) : sizeof(GHit);
     hit_log_enabled();  // (reads the environment on first use: g_hit_log_max_slots)
     const double max_slots = g_hit_log_max_slots * (double)sizeof(GHit) / (double)row_bytes;
@@ -572,7 +574,12 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
         const bool dual = a->dL_dpix2 != nullptr;
         if (dual != (a->background2 != nullptr) || dual != (a->colors2 != nullptr))
             return fail(GSTAR_ERR_INVALID, "two-pass backward: dL_dpix2, background2 and colors2 go together");
-        bl.dL_dpix2 = a->dL_dpix2; bl.bg2 = a->background2; bl.colors2 = a->colors2;
+        const int ch2 = dual ? (a->channels2 == 0 ? 3 : a->channels2) : 3;
+        if (ch2 < 1 || ch2 > 4) return fail(GSTAR_ERR_INVALID, "two-pass backward: channels2 must be 1..4");
+        if (dual && ch2 == 4 && !a->blend_grad_scratch2) return fail(GSTAR_ERR_INVALID, "two-pass backward with four channels: blend_grad_scratch2 [P] is missing");
+        if (dual && ch2 == 4 && deterministic_mode()) return fail(GSTAR_ERR_INVALID, "the deterministic backward covers up to three channels of the second pass");
+        bl.dL_dpix2 = a->dL_dpix2; bl.bg2 = a->background2; bl.colors2 = a->colors2; bl.ch2 = ch2;
+        bl.gacc2 = (dual && ch2 == 4) ? a->blend_grad_scratch2 : nullptr;
         if (deterministic_mode()) {
             // test mode: one row of moments per record, then a fixed-order sum per Gaussian (k_det_reduce); needs the hit log
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;

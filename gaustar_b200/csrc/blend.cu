@@ -132,8 +132,10 @@ __device__ __forceinline__ void produce_batch(const Ring& r, int b, int first_po
 
 // Two feature passes in one blend (NP == 2; SURVEY 8f-1 "generalise the blend to more channels"): the passes share alpha and T, so
 // the second one costs three more multiply-adds per blended pair instead of a whole K6 + K7.  Its per-Gaussian colours are
-// gathered from BlendParams::colors2 by id, its image goes to out_color2 with background bg2, a hit-log row grows from 16 to 32
-// bytes (C_rgb, T | C2_rgb, -), and the second pass's final colour per pixel lives behind the log (GHeader::off_pixstate2).
+// gathered from BlendParams::colors2 by id (a float4 per Gaussian: one 16-byte load), its image goes to out_color2 with background
+// bg2, a hit-log row grows from 16 to 32 bytes (C_rgb, T | C2_0123), and the second pass's final colour per pixel lives behind the
+// log (GHeader::off_pixstate2).  The second "pass" has up to FOUR channels (BlendParams::ch2): depth as one channel plus a normal,
+// say -- with RGB that is the seven-channel blend of SURVEY 8f-1.  Planes >= ch2 of bg2 / out_color2 / dL_dpix2 do not exist.
 __device__ __forceinline__ float4* pixstate2_of(const BlendParams& p)
 {
     return reinterpret_cast<float4*>(const_cast<unsigned char*>(p.packed) + p.hdr->off_pixstate2);
@@ -175,7 +177,7 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
     const int lx = g.px - tile_x0, ly = g.py - tile_y0;
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    float D0 = 0.f, D1 = 0.f, D2 = 0.f;  // NP == 2: the second pass's colour (same alpha, same T)
+    float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f;  // NP == 2: the second pass's colour (same alpha, same T)
     uint32_t last = 0;
     bool done = !g.inside;
 
@@ -221,7 +223,7 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                 int sl[4];
                 bool ok[4];
                 float al[4], cr_[4], cg[4], cbv[4];
-                float e0[4], e1[4], e2[4];
+                float e0[4], e1[4], e2[4], e3[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const bool have = left > 0;
@@ -245,8 +247,8 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                     cbv[u] = *reinterpret_cast<const float*>(rp + 40);             // b
                     cr_[u] = q1.z; cg[u] = q1.w;
                     if constexpr (NP == 2) {
-                        const float* c2 = p.colors2 + (size_t)(*reinterpret_cast<const uint32_t*>(rp + 36)) * 3;  // gid
-                        e0[u] = __ldg(c2); e1[u] = __ldg(c2 + 1); e2[u] = __ldg(c2 + 2);
+                        const float4 c2 = __ldg(reinterpret_cast<const float4*>(p.colors2) + *reinterpret_cast<const uint32_t*>(rp + 36));  // by gid
+                        e0[u] = c2.x; e1[u] = c2.y; e2[u] = c2.z; e3[u] = c2.w;
                     }
                     float dx, dy;
                     const float power = eval_power(q0.x, q0.y, q0.z, q0.w, q1.x, pxf, pyf, dx, dy);
@@ -267,6 +269,7 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                                 D0 = __fmaf_rn(T, __fmul_rn(al[u], e0[u]), D0);
                                 D1 = __fmaf_rn(T, __fmul_rn(al[u], e1[u]), D1);
                                 D2 = __fmaf_rn(T, __fmul_rn(al[u], e2[u]), D2);
+                                D3 = __fmaf_rn(T, __fmul_rn(al[u], e3[u]), D3);
                             }
                             if (log_on) {
                                 const uint4 tail = *reinterpret_cast<const uint4*>(buf + sl[u] * RS + 32);  // foot gid b slot
@@ -278,7 +281,7 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
                                 } else {
                                     float4* row = reinterpret_cast<float4*>(hitlog + ((size_t)tail.w + (uint32_t)((ly - f.y0) * f.w + (lx - f.x0))) * (NP * sizeof(GHit)));
                                     row[0] = make_float4(C0, C1, C2, T);
-                                    row[1] = make_float4(D0, D1, D2, 0.f);
+                                    row[1] = make_float4(D0, D1, D2, D3);
                                 }
                             }
                             T = test_T;
@@ -313,10 +316,11 @@ __device__ __forceinline__ void blend_fwd_fat_tile(const BlendParams& p, const i
         p.out_color[HW + pid] = __fmaf_rn(__ldg(p.bg + 1), T, C1);
         p.out_color[2 * HW + pid] = __fmaf_rn(__ldg(p.bg + 2), T, C2);
         if constexpr (NP == 2) {
-            if (n > 0 && log_on) pixstate2_of(p)[pid] = make_float4(D0, D1, D2, 0.f);
+            if (n > 0 && log_on) pixstate2_of(p)[pid] = make_float4(D0, D1, D2, D3);
             p.out_color2[pid] = __fmaf_rn(__ldg(p.bg2 + 0), T, D0);
-            p.out_color2[HW + pid] = __fmaf_rn(__ldg(p.bg2 + 1), T, D1);
-            p.out_color2[2 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 2), T, D2);
+            if (p.ch2 > 1) p.out_color2[HW + pid] = __fmaf_rn(__ldg(p.bg2 + 1), T, D1);
+            if (p.ch2 > 2) p.out_color2[2 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 2), T, D2);
+            if (p.ch2 > 3) p.out_color2[3 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 3), T, D3);
         }
     }
 }
@@ -427,7 +431,7 @@ struct FwdSmem {
 constexpr int FWD_DYN_SMEM = FWD_NST * FWD_NB * RS + (int)sizeof(FwdSmem) + GSTAR_FWD_SMEM_PAD;  // (the pad: occupancy experiments)
 struct FwdSmem2 {                    // NP == 2: what the second feature pass adds, behind FwdSmem
     float4 hdr2[2][FWD_NB];          // the records' second colour (gathered by id in the group header)
-    float4 state2[256];              // per pixel (C3, C4, C5, -)
+    float4 state2[256];              // per pixel (C3, C4, C5, C6)
 };
 #ifndef GSTAR_FWD2_NST
 #define GSTAR_FWD2_NST 2
@@ -495,8 +499,7 @@ __device__ __forceinline__ void fwd_group_header(FwdSmem& sm, const unsigned cha
         h.pk = (uint32_t)f.w | (light ? 0u : 32u) | ((256u + (slot - slot_b0) - (uint32_t)(f.y0 * f.w + f.x0)) << 6);
         sm.hdr[buf][ri] = h;
         if constexpr (NP == 2) {
-            const float* c2 = colors2 + (size_t)__float_as_uint(q2.y) * 3;  // by Gaussian id
-            sm2->hdr2[buf][ri] = make_float4(__ldg(c2), __ldg(c2 + 1), __ldg(c2 + 2), 0.f);
+            sm2->hdr2[buf][ri] = __ldg(reinterpret_cast<const float4*>(colors2) + __float_as_uint(q2.y));  // by Gaussian id
         }
     }
     if (lane == 0) {
@@ -855,7 +858,8 @@ __device__ __forceinline__ void blend_fwd_body(const BlendParams& p, unsigned ch
                                     const float c3 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].x), S2.x);
                                     const float c4 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].y), S2.y);
                                     const float c5 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].z), S2.z);
-                                    S2.x = upd ? c3 : S2.x; S2.y = upd ? c4 : S2.y; S2.z = upd ? c5 : S2.z;
+                                    const float c6 = __fmaf_rn(S.w, __fmul_rn(al[u], h2[u].w), S2.w);
+                                    S2.x = upd ? c3 : S2.x; S2.y = upd ? c4 : S2.y; S2.z = upd ? c5 : S2.z; S2.w = upd ? c6 : S2.w;
                                 }
                                 // (C_i, T_i): colour including the pair, transmittance in front of it
                                 if constexpr (NP == 1) {
@@ -919,6 +923,7 @@ __device__ __forceinline__ void blend_fwd_body(const BlendParams& p, unsigned ch
                                         S2.x = __fmaf_rn(S.w, __fmul_rn(al, h2.x), S2.x);
                                         S2.y = __fmaf_rn(S.w, __fmul_rn(al, h2.y), S2.y);
                                         S2.z = __fmaf_rn(S.w, __fmul_rn(al, h2.z), S2.z);
+                                        S2.w = __fmaf_rn(S.w, __fmul_rn(al, h2.w), S2.w);
                                     }
                                     if constexpr (NP == 1) {
                                         if (log_on) *reinterpret_cast<float4*>(reinterpret_cast<GHit*>(hlb) + idx) = S;
@@ -980,8 +985,9 @@ __device__ __forceinline__ void blend_fwd_body(const BlendParams& p, unsigned ch
         if constexpr (NP == 2) {
             if (n > 0 && log_on) pixstate2_of(p)[pid] = fin2;
             p.out_color2[pid] = __fmaf_rn(__ldg(p.bg2 + 0), fin.w, fin2.x);
-            p.out_color2[HW + pid] = __fmaf_rn(__ldg(p.bg2 + 1), fin.w, fin2.y);
-            p.out_color2[2 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 2), fin.w, fin2.z);
+            if (p.ch2 > 1) p.out_color2[HW + pid] = __fmaf_rn(__ldg(p.bg2 + 1), fin.w, fin2.y);
+            if (p.ch2 > 2) p.out_color2[2 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 2), fin.w, fin2.z);
+            if (p.ch2 > 3) p.out_color2[3 * HW + pid] = __fmaf_rn(__ldg(p.bg2 + 3), fin.w, fin2.w);
         }
     }
 }
@@ -1211,11 +1217,14 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
                 const float bg_dot = __ldg(p.bg + 0) * d0 + __ldg(p.bg + 1) * d1 + __ldg(p.bg + 2) * d2;
                 pv = make_float4(d0, d1, d2, st.x * d0 + st.y * d1 + st.z * d2 + st.w * bg_dot);
                 if constexpr (NP == 2) {
-                    const float d3 = p.dL_dpix2[pid], d4 = p.dL_dpix2[HW + pid], d5 = p.dL_dpix2[2 * HW + pid];
+                    const int ch2 = p.ch2;
+                    const float d3 = p.dL_dpix2[pid], d4 = ch2 > 1 ? p.dL_dpix2[HW + pid] : 0.f, d5 = ch2 > 2 ? p.dL_dpix2[2 * HW + pid] : 0.f,
+                                d6 = ch2 > 3 ? p.dL_dpix2[3 * HW + pid] : 0.f;
                     const float4 st2 = pixstate2_of(p)[pid];
-                    const float bg2_dot = __ldg(p.bg2 + 0) * d3 + __ldg(p.bg2 + 1) * d4 + __ldg(p.bg2 + 2) * d5;
-                    pv2 = make_float4(d3, d4, d5, 0.f);
-                    pv.w += st2.x * d3 + st2.y * d4 + st2.z * d5 + st.w * bg2_dot;
+                    const float bg2_dot = __ldg(p.bg2 + 0) * d3 + (ch2 > 1 ? __ldg(p.bg2 + 1) * d4 : 0.f) + (ch2 > 2 ? __ldg(p.bg2 + 2) * d5 : 0.f) +
+                                          (ch2 > 3 ? __ldg(p.bg2 + 3) * d6 : 0.f);
+                    pv2 = make_float4(d3, d4, d5, d6);
+                    pv.w += st2.x * d3 + st2.y * d4 + st2.z * d5 + st2.w * d6 + st.w * bg2_dot;
                 }
             }
         }
@@ -1252,10 +1261,10 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
         prefetch_l2(hrow + (area * NP - 1));  // the row need not start on a line boundary
         if (i + GATHER_THREADS < total) prefetch_l2(tile_packed + (size_t)(i + GATHER_THREADS) * 3);
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f;
-        float m9 = 0.f, m10 = 0.f, m11 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+        float m9 = 0.f, m10 = 0.f, m11 = 0.f, m12 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
         if constexpr (NP == 2) {
-            const float* c2 = p.colors2 + (size_t)__float_as_uint(q2.y) * 3;  // the record's second colour, by Gaussian id
-            e0 = __ldg(c2); e1 = __ldg(c2 + 1); e2 = __ldg(c2 + 2);
+            const float4 c2 = __ldg(reinterpret_cast<const float4*>(p.colors2) + __float_as_uint(q2.y));  // the record's second colour, by Gaussian id
+            e0 = c2.x; e1 = c2.y; e2 = c2.z; e3 = c2.w;
         }
         bool any = false;
         int xx = 0, pl = f.y0 * GSTAR_TILE + f.x0;
@@ -1284,9 +1293,9 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
             float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
             if constexpr (NP == 2) {
                 const float4 pv2 = s_pix2[cur_pl];
-                cdot += e0 * pv2.x + e1 * pv2.y + e2 * pv2.z;
-                behind -= hcur2.c0 * pv2.x + hcur2.c1 * pv2.y + hcur2.c2 * pv2.z;
-                m9 = fmaf(w, pv2.x, m9); m10 = fmaf(w, pv2.y, m10); m11 = fmaf(w, pv2.z, m11);
+                cdot += e0 * pv2.x + e1 * pv2.y + e2 * pv2.z + e3 * pv2.w;
+                behind -= hcur2.c0 * pv2.x + hcur2.c1 * pv2.y + hcur2.c2 * pv2.z + hcur2.T * pv2.w;  // (the row's fourth float: C6)
+                m9 = fmaf(w, pv2.x, m9); m10 = fmaf(w, pv2.y, m10); m11 = fmaf(w, pv2.z, m11); m12 = fmaf(w, pv2.w, m12);
             }
             const float dL_dalpha = h.T * cdot - behind * __frcp_rn(1.0f - alpha);
             const float sG = (q1.y * dL_dalpha) * G;
@@ -1304,8 +1313,10 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
                 float* dst = p.gacc + (size_t)__float_as_uint(q2.y) * GSTAR_GACC;
                 red_add_v4(dst, m0, m1, m2, m3);
                 red_add_v4(dst + 4, m4, m5, m6, m7);
-                if constexpr (NP == 2) red_add_v4(dst + 8, m8, m9, m10, m11);
-                else atomicAdd(dst + 8, m8);
+                if constexpr (NP == 2) {
+                    red_add_v4(dst + 8, m8, m9, m10, m11);
+                    if (p.gacc2) atomicAdd(p.gacc2 + __float_as_uint(q2.y), m12);  // the fourth channel's colour moment
+                } else atomicAdd(dst + 8, m8);
             }
         }
     }
@@ -1320,7 +1331,7 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
 #pragma unroll 1
     for (uint32_t r = 0; r < rounds; r++) {
         const uint32_t i = r * stride + ((uint32_t)tid >> lshift);
-        constexpr int NM = NP == 2 ? 12 : 9;  // moments per record
+        constexpr int NM = NP == 2 ? 13 : 9;  // moments per record
         float m[NM];
 #pragma unroll
         for (int c = 0; c < NM; c++) m[c] = 0.f;
@@ -1336,10 +1347,10 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
                 const GHit* hrow = hitlog + (size_t)__float_as_uint(q2.w) * NP;
                 const int area = f.w * f.h;
                 for (int off = q * 128; off < area * NP * (int)sizeof(GHit); off += L * 128) prefetch_l2(reinterpret_cast<const char*>(hrow) + off);
-                float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
                 if constexpr (NP == 2) {
-                    const float* c2 = p.colors2 + (size_t)gid * 3;
-                    e0 = __ldg(c2); e1 = __ldg(c2 + 1); e2 = __ldg(c2 + 2);
+                    const float4 c2 = __ldg(reinterpret_cast<const float4*>(p.colors2) + gid);
+                    e0 = c2.x; e1 = c2.y; e2 = c2.z; e3 = c2.w;
                 }
                 int xx = q, yy = 0;
                 while (xx >= f.w) { xx -= f.w; yy++; }
@@ -1371,9 +1382,9 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
                     float behind = pv.w - (h.c0 * pv.x + h.c1 * pv.y + h.c2 * pv.z);
                     if constexpr (NP == 2) {
                         const float4 pv2 = s_pix2[pl];
-                        cdot += e0 * pv2.x + e1 * pv2.y + e2 * pv2.z;
-                        behind -= h2.c0 * pv2.x + h2.c1 * pv2.y + h2.c2 * pv2.z;
-                        m[9] = fmaf(w, pv2.x, m[9]); m[10] = fmaf(w, pv2.y, m[10]); m[11] = fmaf(w, pv2.z, m[11]);
+                        cdot += e0 * pv2.x + e1 * pv2.y + e2 * pv2.z + e3 * pv2.w;
+                        behind -= h2.c0 * pv2.x + h2.c1 * pv2.y + h2.c2 * pv2.z + h2.T * pv2.w;
+                        m[9] = fmaf(w, pv2.x, m[9]); m[10] = fmaf(w, pv2.y, m[10]); m[11] = fmaf(w, pv2.z, m[11]); m[12] = fmaf(w, pv2.w, m[12]);
                     }
                     const float dL_dalpha = h.T * cdot - behind * __frcp_rn(1.0f - alpha);
                     const float sG = (q1.y * dL_dalpha) * G;
@@ -1402,8 +1413,10 @@ __device__ __forceinline__ void blend_bwd_gather_body(const BlendParams& p)
                 float* dst = p.gacc + (size_t)gid * GSTAR_GACC;
                 red_add_v4(dst, m[0], m[1], m[2], m[3]);
                 red_add_v4(dst + 4, m[4], m[5], m[6], m[7]);
-                if constexpr (NP == 2) red_add_v4(dst + 8, m[8], m[9], m[10], m[11]);
-                else atomicAdd(dst + 8, m[8]);
+                if constexpr (NP == 2) {
+                    red_add_v4(dst + 8, m[8], m[9], m[10], m[11]);
+                    if (p.gacc2) atomicAdd(p.gacc2 + gid, m[12]);
+                } else atomicAdd(dst + 8, m[8]);
             }
         }
     }

@@ -105,10 +105,12 @@ struct BlendParams {
     int P = 0;
     // two feature passes in one blend (blend.cu, NP == 2): per-Gaussian colours [P,3] and background of the second pass, its image,
     // and in the backward its upstream gradient; NULL: single pass
-    const float* colors2 = nullptr;
-    const float* bg2 = nullptr;
-    float* out_color2 = nullptr;
-    const float* dL_dpix2 = nullptr;
+    const float* colors2 = nullptr;   // [P,4] (a float4 per Gaussian; channels >= ch2 must be finite, e.g. zero)
+    const float* bg2 = nullptr;       // [ch2]
+    float* out_color2 = nullptr;      // [ch2,H,W]
+    const float* dL_dpix2 = nullptr;  // [ch2,H,W]
+    int ch2 = 3;                      // channels of the second pass (1..4)
+    float* gacc2 = nullptr;           // backward, ch2 == 4: [P] colour moment of the fourth channel (the first three: gacc slots 9..11)
 };
 
 void launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t s);

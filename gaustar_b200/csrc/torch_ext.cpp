@@ -26,6 +26,15 @@ char* resize_cb(void* user, size_t nbytes)
 
 const float* fptr(const torch::Tensor& t) { return t.numel() == 0 ? nullptr : t.data_ptr<float>(); }
 
+// [P,c] colours of a second pass -> contiguous [P,4] (one float4 per Gaussian; unused channels zero)
+torch::Tensor pad4(const torch::Tensor& t)
+{
+    if (t.size(1) == 4) return t.contiguous();
+    torch::Tensor out = torch::zeros({t.size(0), 4}, t.options());
+    out.slice(1, 0, t.size(1)).copy_(t);
+    return out;
+}
+
 torch::Tensor prep(const torch::Tensor& t, const torch::Device& dev)
 {
     if (t.numel() == 0) return t;
@@ -95,18 +104,20 @@ static std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tenso
         a.forward_only = t_forward_only ? 1 : 0;
         torch::Tensor col2, bg2;
         if (second) {
-            TORCH_CHECK(second->first.is_cuda() && second->first.dim() == 2 && second->first.size(0) == P && second->first.size(1) == 3,
-                        "gaustar_b200: the second pass needs CUDA colours of shape (P, 3)");
-            col2 = prep(second->first, dev); bg2 = prep(second->second, dev);
-            *out2 = torch::empty({3, H, W}, float_opts);
-            a.colors2 = fptr(col2); a.background2 = fptr(bg2); a.out_color2 = out2->data_ptr<float>();
+            TORCH_CHECK(second->first.is_cuda() && second->first.dim() == 2 && second->first.size(0) == P && second->first.size(1) >= 1 &&
+                            second->first.size(1) <= 4 && second->second.numel() == second->first.size(1),
+                        "gaustar_b200: the second pass needs CUDA colours of shape (P, c), c = 1..4, and a background of c values");
+            const int c2 = (int)second->first.size(1);
+            col2 = pad4(prep(second->first, dev)); bg2 = prep(second->second, dev);
+            *out2 = torch::empty({c2, H, W}, float_opts);
+            a.colors2 = fptr(col2); a.background2 = fptr(bg2); a.out_color2 = out2->data_ptr<float>(); a.channels2 = c2;
         }
         rendered = gstar_raster_forward(&a, resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer, stream);
         if (rendered == GSTAR_ERR_NOLOG) return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);  // the caller re-blends instead
         check(rendered);
     } else {
         out_color = torch::zeros({3, H, W}, float_opts);  // rasterize_points.cu:66
-        if (second) *out2 = torch::zeros({3, H, W}, float_opts);
+        if (second) *out2 = torch::zeros({second->second.numel(), H, W}, float_opts);
     }
     return std::make_tuple(rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer);
 }
@@ -185,8 +196,8 @@ struct FusedTargets {
     torch::Tensor means3D, sh, opacity, scales, rotations;
     bool atomic = false;  // several backward calls (different streams) may be adding into these tensors at once
 };
-struct SecondPass {  // backward of a two-pass forward: the second image's upstream gradient, background and colours
-    torch::Tensor dL_dout_color2, background2, colors2;
+struct SecondPass {  // backward of a two-pass forward: the second image's upstream gradient, background, colours; [P] moment scratch of a 4th channel
+    torch::Tensor dL_dout_color2, background2, colors2, scratch2;
 };
 using BwdTuple = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
 static BwdTuple backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
@@ -297,8 +308,14 @@ backward_impl(const torch::Tensor& background, const torch::Tensor& means3D, con
         a.blend_only = 0;
         torch::Tensor dpix2, bg2, col2;
         if (second) {
-            dpix2 = prep(second->dL_dout_color2, dev); bg2 = prep(second->background2, dev); col2 = prep(second->colors2, dev);
-            a.dL_dpix2 = fptr(dpix2); a.background2 = fptr(bg2); a.colors2 = fptr(col2);
+            dpix2 = prep(second->dL_dout_color2, dev); bg2 = prep(second->background2, dev); col2 = pad4(prep(second->colors2, dev));
+            a.dL_dpix2 = fptr(dpix2); a.background2 = fptr(bg2); a.colors2 = fptr(col2); a.channels2 = (int)dpix2.size(0);
+            if (a.channels2 == 4) {
+                TORCH_CHECK(second->scratch2.is_cuda() && second->scratch2.scalar_type() == torch::kFloat32 && second->scratch2.is_contiguous() &&
+                                second->scratch2.numel() == P,
+                            "gaustar_b200: a four-channel second pass needs a zeroed float32 CUDA scratch of P values for the fourth colour moment");
+                a.blend_grad_scratch2 = second->scratch2.data_ptr<float>();
+            }
         }
         check(gstar_raster_backward(&a, stream));
     }
@@ -357,8 +374,9 @@ BwdTuple RasterizeGaussiansBackwardPreloadedCUDA(const torch::Tensor& background
 }
 
 // Backward of rasterize_gaussians_dual: the 21 arguments of rasterize_gaussians_backward + the moment scratch (P x 12, zero or
-// pre-loaded by blend-only calls of further passes) + the second image's upstream gradient, background and colours.  Afterwards
-// columns 9..11 of the scratch are the second pass's dL_dcolors.
+// pre-loaded by blend-only calls of further passes) + the second image's upstream gradient (c, H, W), background (c) and colours
+// (P, c), c = 1..4, and a zeroed scratch of P floats (used iff c == 4; otherwise an empty tensor).  Afterwards columns 9..11 of the
+// scratch are the dL_dcolors of the second pass's first three channels and scratch2 that of the fourth.
 BwdTuple RasterizeGaussiansBackwardDualCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
                                             const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
                                             const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
@@ -367,11 +385,13 @@ BwdTuple RasterizeGaussiansBackwardDualCUDA(const torch::Tensor& background, con
                                             const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
                                             const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug,
                                             torch::Tensor scratch, const torch::Tensor& dL_dout_color2, const torch::Tensor& background2,
-                                            const torch::Tensor& colors2)
+                                            const torch::Tensor& colors2, torch::Tensor scratch2)
 {
     check_scratch(scratch, means3D, means3D.size(0));
-    TORCH_CHECK(dL_dout_color2.is_cuda() && dL_dout_color2.sizes() == dL_dout_color.sizes(), "gaustar_b200: the two upstream gradients must have the same shape");
-    const SecondPass sp{dL_dout_color2, background2, colors2};
+    TORCH_CHECK(dL_dout_color2.is_cuda() && dL_dout_color2.dim() == 3 && dL_dout_color2.size(1) == dL_dout_color.size(1) &&
+                    dL_dout_color2.size(2) == dL_dout_color.size(2) && dL_dout_color2.size(0) == colors2.size(1),
+                "gaustar_b200: the second upstream gradient must be (c, H, W) with c the second pass's channels");
+    const SecondPass sp{dL_dout_color2, background2, colors2, scratch2};
     return backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
                          tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, nullptr, &scratch, &sp);
 }

@@ -340,8 +340,9 @@ def set_pass_fusion(enabled: bool) -> bool:
 
 class _RasterizePasses(torch.autograd.Function):
     """ONE autograd node for several feature passes over the same Gaussians and camera (config #5: RGB through SH, depth,
-    normals): a forward that blends the main pass and the FIRST extra pass in one kernel (the passes share every pair's alpha
-    and transmittance: gstar_fwd_args::colors2), a re-blend per further (colours, background) pair, and a backward whose blend
+    normals): a forward that blends the main pass and the leading extra passes -- as many as fit FOUR channels together, e.g. depth
+    as one channel and a normal as three -- in one kernel (the passes share every pair's alpha and transmittance:
+    gstar_fwd_args::colors2), a re-blend per further (colours [P,3], background) pair, and a backward whose blend
     stage serves the two fused passes at once and whose per-Gaussian stage (cov2D / projection / SH / cov3D,
     backward.cu:144-396) runs ONCE for all passes -- the six geometric blend moments of the passes add, the three colour
     moments of an extra pass are its dL_dcolors (gstar_bwd_args.blend_only).  A view whose hit log cannot be had (switched off,
@@ -359,21 +360,33 @@ class _RasterizePasses(torch.autograd.Function):
         fwd_only = not any(ctx.needs_input_grad) and not rs.debug
         if fwd_only:
             _C.set_forward_only(True)
-        dual = False
+        dual = 0  # extra passes blended together with the main pass
+        col2 = bg2 = None
         try:
             extras, bufs = [], []
             if _PASS_FUSION and extra_colors and means3D.shape[0] > 0:
-                r = _C.rasterize_gaussians_dual(*args, extra_colors[0], extra_bgs[0])
-                dual = r[0] != _ERR_NOLOG
-                if dual:
-                    num_rendered, color, img2, radii, geomBuffer, binningBuffer, imgBuffer = r
-                    extras.append(img2)
+                nch, chans = 0, []
+                for c_k in extra_colors:  # the leading passes that fit four channels together
+                    if nch + c_k.shape[1] > 4:
+                        break
+                    nch += c_k.shape[1]
+                    chans.append(c_k.shape[1])
+                if chans:
+                    col2 = extra_colors[0] if len(chans) == 1 else torch.cat(extra_colors[:len(chans)], 1)
+                    bg2 = extra_bgs[0] if len(chans) == 1 else torch.cat([b.reshape(-1) for b in extra_bgs[:len(chans)]])
+                    r = _C.rasterize_gaussians_dual(*args, col2, bg2)
+                    if r[0] != _ERR_NOLOG:
+                        dual = len(chans)
+                        num_rendered, color, img2, radii, geomBuffer, binningBuffer, imgBuffer = r
+                        extras += list(torch.split(img2, chans, 0)) if dual > 1 else [img2]
             if not dual:
                 num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
-            for bg_k, col_k in list(zip(extra_bgs, extra_colors))[1 if dual else 0:]:
+            for bg_k, col_k in list(zip(extra_bgs, extra_colors))[dual:]:
                 if means3D.shape[0] == 0:
-                    extras.append(torch.zeros_like(color))
+                    extras.append(torch.zeros(col_k.shape[1], rs.image_height, rs.image_width, dtype=torch.float32, device=means3D.device))
                     continue
+                if col_k.shape[1] != 3:
+                    raise Exception('extra_passes: a pass that is not blended together with the first one must have 3 channels')
                 e = torch.Tensor([])  # same camera by construction: no guard
                 _, img_k, bin_k, ib_k = _C.rasterize_gaussians_reblend(bg_k, col_k, rs.image_height, rs.image_width, binningBuffer, imgBuffer,
                                                                        rs.debug, e, e, e, e)
@@ -386,9 +399,11 @@ class _RasterizePasses(torch.autograd.Function):
         ctx.num_rendered = num_rendered
         ctx.extra_bgs = tuple(extra_bgs)
         ctx.dual = dual
+        ctx.dual_chans = [c_k.shape[1] for c_k in extra_colors[:dual]]
+        ctx.dual_bg = bg2 if dual else None
         ctx.set_materialize_grads(False)  # an extra image nobody differentiated costs no backward pass
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer,
-                              extra_colors[0] if dual else torch.empty(0, device=means3D.device), *bufs)
+                              col2 if dual else torch.empty(0, device=means3D.device), *bufs)
         ctx.mark_non_differentiable(radii)
         return (color, radii, *extras)
 
@@ -399,7 +414,7 @@ class _RasterizePasses(torch.autograd.Function):
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, colors2, *bufs = ctx.saved_tensors
         P = means3D.shape[0]
         n_extra = len(ctx.extra_bgs)
-        first = 1 if ctx.dual else 0  # extra passes from here on have binning / image buffers of their own
+        first = ctx.dual  # extra passes from here on have binning / image buffers of their own
         extra_grads = [None] * n_extra
         if grad_out_color is None:
             grad_out_color = torch.zeros(3, rs.image_height, rs.image_width, dtype=torch.float32, device=means3D.device)
@@ -420,10 +435,19 @@ class _RasterizePasses(torch.autograd.Function):
                     extra_grads[k] = scratch[:, 6:9].clone()
                 scratch[:, 6:9].zero_()  # the colour moments are per pass; the geometric ones (columns 0..5) add
             if ctx.dual:
-                g2 = grad_extras[0] if grad_extras[0] is not None else torch.zeros_like(grad_out_color)
-                out = _C.rasterize_gaussians_backward_dual(*args, scratch, g2, ctx.extra_bgs[0], colors2)
-                if ctx.needs_input_grad[10]:
-                    extra_grads[0] = scratch[:, 9:12].clone()  # the second pass's colour moments
+                H, W = rs.image_height, rs.image_width
+                parts = [grad_extras[k] if grad_extras[k] is not None else torch.zeros(c, H, W, dtype=torch.float32, device=means3D.device)
+                         for k, c in enumerate(ctx.dual_chans)]
+                g2 = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+                nch = g2.shape[0]
+                scratch2 = torch.zeros(P if nch == 4 else 0, dtype=torch.float32, device=means3D.device)
+                out = _C.rasterize_gaussians_backward_dual(*args, scratch, g2, ctx.dual_bg, colors2, scratch2)
+                moments = scratch[:, 9:9 + min(nch, 3)] if nch < 4 else torch.cat([scratch[:, 9:12], scratch2[:, None]], 1)  # the fused passes' colour moments
+                off = 0
+                for k, c in enumerate(ctx.dual_chans):
+                    if ctx.needs_input_grad[10 + k]:
+                        extra_grads[k] = moments[:, off:off + c].clone()
+                    off += c
             else:
                 out = _C.rasterize_gaussians_backward_preloaded(*args, scratch)
         grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations = out
@@ -476,8 +500,11 @@ class GaussianRasterizer(nn.Module):
     def forward_passes(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
                        extra_passes=()):
         """Several feature passes over one geometry in ONE call (no counterpart in the reference).
-        The arguments of forward() describe the first pass; ``extra_passes`` is a sequence of ``(colors [P,3], bg [3])``
-        pairs, each rendered like a forward() call with ``colors_precomp=colors`` and that background.  Returns
+        The arguments of forward() describe the first pass; ``extra_passes`` is a sequence of ``(colors [P,c], bg [c])`` pairs,
+        c = 1..4, each rendered like a forward() call with ``colors_precomp=colors`` and that background.  The leading passes that
+        fit four channels together -- depth as ONE channel plus a normal, say -- are blended in the same kernel as the first pass
+        (a seven-channel blend); a pass beyond that is a re-blend and must have 3 channels, and so must every extra pass when the
+        hit log is switched off.  Returns
         ``(color, radii, [extra images])``.  Preprocess, binning and sort run once, and so does the per-Gaussian stage of
         the backward; ``means2D.grad`` receives the sum over the passes."""
         rs = self.raster_settings
@@ -485,8 +512,8 @@ class GaussianRasterizer(nn.Module):
         cols, bgs = [], []
         for col, bg in extra_passes:
             if not (isinstance(col, torch.Tensor) and col.is_cuda and col.dtype == torch.float32 and col.dim() == 2
-                    and col.shape == (means3D.shape[0], 3)):
-                raise Exception('extra_passes: colors must be float32 CUDA tensors of shape (P, 3)')
+                    and col.shape[0] == means3D.shape[0] and 1 <= col.shape[1] <= 4 and bg.numel() == col.shape[1]):
+                raise Exception('extra_passes: colors must be float32 CUDA tensors of shape (P, c), c = 1..4, with a background of c values')
             cols.append(col)
             bgs.append(bg)
         out = _RasterizePasses.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs, tuple(bgs), *cols)

@@ -87,10 +87,14 @@ typedef struct gstar_fwd_args {
      * blend of its own -- bit-identical to that second call.  All three pointers or none.  Unless forward_only is set the call
      * must end with a hit log (gstar_set_hit_log): it waits for the sort instead of the scan, grows the log and re-blends if
      * the view needs more than was provisioned, and fails with GSTAR_ERR_NOLOG when the log is switched off or capped below
-     * the need -- the caller then renders the second pass with gstar_raster_reblend.  Not available while capturing. */
-    const float* colors2;        /* [P,3] or NULL */
-    const float* background2;    /* [3] */
-    float* out_color2;           /* [3,H,W] fully written */
+     * the need -- the caller then renders the second pass with gstar_raster_reblend.  Not available while capturing.
+     * The second "pass" has channels2 = 1..4 channels (0 means 3): depth as ONE channel and a normal as three, say -- with RGB
+     * that is a seven-channel blend.  colors2 is always a float4 per Gaussian (one 16-byte gather; channels >= channels2 must be
+     * finite, e.g. zero); background2 and out_color2 have channels2 entries / planes. */
+    const float* colors2;        /* [P,4] or NULL */
+    const float* background2;    /* [channels2] */
+    float* out_color2;           /* [channels2,H,W] fully written */
+    int channels2;               /* 1..4; 0 = 3 */
 } gstar_fwd_args;
 
 /* Forward pass.  Returns num_rendered (sum of tiles touched), exactly like Rasterizer::forward.
@@ -158,12 +162,16 @@ typedef struct gstar_bwd_args {
      * dL_dcolor, zeroes them, and hands the same scratch -- now pre-loaded -- to the full backward of the last pass: the
      * per-Gaussian stage then runs ONCE for all passes.  (A scratch that is not zero on entry is simply added to.) */
     int blend_only;
-    /* Backward of a two-pass forward (gstar_fwd_args::colors2): the second image's upstream gradient [3,H,W], its background and
-     * its colours.  dL/dalpha of a pair sums both passes; the second pass's dL_dcolors (colour moments) are left in floats 9..11
-     * of every row of blend_grad_scratch, the first pass's go where they always do.  All three or none; must match the forward. */
+    /* Backward of a two-pass forward (gstar_fwd_args::colors2): the second image's upstream gradient [channels2,H,W], its
+     * background and its colours ([P,4], as in the forward).  dL/dalpha of a pair sums both passes; the second pass's dL_dcolors
+     * (colour moments) are left in floats 9..11 of every row of blend_grad_scratch -- and, for a fourth channel, ADDED into
+     * blend_grad_scratch2 [P] (caller-zeroed) -- the first pass's go where they always do.  Must match the forward.  The
+     * deterministic mode covers up to three channels. */
     const float* dL_dpix2;
     const float* background2;
     const float* colors2;
+    int channels2;               /* 1..4; 0 = 3 */
+    float* blend_grad_scratch2;  /* [P], needed iff channels2 == 4 */
 } gstar_bwd_args;
 #define GSTAR_GRAD_SCRATCH_FLOATS 12
 

@@ -299,3 +299,91 @@ def test_fused_forward_is_refused_while_capturing_a_cuda_graph():
     t.start()
     t.join()
     assert "error" not in result and result.get("raised") is True and result.get("finite") is True, result
+
+
+def test_seven_channel_blend_rgb_depth_normal():
+    """RGB + depth as ONE channel + a normal as three (config #5's RGB + depth + normal, SURVEY 8f-1 "C = 7"): the four extra channels
+    ride in the second pass.  Every channel equals, bit for bit, the matching channel of a separate three-channel call; the backward
+    equals the sum of the separate passes and returns all four colour gradients."""
+    d = SCENES["surface_sh3"]()
+    kw = Hh.to_torch_kwargs(d)
+    W, H, P = kw["W"], kw["H"], kw["means3D"].shape[0]
+    g = torch.Generator("cuda").manual_seed(11)
+    depth = torch.rand(P, 1, device="cuda", generator=g) * 6.0
+    normal = torch.nn.functional.normalize(torch.randn(P, 3, device="cuda", generator=g), dim=-1)
+    col4 = torch.cat([depth, normal], 1)
+    bg4 = torch.tensor([10.0, 0.0, 0.5, 1.0], device="cuda")
+    fused = capi.forward(colors2=col4, bg2=bg4, **kw)
+    torch.cuda.synchronize()
+    assert fused["out_color2"].shape == (4, H, W) and capi.hit_log_state(fused)[2]
+    base = {k: v for k, v in kw.items() if k not in ("shs", "colors_precomp")}
+    one = _single(kw)
+    dep = _single(base, colors_precomp=depth.expand(-1, 3).contiguous(), bg=bg4[:1].expand(3).contiguous(), sh_degree=0)
+    nrm = _single(base, colors_precomp=normal, bg=bg4[1:].contiguous(), sh_degree=0)
+    for f in (one, dep, nrm):
+        assert capi.hit_log_state(f)[2] or True
+    assert torch.equal(fused["out_color"], one["out_color"])
+    assert torch.equal(fused["out_color2"][0], dep["out_color"][0]) and torch.equal(fused["out_color2"][1:], nrm["out_color"])
+    # backward
+    dp1 = torch.randn(3, H, W, device="cuda", generator=g)
+    dp4 = torch.randn(4, H, W, device="cuda", generator=g) * 0.5
+    gf = capi.backward(fused, dp1, dL_dout_color2=dp4, colors2=col4, bg2=bg4, **Hh.bwd_kwargs(kw))
+    if not capi.hit_log_state(one)[2]:
+        one = _single(kw)
+    g1 = capi.backward(one, dp1, **Hh.bwd_kwargs(kw))
+    kd = dict(base, colors_precomp=depth.expand(-1, 3).contiguous(), bg=bg4[:1].expand(3).contiguous(), sh_degree=0)
+    dpd = torch.cat([dp4[:1], torch.zeros(2, H, W, device="cuda")], 0)  # only channel 0 of the three-channel depth render takes part
+    gd = capi.backward(dep, dpd, **Hh.bwd_kwargs(kd))
+    kn = dict(base, colors_precomp=normal, bg=bg4[1:].contiguous(), sh_degree=0)
+    gn = capi.backward(nrm, dp4[1:].contiguous(), **Hh.bwd_kwargs(kn))
+    torch.cuda.synchronize()
+    for k in ("dL_dmeans2D", "dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations"):
+        want = g1[k] + gd[k] + gn[k]
+        err = float((gf[k] - want).abs().max() / (g1[k].abs().max() + gd[k].abs().max() + gn[k].abs().max()))
+        assert err < _tol(k), (k, err)
+    assert gf["dL_dcolors2"].shape == (P, 4)
+    assert Hh.rel_err(gf["dL_dcolors2"][:, 0].cpu(), gd["dL_dcolors"][:, 0].cpu()) < PAIR_TOL
+    assert Hh.rel_err(gf["dL_dcolors2"][:, 1:].cpu(), gn["dL_dcolors"].cpu()) < PAIR_TOL
+    assert Hh.rel_err(gf["dL_dsh"].cpu(), g1["dL_dsh"].cpu()) < PAIR_TOL
+
+
+def test_forward_passes_fuses_depth_and_normal_into_one_blend():
+    """Through the operator: forward_passes(extra_passes=[(depth [P,1], bg [1]), (normal [P,3], bg [3])]) blends all seven channels
+    at once; images and gradients equal the same passes rendered one by one (depth expanded to three equal channels)."""
+    import diff_gaussian_rasterization as dgr
+    kw = Hh.to_torch_kwargs(SCENES["surface_sh3"]())
+    P, H, W = kw["means3D"].shape[0], kw["H"], kw["W"]
+    gsd = torch.Generator("cuda").manual_seed(5)
+    wts = [torch.randn(3, H, W, device="cuda", generator=gsd), torch.randn(1, H, W, device="cuda", generator=gsd), torch.randn(3, H, W, device="cuda", generator=gsd)]
+    bgd, bgn = torch.tensor([10.0], device="cuda"), torch.tensor([0.0, 0.5, 1.0], device="cuda")
+
+    def step(one_channel_depth):
+        leaves = {k: kw[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+        rs = dgr.GaussianRasterizationSettings(H, W, kw["tan_fovx"], kw["tan_fovy"], kw["bg"], 1.0, kw["viewmatrix"].view(4, 4), kw["projmatrix"].view(4, 4),
+                                               kw["sh_degree"], kw["campos"], False, False)
+        vm = kw["viewmatrix"].view(4, 4)
+        depth = (leaves["means3D"] @ vm[:3, 2] + vm[3, 2])[:, None]
+        normal = torch.nn.functional.normalize(leaves["means3D"], dim=-1)
+        if one_channel_depth:
+            passes = [(depth.contiguous(), bgd), (normal, bgn)]
+        else:
+            passes = [(depth.expand(-1, 3).contiguous(), bgd.expand(3).contiguous()), (normal, bgn)]
+        old = dgr.set_pass_fusion(one_channel_depth)
+        try:
+            img, _, extra = dgr.GaussianRasterizer(rs).forward_passes(means3D=leaves["means3D"], means2D=torch.zeros(P, 3, device="cuda", requires_grad=True),
+                                                                     opacities=leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+                                                                     rotations=leaves["rotations"], extra_passes=passes)
+        finally:
+            dgr.set_pass_fusion(old)
+        dimg = extra[0][:1]
+        ((img * wts[0]).sum() + (dimg * wts[1]).sum() + (extra[1] * wts[2]).sum()).backward()
+        torch.cuda.synchronize()
+        return [img.detach(), dimg.detach(), extra[1].detach()], {k: v.grad for k, v in leaves.items()}
+
+    step(True)
+    imgs_f, grads_f = step(True)
+    imgs_u, grads_u = step(False)
+    for a, b in zip(imgs_f, imgs_u):
+        assert torch.equal(a, b)
+    for k in grads_u:
+        assert Hh.rel_err(grads_f[k].cpu(), grads_u[k].cpu()) < _tol(k), (k, Hh.rel_err(grads_f[k].cpu(), grads_u[k].cpu()))

@@ -17,6 +17,7 @@ ap.add_argument("--precomp", action="store_true")
 ap.add_argument("--random", action="store_true")
 ap.add_argument("--no-log", action="store_true")
 ap.add_argument("--dual", action="store_true", help="two feature passes in one blend (gstar_fwd_args::colors2)")
+ap.add_argument("--ch2", type=int, default=3, help="channels of the second pass with --dual (1..4)")
 a = ap.parse_args()
 if a.no_log:
     capi.set_hit_log(0)
@@ -32,8 +33,9 @@ dpix = torch.randn(3, a.H, a.W, device="cuda") / (a.W * a.H)
 camkw = [dict(viewmatrix=t(c.viewmatrix), projmatrix=t(c.projmatrix), campos=t(c.campos), tan_fovx=c.tanfovx, tan_fovy=c.tanfovy) for c in cams]
 
 
-col2 = torch.rand(g.P, 3, device="cuda") * 5 if a.dual else None
-bg2 = torch.full((3,), 10.0, device="cuda")
+col2 = torch.rand(g.P, a.ch2, device="cuda") * 5 if a.dual else None
+bg2 = torch.full((a.ch2,), 10.0, device="cuda")
+dpix2 = torch.randn(a.ch2, a.H, a.W, device="cuda") / (a.W * a.H)
 
 
 def one(v):
@@ -41,7 +43,7 @@ def one(v):
     bk = {k: v2 for k, v2 in kw.items() if k not in ("opacities", "W", "H")}
     if a.dual:
         f = capi.forward(colors2=col2, bg2=bg2, **kw)
-        capi.backward(f, dpix, dL_dout_color2=dpix, colors2=col2, bg2=bg2, **bk)
+        capi.backward(f, dpix, dL_dout_color2=dpix2, colors2=col2, bg2=bg2, **bk)
     else:
         f = capi.forward(**kw)
         capi.backward(f, dpix, **bk)

@@ -17,6 +17,8 @@ ap.add_argument("--H", type=int, default=1080)
 ap.add_argument("--views", type=int, default=12)
 ap.add_argument("--passes", type=int, default=2, help="feature passes per view in the training step (config #5: 3 = RGB, depth, normal)")
 ap.add_argument("--out", default="")
+ap.add_argument("--depth-one-channel", action="store_true", help="forward_passes variant: depth as ONE channel (and the normal as three): all extra "
+                "channels ride in the same blend as the first pass (seven channels)")
 a = ap.parse_args()
 
 g = scene.surface_gaussians(a.P, sh_degree=3)
@@ -39,8 +41,8 @@ def step_fused(v):
     """The same step through GaussianRasterizer.forward_passes: one autograd node for all passes."""
     c = camkw[v % len(camkw)]
     p = params
-    depth = (p["means3D"] @ c["vm"][:3, 2] + c["vm"][3, 2])[:, None].expand(-1, 3)
-    passes = [(depth, bg2)]
+    depth = (p["means3D"] @ c["vm"][:3, 2] + c["vm"][3, 2])[:, None]
+    passes = [(depth.contiguous(), bg2[:1])] if a.depth_one_channel else [(depth.expand(-1, 3), bg2)]
     for _k in range(a.passes - 2):
         passes.append((torch.nn.functional.normalize(p["means3D"] - center, dim=-1), bg1))
     img, _, extra = dgr.GaussianRasterizer(settings(c, bg1, 3)).forward_passes(
