@@ -373,7 +373,7 @@ class _RasterizePasses(torch.autograd.Function):
                     chans.append(c_k.shape[1])
                 if chans:
                     col2 = extra_colors[0] if len(chans) == 1 else torch.cat(extra_colors[:len(chans)], 1)
-                    bg2 = extra_bgs[0] if len(chans) == 1 else torch.cat([b.reshape(-1) for b in extra_bgs[:len(chans)]])
+                    bg2 = torch.cat([b.reshape(-1).to(device=means3D.device, dtype=torch.float32) for b in extra_bgs[:len(chans)]])
                     r = _C.rasterize_gaussians_dual(*args, col2, bg2)
                     if r[0] != _ERR_NOLOG:
                         dual = len(chans)
