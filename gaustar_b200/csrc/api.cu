@@ -444,7 +444,7 @@ int gstar_raster_forward(const gstar_fwd_args* a, gstar_alloc_fn geom_alloc, voi
         }
         if (!overflow) {
             if (need_log && cap > 0) {  // (the event waited for above was recorded behind the sort)
-                const double need = (double)(((unsigned long long)ctx->host_counts[5] << 32) | ctx->host_counts[4]);
+                const double need = (double)(((unsigned long long)ctx->host_counts[7] << 32) | ctx->host_counts[6]);  // (k_publish_log's own words)
                 if (need > (double)log_slots) {
                     if (attempt == 2) return fail(GSTAR_ERR_INVALID, "hit-log need changed between attempts");
                     log_force = std::ceil((need * 1.25 + 65536.0) / LOG_QUANTUM) * LOG_QUANTUM;
@@ -603,6 +603,7 @@ int gstar_raster_backward(const gstar_bwd_args* a, void* stream_)
             StageScope sc(GSTAR_STAGE_BLEND_BWD, stream);
             launch_blend_bwd_gather(bl, stream);
             if (!dual) launch_blend_bwd(bl, stream);
+            else launch_poison_no_log(bl.hdr, bl.gacc, (size_t)a->P * GSTAR_GACC, stream);
         }
         STAGE_CHECK("blend_bwd");
     }

@@ -742,9 +742,11 @@ void launch_tile_scan(const BinParams& p, cudaStream_t s) { k_tile_scan<<<1, SCA
 void launch_emit(const BinParams& p, cudaStream_t s) { k_emit<<<(p.P + 255) / 256, 256, 0, s>>>(p); }
 __global__ void k_publish_log(const GHeader* hdr, volatile uint32_t* host_counts)
 {
+    // words 6..7, not the 4..5 that every blend_fwd writes when it gets there: a blend of an EARLIER call of this thread may still be
+    // running on another stream, and the host reads these right behind this kernel
     const unsigned long long need = hdr->log_cursor;
-    host_counts[4] = (uint32_t)need;
-    host_counts[5] = (uint32_t)(need >> 32);
+    host_counts[6] = (uint32_t)need;
+    host_counts[7] = (uint32_t)(need >> 32);
     __threadfence_system();
 }
 void launch_publish_log(const GHeader* hdr, volatile uint32_t* host_counts, cudaStream_t s) { k_publish_log<<<1, 1, 0, s>>>(hdr, host_counts); }

@@ -1527,6 +1527,13 @@ __global__ void __launch_bounds__(256) k_poison(const GHeader* __restrict__ hdr,
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = nan;
 }
 void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s, int any_overflow) { k_poison<<<296, 256, 0, s>>>(hdr, out, n, (uint32_t)any_overflow); }
+__global__ void __launch_bounds__(256) k_poison_no_log(const GHeader* __restrict__ hdr, float* __restrict__ gacc, size_t n)
+{
+    if (!hdr->log_overflow || hdr->overflow) return;  // the usual case: one load per thread
+    const float nan = __uint_as_float(0x7fc00000u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gacc[i] = nan;
+}
+void launch_poison_no_log(const GHeader* hdr, float* gacc, size_t n, cudaStream_t s) { k_poison_no_log<<<296, 256, 0, s>>>(hdr, gacc, n); }
 
 void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, uint32_t* dst_point_list, uint32_t R, const float* colors, GHeader* hdr,
                     int disable_log, const CameraCheck& cam, cudaStream_t s)

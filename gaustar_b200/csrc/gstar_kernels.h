@@ -122,7 +122,7 @@ void launch_geom_unpack(const GRec* recs, const GAux* aux, int P, float* depths,
 void launch_tile_scan(const BinParams& p, cudaStream_t s);
 void launch_emit(const BinParams& p, cudaStream_t s);
 void launch_tile_sort(const BinParams& p, cudaStream_t s);
-void launch_publish_log(const GHeader* hdr, volatile uint32_t* host_counts, cudaStream_t s);  // host_counts[4..5] = hit-log slots the view needs
+void launch_publish_log(const GHeader* hdr, volatile uint32_t* host_counts, cudaStream_t s);  // host_counts[6..7] = hit-log slots the view needs
 int  tile_sort_setup();  // one-time cudaFuncSetAttribute calls; returns cudaError_t
 int  preprocess_setup();
 int  blend_setup();
@@ -145,6 +145,9 @@ void launch_recolor(const unsigned char* src_packed, unsigned char* dst_packed, 
 // fills `out` with NaN if the header says the re-blend was refused on the device (overflow == 2) or, with any_overflow, if
 // the call found its instance capacity too small (a replayed CUDA graph cannot grow the buffer)
 void launch_poison(const GHeader* hdr, float* out, size_t n, cudaStream_t s, int any_overflow = 0);
+// two-pass backward: NaN into the moment scratch if the forward ended without a hit log after all (there is no walk-back kernel over
+// two passes; gstar_raster_forward guarantees the log, this makes a violated guarantee loud instead of a silent zero gradient)
+void launch_poison_no_log(const GHeader* hdr, float* gacc, size_t n, cudaStream_t s);
 
 // mesh-bound SuGaR prologue (sugar_prologue.cu).  Forward fills points / scaling / quats / opac; backward reads the
 // g_* upstream gradients (NULL: zero) and fills d_scales / d_cplx / d_dens and ACCUMULATES into d_verts (zeroed by the caller).

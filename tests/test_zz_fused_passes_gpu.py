@@ -118,6 +118,13 @@ def test_fused_forward_only_needs_no_log_and_is_bit_identical():
     two = _single(dict(kw2, colors_precomp=col2, bg=bg2, sh_degree=0), forward_only=True)
     assert not capi.hit_log_state(fused)[2]
     assert torch.equal(fused["out_color"], one["out_color"]) and torch.equal(fused["out_color2"], two["out_color"])
+    # a backward on such a forward has no log to gather from and no walk-back kernel over two passes: it says so with NaN, never with
+    # a silently empty blend gradient
+    dp = torch.ones(3, kw["H"], kw["W"], device="cuda")
+    g = capi.backward(fused, dp, dL_dout_color2=dp, colors2=col2, bg2=bg2, **Hh.bwd_kwargs(kw))
+    torch.cuda.synchronize()
+    vis = fused["radii"] > 0
+    assert torch.isnan(g["dL_dmeans3D"][vis]).all()
 
 
 def test_a_view_that_outgrows_its_log_provision_grows_it_inside_the_call():
