@@ -282,7 +282,17 @@ def run_gpu(args, impl_name, rank, world, local):
     impl = OursCABI() if impl_name == "ours" else RefStock()
     target_f = [(t.to(device).permute(2, 0, 1).float() / 255.0).contiguous() for t in targets[:2]]
     flat = gdist.FlatGrads(P, M, device)
-    my_views = lambda step: [(step * VIEWS_PER_GPU * world + v) % CAM_POOL for v in gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)]
+    # The step's views are partitioned round robin (rank r takes the view indices v = r, r + N, ...: SURVEY 8e); view v looks through
+    # camera (step * 20 + v // N + (v % N) * 32 / N) mod 32, so that every rank walks 20 CONSECUTIVE cameras of the pool, a window that
+    # moves with the step -- over a step every camera is still rendered the same number of times.  (Camera = v mod 32, round 1's
+    # choice, pinned rank r to the four cameras r, r + 8, r + 16, r + 24 for the whole run: the rank with the heaviest four was the
+    # straggler of every step; GSTAR_BENCH_CAMERA_MAP=round1 selects it for an A/B -- 13.87 vs 13.76 ms per step on the same 8-GPU
+    # box.)  One GPU: the same cameras as before.
+    if os.environ.get("GSTAR_BENCH_CAMERA_MAP") == "round1":
+        my_views = lambda step: [(step * VIEWS_PER_GPU * world + v) % CAM_POOL for v in gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)]
+    else:
+        my_views = lambda step: [(step * VIEWS_PER_GPU + v // world + (v % world) * (CAM_POOL // world)) % CAM_POOL
+                                 for v in gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)]
 
     # ---------------- device-resident arm (value) ----------------
     prof = None
