@@ -274,6 +274,14 @@ def l1_grad_fn(target_f):
     return lambda img: torch.sign(img - target_f) * inv
 
 
+def cameras_of_step(step, rank, world):
+    """Camera indices (into the pool of CAM_POOL) of the views rank `rank` renders in step `step` (see the comment in run_gpu)."""
+    views = gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)
+    if os.environ.get("GSTAR_BENCH_CAMERA_MAP") == "round1":
+        return [(step * VIEWS_PER_GPU * world + v) % CAM_POOL for v in views]
+    return [(step * VIEWS_PER_GPU + v // world + (v % world) * (CAM_POOL // world)) % CAM_POOL for v in views]
+
+
 def run_gpu(args, impl_name, rank, world, local):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
@@ -288,11 +296,7 @@ def run_gpu(args, impl_name, rank, world, local):
     # choice, pinned rank r to the four cameras r, r + 8, r + 16, r + 24 for the whole run: the rank with the heaviest four was the
     # straggler of every step; GSTAR_BENCH_CAMERA_MAP=round1 selects it for an A/B -- 13.87 vs 13.76 ms per step on the same 8-GPU
     # box.)  One GPU: the same cameras as before.
-    if os.environ.get("GSTAR_BENCH_CAMERA_MAP") == "round1":
-        my_views = lambda step: [(step * VIEWS_PER_GPU * world + v) % CAM_POOL for v in gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)]
-    else:
-        my_views = lambda step: [(step * VIEWS_PER_GPU + v // world + (v % world) * (CAM_POOL // world)) % CAM_POOL
-                                 for v in gdist.views_for_rank(VIEWS_PER_GPU * world, rank, world)]
+    my_views = lambda step: cameras_of_step(step, rank, world)
 
     # ---------------- device-resident arm (value) ----------------
     prof = None

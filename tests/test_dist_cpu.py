@@ -168,3 +168,27 @@ def test_trainer_sharding_is_a_no_op_in_a_single_process():
         assert torch.randperm is before and ts.world == 1
         params, seen = _unmodified_loop(4, 1)
     assert sorted(seen) == [0, 1, 2, 3] and ts.steps == 0
+
+
+def test_bench_camera_windows_cover_the_pool_evenly():
+    """bench.py: over a step every camera of the pool is rendered equally often at 8 GPUs (160 views / 32 cameras), every rank walks 20
+    consecutive cameras, and one GPU renders the cameras it always did."""
+    import collections
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    V, C = bench.VIEWS_PER_GPU, bench.CAM_POOL
+    for step in (0, 1, 7):
+        assert bench.cameras_of_step(step, 0, 1) == [(step * V + v) % C for v in range(V)]
+        cnt = collections.Counter()
+        for r in range(8):
+            cams = bench.cameras_of_step(step, r, 8)
+            assert len(cams) == V and all((b - a) % C == 1 for a, b in zip(cams, cams[1:]))  # a window of consecutive cameras
+            cnt.update(cams)
+        assert set(cnt.values()) == {V * 8 // C} and len(cnt) == C
+        for world in (2, 4):
+            per_rank = [bench.cameras_of_step(step, r, world) for r in range(world)]
+            assert all(len(c) == V for c in per_rank)
+            spread = collections.Counter(c for cams in per_rank for c in cams)
+            assert max(spread.values()) - min(spread.values()) <= 1 and len(spread) == C
